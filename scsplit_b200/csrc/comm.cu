@@ -1,0 +1,114 @@
+// Multi-GPU plumbing: NCCL is loaded with dlopen so the single-GPU library has no link-time dependency on it.
+// Cells are sharded across ranks; the only data-path exchange is one sum all-reduce of
+// the packed M-step statistics per iteration, issued on the context's stream between the M-step SpMM and
+// k_finalize.  The unique id travels through the host (torch.distributed broadcast in scsplit_b200/dist.py).
+#include <dlfcn.h>
+
+#include "common.cuh"
+
+namespace scs {
+
+// minimal NCCL surface (stable since NCCL 2.x); types mirrored to avoid a header dependency at build time
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+enum { ncclSuccess_ = 0 };
+enum { ncclInt64_ = 4, ncclFloat64_ = 8 };   // ncclDataType_t values
+enum { ncclSum_ = 0 };
+
+struct NcclApi {
+    void* lib = nullptr;
+    int (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    int (*CommDestroy)(ncclComm_t) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+
+static NcclApi g_nccl;
+
+static int load_nccl() {
+    if (g_nccl.lib) return 0;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) {
+        g_nccl.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (g_nccl.lib) break;
+    }
+    SCS_CHECK(g_nccl.lib, "cannot dlopen libnccl.so.2: %s", dlerror());
+    g_nccl.GetUniqueId = (decltype(g_nccl.GetUniqueId))dlsym(g_nccl.lib, "ncclGetUniqueId");
+    g_nccl.CommInitRank = (decltype(g_nccl.CommInitRank))dlsym(g_nccl.lib, "ncclCommInitRank");
+    g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))dlsym(g_nccl.lib, "ncclCommDestroy");
+    g_nccl.AllReduce = (decltype(g_nccl.AllReduce))dlsym(g_nccl.lib, "ncclAllReduce");
+    g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))dlsym(g_nccl.lib, "ncclGetErrorString");
+    SCS_CHECK(g_nccl.GetUniqueId && g_nccl.CommInitRank && g_nccl.CommDestroy && g_nccl.AllReduce, "libnccl lacks required symbols");
+    return 0;
+}
+
+#define SCS_NCCL(expr)                                                                                   \
+    do {                                                                                                 \
+        int _r = (expr);                                                                                 \
+        if (_r != 0) {                                                                                   \
+            set_error("%s failed: %s", #expr, g_nccl.GetErrorString ? g_nccl.GetErrorString(_r) : "?");  \
+            return 1;                                                                                    \
+        }                                                                                                \
+    } while (0)
+
+int comm_allreduce_f64(scs_ctx* ctx, double* buf, int64_t count) {
+    if (ctx->world <= 1) return 0;
+    SCS_NCCL(g_nccl.AllReduce(buf, buf, (size_t)count, ncclFloat64_, ncclSum_, (ncclComm_t)ctx->comm, ctx->stream));
+    return 0;
+}
+
+int comm_allreduce_i64(scs_ctx* ctx, int64_t* buf, int64_t count) {
+    if (ctx->world <= 1) return 0;
+    SCS_NCCL(g_nccl.AllReduce(buf, buf, (size_t)count, ncclInt64_, ncclSum_, (ncclComm_t)ctx->comm, ctx->stream));
+    return 0;
+}
+
+int comm_destroy(scs_ctx* ctx) {
+    if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)ctx->comm);
+    ctx->comm = nullptr;
+    ctx->world = 1;
+    ctx->rank = 0;
+    return 0;
+}
+
+int recompute_kalt(scs_ctx* ctx);   // api.cu
+
+}  // namespace scs
+
+using namespace scs;
+
+extern "C" {
+
+int scs_comm_unique_id(uint8_t id[128]) {
+    SCS_CHECK(id, "null argument");
+    SCS_TRY(load_nccl());
+    ncclUniqueId uid;
+    SCS_NCCL(g_nccl.GetUniqueId(&uid));
+    memcpy(id, uid.internal, 128);
+    return 0;
+}
+
+int scs_comm_init(scs_ctx* ctx, const uint8_t id[128], int rank, int world) {
+    SCS_CHECK(ctx && id, "null argument");
+    SCS_CHECK(world >= 1 && rank >= 0 && rank < world, "bad rank %d / world %d", rank, world);
+    SCS_CHECK(!ctx->comm, "communicator already initialised");
+    if (world == 1) return 0;
+    SCS_TRY(load_nccl());
+    SCS_CUDA(cudaSetDevice(ctx->device));
+    ncclUniqueId uid;
+    memcpy(uid.internal, id, 128);
+    ncclComm_t comm = nullptr;
+    SCS_NCCL(g_nccl.CommInitRank(&comm, world, uid, rank));
+    ctx->comm = comm;
+    ctx->rank = rank;
+    ctx->world = world;
+    // k_alt is a function of the GLOBAL per-SNV sums (scSplit:101-103): reduce the integer sums once
+    SCS_TRY(comm_allreduce_i64(ctx, ctx->sum_alt, ctx->V));
+    SCS_TRY(comm_allreduce_i64(ctx, ctx->sum_ref, ctx->V));
+    SCS_TRY(recompute_kalt(ctx));
+    SCS_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,286 @@
+// EM driver: restart-batched run_EM (scSplit:148-162) with the stop rule evaluated on the device, plus the
+// step-level E/M entry points used by the parity tests.
+#include "em_kernels.cuh"
+#include "spmm_tiled.cuh"
+
+namespace scs {
+
+// compile-time state count (padded to even) dispatch
+#define SCS_DISPATCH_KP(KP_, ...)                                     \
+    switch (KP_) {                                                    \
+        case 2: { constexpr int KPc = 2; __VA_ARGS__; } break;        \
+        case 4: { constexpr int KPc = 4; __VA_ARGS__; } break;        \
+        case 6: { constexpr int KPc = 6; __VA_ARGS__; } break;        \
+        case 8: { constexpr int KPc = 8; __VA_ARGS__; } break;        \
+        case 10: { constexpr int KPc = 10; __VA_ARGS__; } break;      \
+        case 12: { constexpr int KPc = 12; __VA_ARGS__; } break;      \
+        case 14: { constexpr int KPc = 14; __VA_ARGS__; } break;      \
+        case 16: { constexpr int KPc = 16; __VA_ARGS__; } break;      \
+        case 18: { constexpr int KPc = 18; __VA_ARGS__; } break;      \
+        case 20: { constexpr int KPc = 20; __VA_ARGS__; } break;      \
+        case 22: { constexpr int KPc = 22; __VA_ARGS__; } break;      \
+        case 24: { constexpr int KPc = 24; __VA_ARGS__; } break;      \
+        case 26: { constexpr int KPc = 26; __VA_ARGS__; } break;      \
+        case 28: { constexpr int KPc = 28; __VA_ARGS__; } break;      \
+        case 30: { constexpr int KPc = 30; __VA_ARGS__; } break;      \
+        case 32: { constexpr int KPc = 32; __VA_ARGS__; } break;      \
+        default: scs::set_error("unsupported KP=%d", KP_); return 1;  \
+    }
+
+static int timing_begin(scs_ctx* ctx, cudaEvent_t* a, cudaEvent_t* b) {
+    if (!ctx->timing || ctx->ev_pending.size() >= 8192) { *a = *b = nullptr; return 0; }
+    for (cudaEvent_t* e : {a, b}) {
+        if (!ctx->ev_pool.empty()) { *e = ctx->ev_pool.back(); ctx->ev_pool.pop_back(); }
+        else SCS_CUDA(cudaEventCreate(e));
+    }
+    SCS_CUDA(cudaEventRecord(*a, ctx->stream));
+    return 0;
+}
+static int timing_end(scs_ctx* ctx, int kind, cudaEvent_t a, cudaEvent_t b) {
+    if (!a) return 0;
+    SCS_CUDA(cudaEventRecord(b, ctx->stream));
+    ctx->ev_pending.push_back({kind, {a, b}});
+    return 0;
+}
+
+int launch_spmm(scs_ctx* ctx, int kind, int KP, int R, const double* X, int64_t x_stride, double* Y, int64_t y_stride,
+                const int32_t* done) {
+    const Stream& s = kind == 0 ? ctx->E : ctx->M;
+    cudaEvent_t ea, eb;
+    SCS_TRY(timing_begin(ctx, &ea, &eb));
+    int variant = ctx->variant;
+    if (variant == 0) variant = tiled_supported(ctx, kind, KP) ? 2 : 1;
+    if (variant == 2) {
+        SCS_TRY(launch_spmm_tiled(ctx, kind, KP, R, X, x_stride, Y, y_stride, done));
+    } else {
+        const int WPB = 8;
+        dim3 grid((unsigned)((s.nrows + WPB - 1) / WPB), (unsigned)R);
+        SCS_DISPATCH_KP(KP, {
+            if (kind == 0)
+                k_spmm_rows<KPc, 1><<<grid, WPB * 32, 0, ctx->stream>>>(s.nrows, s.lptr, s.lcode, s.hptr, s.hcode, s.hcnt, X,
+                                                                     x_stride, Y, y_stride, done);
+            else
+                k_spmm_rows<KPc, 2><<<grid, WPB * 32, 0, ctx->stream>>>(s.nrows, s.lptr, s.lcode, s.hptr, s.hcode, s.hcnt, X,
+                                                                     x_stride, Y, y_stride, done);
+        });
+        ctx->launches++;
+    }
+    SCS_TRY(timing_end(ctx, kind, ea, eb));
+    SCS_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int em_free(scs_ctx* ctx) {
+    EmState& em = ctx->em;
+    dev_free(em.T); dev_free(em.P); dev_free(em.L); dev_free(em.W); dev_free(em.stats); dev_free(em.lps);
+    dev_free(em.partial); dev_free(em.hist); dev_free(em.ll_prev); dev_free(em.iters); dev_free(em.done);
+    em = EmState();
+    return 0;
+}
+
+static int tables_from_P(scs_ctx* ctx, int r0, int nr) {
+    EmState& em = ctx->em;
+    dim3 grid((unsigned)((ctx->V * em.KP + 255) / 256), (unsigned)nr);
+    k_tables_from_P<<<grid, 256, 0, ctx->stream>>>(ctx->V, em.K, em.KP, em.P + (int64_t)r0 * ctx->V * em.KP,
+                                                   em.T + (int64_t)r0 * 2 * ctx->V * em.KP);
+    ctx->launches++;
+    SCS_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ---- the five launches of one iteration -----------------------------------------------------------------
+static int run_e(scs_ctx* ctx, const int32_t* done) {
+    EmState& em = ctx->em;
+    const int64_t V = ctx->V, N = ctx->N;
+    SCS_TRY(launch_spmm(ctx, 0, em.KP, em.R, em.T, 2 * V * em.KP, em.L, N * em.KP, done));
+    dim3 grid((unsigned)em.nblk, (unsigned)em.R);
+    SCS_DISPATCH_KP(em.KP, (k_bayes<KPc><<<grid, 256, 0, ctx->stream>>>(N, em.K, em.L, em.W, em.lps, em.partial, em.nblk, done)));
+    k_reduce_stats<<<em.R, 256, 0, ctx->stream>>>(em.KP, em.partial, em.nblk, em.stats, em.stats_stride, 2 * V * em.KP, 1, done);
+    ctx->launches += 2;
+    SCS_CUDA(cudaGetLastError());
+    return 0;
+}
+
+static int run_m(scs_ctx* ctx, const int32_t* done, int track, int check_conv) {
+    EmState& em = ctx->em;
+    const int64_t V = ctx->V, N = ctx->N;
+    SCS_TRY(launch_spmm(ctx, 1, em.KP, em.R, em.W, N * em.KP, em.stats, em.stats_stride, done));
+    if (ctx->world > 1) SCS_TRY(comm_allreduce_f64(ctx, em.stats, (int64_t)em.R * em.stats_stride));
+    dim3 grid((unsigned)((V * em.KP + 255) / 256), (unsigned)em.R);
+    k_finalize<<<grid, 256, 0, ctx->stream>>>(V, em.K, em.KP, em.stats, em.stats_stride, ctx->kalt, em.P, em.T, done);
+    k_update_prior<<<em.R, 32, 0, ctx->stream>>>(em.K, em.KP, em.stats, em.stats_stride, 2 * V * em.KP, em.lps, em.hist,
+                                                 em.max_iter, em.ll_prev, em.iters, em.done, track, check_conv);
+    ctx->launches += 2;
+    SCS_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace scs
+
+using namespace scs;
+
+extern "C" {
+
+int scs_em_end(scs_ctx* ctx) {
+    SCS_CHECK(ctx, "null context");
+    SCS_CUDA(cudaSetDevice(ctx->device));
+    return em_free(ctx);
+}
+
+int scs_em_begin(scs_ctx* ctx, int R, int K, const double* P0, int max_iter) {
+    SCS_CHECK(ctx, "null context");
+    SCS_CHECK(R >= 1, "R must be >= 1");
+    SCS_CHECK(K >= 1 && K <= SCS_MAX_K, "K must be in [1, %d] (got %d)", SCS_MAX_K, K);
+    SCS_CHECK(max_iter >= 1, "max_iter must be >= 1");
+    SCS_CHECK(P0, "P0 is null");
+    SCS_CUDA(cudaSetDevice(ctx->device));
+    em_free(ctx);
+    EmState& em = ctx->em;
+    const int64_t V = ctx->V, N = ctx->N;
+    em.R = R; em.K = K; em.KP = round_even(K); em.max_iter = max_iter;
+    const int KP = em.KP;
+    em.stats_stride = 2 * V * KP + KP + 2;
+    em.nblk = (int)((N + 255) / 256);
+    SCS_TRY(dev_alloc(ctx, &em.T, (int64_t)R * 2 * V * KP));
+    SCS_TRY(dev_alloc(ctx, &em.P, (int64_t)R * V * KP));
+    SCS_TRY(dev_alloc(ctx, &em.L, (int64_t)R * N * KP));
+    SCS_TRY(dev_alloc(ctx, &em.W, (int64_t)R * N * KP));
+    SCS_TRY(dev_alloc(ctx, &em.stats, (int64_t)R * em.stats_stride));
+    SCS_TRY(dev_alloc(ctx, &em.lps, (int64_t)R * KP));
+    SCS_TRY(dev_alloc(ctx, &em.partial, (int64_t)R * em.nblk * (KP + 1)));
+    SCS_TRY(dev_alloc(ctx, &em.hist, (int64_t)R * max_iter));
+    SCS_TRY(dev_alloc(ctx, &em.ll_prev, R));
+    SCS_TRY(dev_alloc(ctx, &em.iters, R));
+    SCS_TRY(dev_alloc(ctx, &em.done, R));
+    cudaStream_t st = ctx->stream;
+    SCS_CUDA(cudaMemsetAsync(em.P, 0, (size_t)R * V * KP * 8, st));
+    SCS_CUDA(cudaMemsetAsync(em.W, 0, (size_t)R * N * KP * 8, st));
+    SCS_CUDA(cudaMemsetAsync(em.L, 0, (size_t)R * N * KP * 8, st));
+    SCS_CUDA(cudaMemsetAsync(em.stats, 0, (size_t)R * em.stats_stride * 8, st));
+    SCS_CUDA(cudaMemsetAsync(em.hist, 0, (size_t)R * max_iter * 8, st));
+    SCS_CUDA(cudaMemsetAsync(em.iters, 0, (size_t)R * 4, st));
+    SCS_CUDA(cudaMemsetAsync(em.done, 0, (size_t)R * 4, st));
+    SCS_CUDA(cudaMemcpy2DAsync(em.P, (size_t)KP * 8, P0, (size_t)K * 8, (size_t)K * 8, (size_t)R * V, cudaMemcpyHostToDevice, st));
+    // lP_s = [log2(1/K)] * K (scSplit:91); sum_log_likelihood = [1, 2] (scSplit:155) -> previous LL = 2
+    std::vector<double> h_lps((size_t)R * KP, 0.0), h_prev((size_t)R, 2.0);
+    const double l0 = log2(1.0 / (double)K);
+    for (int r = 0; r < R; ++r)
+        for (int k = 0; k < K; ++k) h_lps[(size_t)r * KP + k] = l0;
+    SCS_CUDA(cudaMemcpyAsync(em.lps, h_lps.data(), h_lps.size() * 8, cudaMemcpyHostToDevice, st));
+    SCS_CUDA(cudaMemcpyAsync(em.ll_prev, h_prev.data(), h_prev.size() * 8, cudaMemcpyHostToDevice, st));
+    SCS_TRY(tables_from_P(ctx, 0, R));
+    SCS_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int scs_estep(scs_ctx* ctx) {
+    SCS_CHECK(ctx && ctx->em.R, "EM state not initialised (call scs_em_begin)");
+    SCS_CUDA(cudaSetDevice(ctx->device));
+    SCS_TRY(run_e(ctx, nullptr));
+    SCS_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int scs_mstep(scs_ctx* ctx) {
+    SCS_CHECK(ctx && ctx->em.R, "EM state not initialised (call scs_em_begin)");
+    SCS_CUDA(cudaSetDevice(ctx->device));
+    EmState& em = ctx->em;
+    // column mass of whatever W currently holds (it may have been injected with scs_em_set)
+    dim3 grid((unsigned)em.nblk, (unsigned)em.R);
+    SCS_DISPATCH_KP(em.KP, (k_colsum_partial<KPc><<<grid, 256, 0, ctx->stream>>>(ctx->N, em.W, em.partial, em.nblk)));
+    k_reduce_stats<<<em.R, 256, 0, ctx->stream>>>(em.KP, em.partial, em.nblk, em.stats, em.stats_stride, 2 * ctx->V * em.KP, 0, nullptr);
+    ctx->launches += 2;
+    SCS_TRY(run_m(ctx, nullptr, 0, 0));
+    SCS_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int scs_em_iterate(scs_ctx* ctx, int n_iter, int check_conv) {
+    SCS_CHECK(ctx && ctx->em.R, "EM state not initialised (call scs_em_begin)");
+    SCS_CUDA(cudaSetDevice(ctx->device));
+    EmState& em = ctx->em;
+    const int32_t* done = check_conv ? em.done : nullptr;
+    std::vector<int32_t> h_done((size_t)em.R);
+    const int POLL = 8;   // iterations between host polls of the device-side convergence flags
+    for (int i = 0; i < n_iter; ++i) {
+        SCS_TRY(run_e(ctx, done));
+        SCS_TRY(run_m(ctx, done, 1, check_conv));
+        if (check_conv && ((i + 1) % POLL == 0 || i + 1 == n_iter)) {
+            SCS_CUDA(cudaMemcpyAsync(h_done.data(), em.done, (size_t)em.R * 4, cudaMemcpyDeviceToHost, ctx->stream));
+            SCS_CUDA(cudaStreamSynchronize(ctx->stream));
+            bool all = true;
+            for (int32_t d : h_done) all = all && d;
+            if (all) break;
+        }
+    }
+    SCS_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int scs_em_run(scs_ctx* ctx) {
+    SCS_CHECK(ctx && ctx->em.R, "EM state not initialised (call scs_em_begin)");
+    return scs_em_iterate(ctx, ctx->em.max_iter, 1);
+}
+
+int scs_em_status(scs_ctx* ctx, int32_t* iters, int32_t* converged, double* ll) {
+    SCS_CHECK(ctx && ctx->em.R, "EM state not initialised (call scs_em_begin)");
+    SCS_CUDA(cudaSetDevice(ctx->device));
+    EmState& em = ctx->em;
+    std::vector<int32_t> it((size_t)em.R);
+    SCS_CUDA(cudaMemcpyAsync(it.data(), em.iters, (size_t)em.R * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    SCS_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int r = 0; r < em.R; ++r) {
+        if (iters) iters[r] = it[r];
+        if (converged) converged[r] = it[r] < em.max_iter ? 1 : 0;   // scSplit:162
+    }
+    if (ll) SCS_CUDA(cudaMemcpyAsync(ll, em.ll_prev, (size_t)em.R * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    SCS_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int scs_em_get(scs_ctx* ctx, int restart, int what, double* out) {
+    SCS_CHECK(ctx && ctx->em.R, "EM state not initialised (call scs_em_begin)");
+    EmState& em = ctx->em;
+    SCS_CHECK(restart >= 0 && restart < em.R, "restart %d out of range", restart);
+    SCS_CHECK(out, "null output");
+    SCS_CUDA(cudaSetDevice(ctx->device));
+    const int64_t V = ctx->V, N = ctx->N;
+    const int K = em.K, KP = em.KP;
+    SCS_CUDA(cudaStreamSynchronize(ctx->stream));
+    switch (what) {
+        case SCS_P: SCS_CUDA(cudaMemcpy2DAsync(out, (size_t)K * 8, em.P + (int64_t)restart * V * KP, (size_t)KP * 8, (size_t)K * 8, (size_t)V, cudaMemcpyDeviceToHost, ctx->stream)); break;
+        case SCS_W: SCS_CUDA(cudaMemcpy2DAsync(out, (size_t)K * 8, em.W + (int64_t)restart * N * KP, (size_t)KP * 8, (size_t)K * 8, (size_t)N, cudaMemcpyDeviceToHost, ctx->stream)); break;
+        case SCS_L: SCS_CUDA(cudaMemcpy2DAsync(out, (size_t)K * 8, em.L + (int64_t)restart * N * KP, (size_t)KP * 8, (size_t)K * 8, (size_t)N, cudaMemcpyDeviceToHost, ctx->stream)); break;
+        case SCS_LPS: SCS_CUDA(cudaMemcpyAsync(out, em.lps + (int64_t)restart * KP, (size_t)K * 8, cudaMemcpyDeviceToHost, ctx->stream)); break;
+        case SCS_LLHIST: SCS_CUDA(cudaMemcpyAsync(out, em.hist + (int64_t)restart * em.max_iter, (size_t)em.max_iter * 8, cudaMemcpyDeviceToHost, ctx->stream)); break;
+        case SCS_STATS: SCS_CUDA(cudaMemcpyAsync(out, em.stats + (int64_t)restart * em.stats_stride, (size_t)em.stats_stride * 8, cudaMemcpyDeviceToHost, ctx->stream)); break;
+        default: SCS_CHECK(false, "unknown array id %d", what);
+    }
+    SCS_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int scs_em_set(scs_ctx* ctx, int restart, int what, const double* in) {
+    SCS_CHECK(ctx && ctx->em.R, "EM state not initialised (call scs_em_begin)");
+    EmState& em = ctx->em;
+    SCS_CHECK(restart >= 0 && restart < em.R, "restart %d out of range", restart);
+    SCS_CHECK(in, "null input");
+    SCS_CUDA(cudaSetDevice(ctx->device));
+    const int64_t V = ctx->V, N = ctx->N;
+    const int K = em.K, KP = em.KP;
+    SCS_CUDA(cudaStreamSynchronize(ctx->stream));
+    switch (what) {
+        case SCS_P:
+            SCS_CUDA(cudaMemcpy2DAsync(em.P + (int64_t)restart * V * KP, (size_t)KP * 8, in, (size_t)K * 8, (size_t)K * 8, (size_t)V, cudaMemcpyHostToDevice, ctx->stream));
+            SCS_TRY(tables_from_P(ctx, restart, 1));
+            break;
+        case SCS_W: SCS_CUDA(cudaMemcpy2DAsync(em.W + (int64_t)restart * N * KP, (size_t)KP * 8, in, (size_t)K * 8, (size_t)K * 8, (size_t)N, cudaMemcpyHostToDevice, ctx->stream)); break;
+        case SCS_L: SCS_CUDA(cudaMemcpy2DAsync(em.L + (int64_t)restart * N * KP, (size_t)KP * 8, in, (size_t)K * 8, (size_t)K * 8, (size_t)N, cudaMemcpyHostToDevice, ctx->stream)); break;
+        case SCS_LPS: SCS_CUDA(cudaMemcpyAsync(em.lps + (int64_t)restart * KP, in, (size_t)K * 8, cudaMemcpyHostToDevice, ctx->stream)); break;
+        default: SCS_CHECK(false, "array id %d cannot be set", what);
+    }
+    SCS_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,282 @@
+// EM kernels of the scSplit hot path (sm_100a).  See DESIGN.md for the roofline of each.
+//
+//   k_spmm_rows     Y[row,:] = sum_{count-1 entries} X[g(code),:] + sum_{count>1 entries} cnt * X[g(code),:]
+//                   E-step:  rows = cells,        X = log table T[2V][KP],  Y = L[N][KP]      (scSplit:175-178)
+//                   M-step:  rows = 2V pseudo-rows, X = W[N][KP],           Y = S[2V][KP]     (scSplit:196)
+//   k_bayes         W, per-cell LL, fixed-order block partials of column mass and LL           (scSplit:181-188)
+//   k_reduce_stats  block partials -> colsum[K], LL                                            (scSplit:188,198)
+//   k_finalize      S, k_alt -> P, log2 P, log2(1-P)                                            (scSplit:196, 176-177)
+//   k_update_prior  colsum -> lP_s; LL history; bitwise stop rule                               (scSplit:198, 156-161)
+#pragma once
+#include "common.cuh"
+
+namespace scs {
+
+__device__ __forceinline__ double2 ldg2(const double* p) { return __ldg(reinterpret_cast<const double2*>(p)); }
+
+// ---------------------------------------------------------------------------------------------------------
+// v1: one warp per row, lanes stride over the row's entries, gathers straight from global memory (L1/L2).
+// ---------------------------------------------------------------------------------------------------------
+template <int KP, int SHIFT>
+__global__ void __launch_bounds__(256) k_spmm_rows(int64_t nrows, const int64_t* __restrict__ lptr,
+                                                   const uint32_t* __restrict__ lcode, const int64_t* __restrict__ hptr,
+                                                   const uint32_t* __restrict__ hcode, const int32_t* __restrict__ hcnt,
+                                                   const double* __restrict__ X, int64_t x_stride, double* __restrict__ Y,
+                                                   int64_t y_stride, const int32_t* __restrict__ done) {
+    const int r = blockIdx.y;
+    if (done && done[r]) return;
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= nrows) return;
+    X += (int64_t)r * x_stride;
+    Y += (int64_t)r * y_stride;
+    double acc[KP];
+#pragma unroll
+    for (int k = 0; k < KP; ++k) acc[k] = 0.0;
+
+    const int64_t lb = lptr[row], le = lptr[row + 1];
+    int64_t e = lb + lane;
+    for (; e + 32 < le; e += 64) {  // two independent gathers in flight per lane
+        const uint32_t c0 = __ldg(lcode + e), c1 = __ldg(lcode + e + 32);
+        const double* x0 = X + (int64_t)(c0 >> SHIFT) * KP;
+        const double* x1 = X + (int64_t)(c1 >> SHIFT) * KP;
+        double2 t0[KP / 2], t1[KP / 2];
+#pragma unroll
+        for (int j = 0; j < KP / 2; ++j) { t0[j] = ldg2(x0 + 2 * j); t1[j] = ldg2(x1 + 2 * j); }
+#pragma unroll
+        for (int j = 0; j < KP / 2; ++j) {
+            acc[2 * j] += t0[j].x; acc[2 * j + 1] += t0[j].y;
+            acc[2 * j] += t1[j].x; acc[2 * j + 1] += t1[j].y;
+        }
+    }
+    if (e < le) {
+        const uint32_t c0 = __ldg(lcode + e);
+        const double* x0 = X + (int64_t)(c0 >> SHIFT) * KP;
+#pragma unroll
+        for (int j = 0; j < KP / 2; ++j) { double2 t = ldg2(x0 + 2 * j); acc[2 * j] += t.x; acc[2 * j + 1] += t.y; }
+    }
+    const int64_t hb = hptr[row], he = hptr[row + 1];
+    for (int64_t h = hb + lane; h < he; h += 32) {
+        const uint32_t c0 = __ldg(hcode + h);
+        const double cnt = (double)__ldg(hcnt + h);
+        const double* x0 = X + (int64_t)(c0 >> SHIFT) * KP;
+#pragma unroll
+        for (int j = 0; j < KP / 2; ++j) {
+            double2 t = ldg2(x0 + 2 * j);
+            acc[2 * j] += cnt * t.x;       // contracted to one DFMA (count is an exact small integer)
+            acc[2 * j + 1] += cnt * t.y;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < KP; ++k) {
+#pragma unroll
+        for (int o = 16; o; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+    }
+    double* y = Y + row * KP;
+#pragma unroll
+    for (int j = 0; j < KP / 2; ++j)
+        if (lane == j) *reinterpret_cast<double2*>(y + 2 * j) = make_double2(acc[2 * j], acc[2 * j + 1]);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Fixed-order block reduction of NV values per thread (256 threads): shuffle tree inside each warp, then the
+// 8 warp results are added in warp order.  Same bits for the same inputs, every run.
+// ---------------------------------------------------------------------------------------------------------
+template <int NV>
+__device__ __forceinline__ void block_reduce_store(double (&v)[NV], double* smem /*[8][NV]*/, double* out /*[NV]*/) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+#pragma unroll
+        for (int o = 16; o; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) smem[warp * NV + k] = v[k];
+    }
+    __syncthreads();
+    if (threadIdx.x < NV) {
+        double s = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += smem[w * NV + threadIdx.x];
+        out[threadIdx.x] = s;
+    }
+}
+
+// W[c,i] = 1 / sum_j 2^(((L_j + s_j) - L_i) - s_i)   (scSplit:181-185, j ascending, left-to-right)
+// ll_c   = log2( sum_k 2^((L_k - max_k L) + s_k) ) + max_k L   with pandas skipna  (scSplit:188)
+// partial[r][blk][0..KP) = sum over the block's cells of W[c,k] (NaN skipped, scSplit:198), [KP] = sum of ll_c
+template <int KP>
+__global__ void __launch_bounds__(256) k_bayes(int64_t N, int K, const double* __restrict__ L, double* __restrict__ W,
+                                               const double* __restrict__ lps, double* __restrict__ partial, int nblk,
+                                               const int32_t* __restrict__ done) {
+    const int r = blockIdx.y;
+    if (done && done[r]) return;
+    __shared__ double s_lps[KP];
+    __shared__ double s_red[8 * (KP + 1)];
+    if (threadIdx.x < KP) s_lps[threadIdx.x] = lps[(int64_t)r * KP + threadIdx.x];
+    __syncthreads();
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    double v[KP + 1];
+#pragma unroll
+    for (int k = 0; k <= KP; ++k) v[k] = 0.0;
+    if (c < N) {
+        const double* l = L + ((int64_t)r * N + c) * KP;
+        double Lr[KP], t[KP];
+#pragma unroll
+        for (int j = 0; j < KP / 2; ++j) { double2 x = *reinterpret_cast<const double2*>(l + 2 * j); Lr[2 * j] = x.x; Lr[2 * j + 1] = x.y; }
+#pragma unroll
+        for (int k = 0; k < KP; ++k) t[k] = Lr[k] + s_lps[k];     // L_j + s_j
+        double w[KP];
+#pragma unroll
+        for (int i = 0; i < KP; ++i) {
+            double denom = 0.0;
+            if (i < K) {
+#pragma unroll
+                for (int j = 0; j < KP; ++j)
+                    if (j < K) denom += exp2((t[j] - Lr[i]) - s_lps[i]);
+                w[i] = 1.0 / denom;
+            } else {
+                w[i] = 0.0;
+            }
+        }
+        double* wout = W + ((int64_t)r * N + c) * KP;
+#pragma unroll
+        for (int j = 0; j < KP / 2; ++j) *reinterpret_cast<double2*>(wout + 2 * j) = make_double2(w[2 * j], w[2 * j + 1]);
+        // total log-likelihood term (skipna max, skipna sum)
+        double m = Lr[0];
+#pragma unroll
+        for (int k = 1; k < KP; ++k)
+            if (k < K) m = fmax(m, Lr[k]);          // fmax ignores NaN operands; NaN only if every L is NaN
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < KP; ++k)
+            if (k < K) {
+                double x = exp2((Lr[k] - m) + s_lps[k]);
+                if (x == x) s += x;
+            }
+        double ll = log2(s) + m;
+#pragma unroll
+        for (int k = 0; k < KP; ++k) v[k] = (w[k] == w[k]) ? w[k] : 0.0;
+        v[KP] = (ll == ll) ? ll : 0.0;
+    }
+    block_reduce_store<KP + 1>(v, s_red, partial + ((int64_t)r * nblk + blockIdx.x) * (KP + 1));
+}
+
+// column mass of an arbitrary W (step-level M-step entry): same block mapping and order as k_bayes
+template <int KP>
+__global__ void __launch_bounds__(256) k_colsum_partial(int64_t N, const double* __restrict__ W, double* __restrict__ partial,
+                                                        int nblk) {
+    const int r = blockIdx.y;
+    __shared__ double s_red[8 * (KP + 1)];
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    double v[KP + 1];
+#pragma unroll
+    for (int k = 0; k <= KP; ++k) v[k] = 0.0;
+    if (c < N) {
+        const double* w = W + ((int64_t)r * N + c) * KP;
+#pragma unroll
+        for (int k = 0; k < KP; ++k) { double x = w[k]; v[k] = (x == x) ? x : 0.0; }
+    }
+    // [KP] (LL) is left untouched by the caller's reduce (mask below)
+    block_reduce_store<KP + 1>(v, s_red, partial + ((int64_t)r * nblk + blockIdx.x) * (KP + 1));
+}
+
+// partial[r][blk][KP+1] -> tail[r][0..KP] (colsum, LL); one block of 256 threads per restart, fixed order.
+static __global__ void __launch_bounds__(256) k_reduce_stats(int KP, const double* __restrict__ partial, int nblk, double* __restrict__ stats,
+                                                      int64_t stats_stride, int64_t tail_off, int with_ll,
+                                                      const int32_t* __restrict__ done) {
+    const int r = blockIdx.x;
+    if (done && done[r]) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int NV = KP + 1;
+    for (int k = warp; k < NV; k += 8) {
+        double s = 0.0;
+        for (int b = lane; b < nblk; b += 32) s += partial[((int64_t)r * nblk + b) * NV + k];
+#pragma unroll
+        for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0 && (k < KP || with_ll)) stats[(int64_t)r * stats_stride + tail_off + k] = s;
+    }
+}
+
+// P = (altW + k_alt) / ((altW + refW) + 1);  T[2v] = log2 P, T[2v+1] = log2(1 - P)   (scSplit:196, 176-177)
+static __global__ void __launch_bounds__(256) k_finalize(int64_t V, int K, int KP, const double* __restrict__ stats, int64_t stats_stride,
+                                                  const double* __restrict__ kalt, double* __restrict__ P, double* __restrict__ T,
+                                                  const int32_t* __restrict__ done) {
+    const int r = blockIdx.y;
+    if (done && done[r]) return;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= V * KP) return;
+    const int64_t v = i / KP;
+    const int k = (int)(i - v * KP);
+    const double* S = stats + (int64_t)r * stats_stride;
+    double p = 0.0, lp = 0.0, lq = 0.0;
+    if (k < K) {
+        const double a = S[(2 * v) * KP + k], rf = S[(2 * v + 1) * KP + k];
+        p = (a + kalt[v]) / ((a + rf) + 1.0);
+        lp = log2(p);
+        lq = log2(1.0 - p);
+    }
+    P[((int64_t)r * V + v) * KP + k] = p;
+    if (T) {
+        T[((int64_t)r * 2 * V + 2 * v) * KP + k] = lp;
+        T[((int64_t)r * 2 * V + 2 * v + 1) * KP + k] = lq;
+    }
+}
+
+// log tables from a given P (EM start, scs_em_set(SCS_P), post-EM scores)
+static __global__ void __launch_bounds__(256) k_tables_from_P(int64_t V, int K, int KP, const double* __restrict__ P, double* __restrict__ T) {
+    const int r = blockIdx.y;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= V * KP) return;
+    const int64_t v = i / KP;
+    const int k = (int)(i - v * KP);
+    double lp = 0.0, lq = 0.0;
+    if (k < K) {
+        const double p = P[((int64_t)r * V + v) * KP + k];
+        lp = log2(p);
+        lq = log2(1.0 - p);
+    }
+    T[((int64_t)r * 2 * V + 2 * v) * KP + k] = lp;
+    T[((int64_t)r * 2 * V + 2 * v + 1) * KP + k] = lq;
+}
+
+// numpy's pairwise add.reduce for n < 128 contiguous doubles (what pandas Series.sum() runs for K values)
+__device__ __forceinline__ double numpy_sum_small(const double* a, int n) {
+    if (n < 8) {
+        double s = 0.0;   // numpy starts from a[0]; 0.0 + a[0] is exact, and colsums are never -0.0
+        for (int i = 0; i < n; ++i) s += a[i];
+        return s;
+    }
+    double r0 = a[0], r1 = a[1], r2 = a[2], r3 = a[3], r4 = a[4], r5 = a[5], r6 = a[6], r7 = a[7];
+    int i = 8;
+    for (; i < n - (n % 8); i += 8) {
+        r0 += a[i]; r1 += a[i + 1]; r2 += a[i + 2]; r3 += a[i + 3];
+        r4 += a[i + 4]; r5 += a[i + 5]; r6 += a[i + 6]; r7 += a[i + 7];
+    }
+    double res = ((r0 + r1) + (r2 + r3)) + ((r4 + r5) + (r6 + r7));
+    for (; i < n; ++i) res += a[i];
+    return res;
+}
+
+// lP_s = log2(colsum) - log2(sum colsum)  (scSplit:198); LL history and the bitwise stop rule (scSplit:156-162)
+static __global__ void k_update_prior(int K, int KP, const double* __restrict__ stats, int64_t stats_stride, int64_t tail_off,
+                               double* __restrict__ lps, double* __restrict__ hist, int max_iter, double* __restrict__ ll_prev,
+                               int32_t* __restrict__ iters, int32_t* __restrict__ done, int track, int check_conv) {
+    const int r = blockIdx.x;
+    if (track && check_conv && done[r]) return;
+    if (threadIdx.x != 0) return;
+    const double* tail = stats + (int64_t)r * stats_stride + tail_off;
+    const double tot = numpy_sum_small(tail, K);
+    const double ltot = log2(tot);
+    for (int k = 0; k < K; ++k) lps[(int64_t)r * KP + k] = log2(tail[k]) - ltot;
+    if (track) {
+        const double ll = tail[KP];
+        const int it = iters[r];
+        if (it < max_iter) hist[(int64_t)r * max_iter + it] = ll;
+        iters[r] = it + 1;
+        if (check_conv && (ll == ll_prev[r] || it + 1 >= max_iter)) done[r] = 1;
+        ll_prev[r] = ll;
+    }
+}
+
+}  // namespace scs

@@ -1,0 +1,307 @@
+// Device layout build: turns the reference's two SNV-major CSR count matrices (scSplit:546-547) into the
+// two packed entry streams the EM kernels read (DESIGN.md "Data layout in HBM").
+//
+// Everything after the host->device copies runs on the GPU and is deterministic: the SNV-major stream keeps
+// the input order, the cell-major stream is a STABLE radix sort of it by cell, so every row's entries are in
+// ascending (SNV, allele) order on every run and the floating-point summation order of the EM never changes.
+// cub (part of the CUDA toolkit) is used for the one-time scan/sort only, never on the per-iteration path.
+#include <cub/cub.cuh>
+
+#include "common.cuh"
+
+namespace scs {
+
+__device__ __forceinline__ int64_t load_count(const void* data, int64_t i, int bytes) {
+    if (bytes == 2) return ((const int16_t*)data)[i];
+    if (bytes == 4) return ((const int32_t*)data)[i];
+    return ((const int64_t*)data)[i];
+}
+
+// one warp per pseudo-row pr = 2v + sel: number of count==1 / count>1 entries and the integer row sum
+__global__ void k_count_rows(int64_t V, const int64_t* a_ptr, const void* a_val, const int64_t* r_ptr, const void* r_val,
+                             int bytes, int64_t* cntL, int64_t* cntH, int64_t* rowsum, int* err) {
+    int64_t pr = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    int lane = threadIdx.x & 31;
+    if (pr >= 2 * V) return;
+    int64_t v = pr >> 1;
+    int sel = (int)(pr & 1);
+    const int64_t* ptr = sel ? r_ptr : a_ptr;
+    const void* val = sel ? r_val : a_val;
+    int64_t b = ptr[v], e = ptr[v + 1];
+    int64_t nl = 0, nh = 0, s = 0;
+    for (int64_t i = b + lane; i < e; i += 32) {
+        int64_t c = load_count(val, i, bytes);
+        if (c <= 0 || c > 2147483647LL) atomicExch(err, 1);
+        nl += (c == 1);
+        nh += (c > 1);
+        s += c;
+    }
+    for (int o = 16; o; o >>= 1) {
+        nl += __shfl_xor_sync(0xffffffffu, nl, o);
+        nh += __shfl_xor_sync(0xffffffffu, nh, o);
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+    }
+    if (lane == 0) {
+        cntL[pr] = nl;
+        cntH[pr] = nh;
+        rowsum[pr] = s;
+    }
+}
+
+// one warp per pseudo-row: ordered (ballot) split of its entries into the light and heavy SNV-major streams,
+// plus the (cell key, cell-major code) pairs that the stable sort turns into the cell-major stream.
+__global__ void k_fill_M(int64_t V, int64_t N, const int64_t* a_ptr, const int32_t* a_idx, const void* a_val,
+                         const int64_t* r_ptr, const int32_t* r_idx, const void* r_val, int bytes,
+                         const int64_t* lptr, const int64_t* hptr, uint32_t* lcode, uint32_t* hcode, int32_t* hcnt,
+                         uint32_t* lkey, uint32_t* lval, uint32_t* hkey, uint64_t* hval,
+                         unsigned long long* ndup, int* err) {
+    int64_t pr = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    int lane = threadIdx.x & 31;
+    if (pr >= 2 * V) return;
+    int64_t v = pr >> 1;
+    int sel = (int)(pr & 1);
+    const int64_t* ptr = sel ? r_ptr : a_ptr;
+    const int32_t* idx = sel ? r_idx : a_idx;
+    const void* val = sel ? r_val : a_val;
+    int64_t b = ptr[v], e = ptr[v + 1];
+    int64_t ab = a_ptr[v], ae = a_ptr[v + 1];
+    int64_t lpos = lptr[pr], hpos = hptr[pr];
+    unsigned long long dups = 0;
+    for (int64_t i0 = b; i0 < e; i0 += 32) {
+        int64_t i = i0 + lane;
+        bool valid = i < e;
+        int64_t c = valid ? load_count(val, i, bytes) : 0;
+        int32_t cell = valid ? idx[i] : 0;
+        if (valid && (cell < 0 || cell >= N)) atomicExch(err, 2);
+        if (valid && i > b && idx[i - 1] >= cell) atomicExch(err, 3);  // indices must be sorted and unique
+        uint32_t dup = 0;
+        if (valid && sel) {  // does the same (SNV, cell) have an alt entry?  binary search in the alt row
+            int64_t lo = ab, hi = ae;
+            while (lo < hi) {
+                int64_t mid = (lo + hi) >> 1;
+                if (a_idx[mid] < cell) lo = mid + 1; else hi = mid;
+            }
+            dup = (lo < ae && a_idx[lo] == cell) ? 1u : 0u;
+            dups += dup;
+        }
+        bool light = valid && c == 1, heavy = valid && c > 1;
+        unsigned ml = __ballot_sync(0xffffffffu, light), mh = __ballot_sync(0xffffffffu, heavy);
+        unsigned lt = (1u << lane) - 1u;
+        uint32_t codeM = ((uint32_t)cell << 2) | ((uint32_t)sel << 1) | dup;
+        uint32_t codeE = ((uint32_t)v << 2) | ((uint32_t)sel << 1) | dup;
+        if (light) {
+            int64_t p = lpos + __popc(ml & lt);
+            lcode[p] = codeM;
+            lkey[p] = (uint32_t)cell;
+            lval[p] = codeE;
+        }
+        if (heavy) {
+            int64_t p = hpos + __popc(mh & lt);
+            hcode[p] = codeM;
+            hcnt[p] = (int32_t)c;
+            hkey[p] = (uint32_t)cell;
+            hval[p] = (uint64_t)codeE | ((uint64_t)(uint32_t)c << 32);
+        }
+        lpos += __popc(ml);
+        hpos += __popc(mh);
+    }
+    for (int o = 16; o; o >>= 1) dups += __shfl_xor_sync(0xffffffffu, dups, o);
+    if (lane == 0 && dups) atomicAdd(ndup, dups);
+}
+
+// row pointers from sorted keys: ptr[r] = first position whose key >= r
+__global__ void k_ptr_from_sorted(const uint32_t* keys, int64_t n, int64_t nrows, int64_t* ptr) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > n) return;
+    int64_t kprev = (i == 0) ? -1 : (int64_t)keys[i - 1];
+    int64_t k = (i == n) ? nrows : (int64_t)keys[i];
+    for (int64_t r = kprev + 1; r <= k; ++r) ptr[r] = i;
+}
+
+__global__ void k_split_heavy(const uint64_t* hval, int64_t n, uint32_t* hcode, int32_t* hcnt) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t x = hval[i];
+    hcode[i] = (uint32_t)x;
+    hcnt[i] = (int32_t)(x >> 32);
+}
+
+__global__ void k_row_sums(int64_t V, const int64_t* rowsum, int64_t* sum_alt, int64_t* sum_ref) {
+    int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= V) return;
+    sum_alt[v] = rowsum[2 * v];
+    sum_ref[v] = rowsum[2 * v + 1];
+}
+
+// k_alt, scSplit:100-103: N_alt / (N_ref + N_alt) with N_x = row sum + 1; integer-exact operands
+__global__ void k_kalt(int64_t V, const int64_t* sum_alt, const int64_t* sum_ref, double* kalt) {
+    int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= V) return;
+    int64_t na = sum_alt[v] + 1, nr = sum_ref[v] + 1;
+    kalt[v] = (double)na / (double)(nr + na);
+}
+
+void free_stream(Stream& s) {
+    dev_free(s.lptr);
+    dev_free(s.hptr);
+    dev_free(s.lcode);
+    dev_free(s.hcode);
+    dev_free(s.hcnt);
+}
+
+static int bits_for(int64_t n) {
+    int b = 1;
+    while ((1LL << b) < n) ++b;
+    return b;
+}
+
+template <typename VT>
+static int stable_sort_by_cell(scs_ctx* ctx, const uint32_t* kin, uint32_t* kout, const VT* vin, VT* vout, int64_t n,
+                               int64_t nrows) {
+    if (n == 0) return 0;
+    size_t tb = 0;
+    int eb = bits_for(nrows);
+    SCS_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, kin, kout, vin, vout, n, 0, eb, ctx->stream));
+    void* tmp = nullptr;
+    SCS_CUDA(cudaMalloc(&tmp, tb ? tb : 1));
+    cudaError_t e = cub::DeviceRadixSort::SortPairs(tmp, tb, kin, kout, vin, vout, n, 0, eb, ctx->stream);
+    cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
+    cudaFree(tmp);
+    SCS_CUDA(e);
+    SCS_CUDA(e2);
+    ctx->launches += 4;
+    return 0;
+}
+
+static int inclusive_scan_into_ptr(scs_ctx* ctx, const int64_t* cnt, int64_t* ptr, int64_t n) {
+    SCS_CUDA(cudaMemsetAsync(ptr, 0, sizeof(int64_t), ctx->stream));
+    size_t tb = 0;
+    SCS_CUDA(cub::DeviceScan::InclusiveSum(nullptr, tb, cnt, ptr + 1, n, ctx->stream));
+    void* tmp = nullptr;
+    SCS_CUDA(cudaMalloc(&tmp, tb ? tb : 1));
+    cudaError_t e = cub::DeviceScan::InclusiveSum(tmp, tb, cnt, ptr + 1, n, ctx->stream);
+    cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
+    cudaFree(tmp);
+    SCS_CUDA(e);
+    SCS_CUDA(e2);
+    ctx->launches += 2;
+    return 0;
+}
+
+int build_layout(scs_ctx* ctx, const int64_t* ref_indptr, const int32_t* ref_indices, const void* ref_data,
+                 const int64_t* alt_indptr, const int32_t* alt_indices, const void* alt_data, int data_bytes) {
+    const int64_t V = ctx->V, N = ctx->N;
+    SCS_CHECK(data_bytes == 2 || data_bytes == 4 || data_bytes == 8, "data_bytes must be 2, 4 or 8 (got %d)", data_bytes);
+    SCS_CHECK(V > 0 && N > 0, "empty matrix: V=%lld N=%lld", (long long)V, (long long)N);
+    SCS_CHECK(V < (1LL << 29) && N < (1LL << 29), "V and N must be below 2^29");
+    SCS_CHECK(ref_indptr[0] == 0 && alt_indptr[0] == 0, "indptr[0] must be 0");
+    const int64_t nR = ref_indptr[V], nA = alt_indptr[V];
+    SCS_CHECK(nR >= 0 && nA >= 0, "negative nnz");
+    ctx->nnz_ref = nR;
+    ctx->nnz_alt = nA;
+    cudaStream_t st = ctx->stream;
+
+    // ---- host -> device (raw CSR of both matrices); temporaries, freed before returning
+    int64_t *a_ptr = nullptr, *r_ptr = nullptr;
+    int32_t *a_idx = nullptr, *r_idx = nullptr;
+    void *a_val = nullptr, *r_val = nullptr;
+    SCS_CUDA(cudaMalloc((void**)&a_ptr, (V + 1) * sizeof(int64_t)));
+    SCS_CUDA(cudaMalloc((void**)&r_ptr, (V + 1) * sizeof(int64_t)));
+    SCS_CUDA(cudaMalloc((void**)&a_idx, (size_t)(nA ? nA : 1) * 4));
+    SCS_CUDA(cudaMalloc((void**)&r_idx, (size_t)(nR ? nR : 1) * 4));
+    SCS_CUDA(cudaMalloc(&a_val, (size_t)(nA ? nA : 1) * data_bytes));
+    SCS_CUDA(cudaMalloc(&r_val, (size_t)(nR ? nR : 1) * data_bytes));
+    SCS_CUDA(cudaMemcpyAsync(a_ptr, alt_indptr, (V + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    SCS_CUDA(cudaMemcpyAsync(r_ptr, ref_indptr, (V + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    if (nA) SCS_CUDA(cudaMemcpyAsync(a_idx, alt_indices, (size_t)nA * 4, cudaMemcpyHostToDevice, st));
+    if (nR) SCS_CUDA(cudaMemcpyAsync(r_idx, ref_indices, (size_t)nR * 4, cudaMemcpyHostToDevice, st));
+    if (nA) SCS_CUDA(cudaMemcpyAsync(a_val, alt_data, (size_t)nA * data_bytes, cudaMemcpyHostToDevice, st));
+    if (nR) SCS_CUDA(cudaMemcpyAsync(r_val, ref_data, (size_t)nR * data_bytes, cudaMemcpyHostToDevice, st));
+
+    int* err = nullptr;
+    unsigned long long* ndup = nullptr;
+    SCS_CUDA(cudaMalloc((void**)&err, sizeof(int)));
+    SCS_CUDA(cudaMalloc((void**)&ndup, sizeof(unsigned long long)));
+    SCS_CUDA(cudaMemsetAsync(err, 0, sizeof(int), st));
+    SCS_CUDA(cudaMemsetAsync(ndup, 0, sizeof(unsigned long long), st));
+
+    // ---- SNV-major stream (2V pseudo-rows)
+    Stream& M = ctx->M;
+    M.nrows = 2 * V;
+    int64_t *cntL = nullptr, *cntH = nullptr, *rowsum = nullptr;
+    SCS_CUDA(cudaMalloc((void**)&cntL, 2 * V * sizeof(int64_t)));
+    SCS_CUDA(cudaMalloc((void**)&cntH, 2 * V * sizeof(int64_t)));
+    SCS_CUDA(cudaMalloc((void**)&rowsum, 2 * V * sizeof(int64_t)));
+    const int WPB = 8;  // warps per block
+    unsigned gridPR = (unsigned)((2 * V + WPB - 1) / WPB);
+    k_count_rows<<<gridPR, WPB * 32, 0, st>>>(V, a_ptr, a_val, r_ptr, r_val, data_bytes, cntL, cntH, rowsum, err);
+    ctx->launches++;
+    SCS_TRY(dev_alloc(ctx, &M.lptr, 2 * V + 1));
+    SCS_TRY(dev_alloc(ctx, &M.hptr, 2 * V + 1));
+    SCS_TRY(inclusive_scan_into_ptr(ctx, cntL, M.lptr, 2 * V));
+    SCS_TRY(inclusive_scan_into_ptr(ctx, cntH, M.hptr, 2 * V));
+    int herr = 0;
+    SCS_CUDA(cudaMemcpy(&herr, err, sizeof(int), cudaMemcpyDeviceToHost));
+    SCS_CHECK(herr == 0, "count matrices must hold strictly positive counts that fit int32 (explicit zeros are not allowed)");
+    SCS_CUDA(cudaMemcpy(&M.n_light, M.lptr + 2 * V, sizeof(int64_t), cudaMemcpyDeviceToHost));
+    SCS_CUDA(cudaMemcpy(&M.n_heavy, M.hptr + 2 * V, sizeof(int64_t), cudaMemcpyDeviceToHost));
+    SCS_CHECK(M.n_light + M.n_heavy == nA + nR, "internal: light+heavy != nnz");
+    SCS_TRY(dev_alloc(ctx, &M.lcode, M.n_light));
+    SCS_TRY(dev_alloc(ctx, &M.hcode, M.n_heavy));
+    SCS_TRY(dev_alloc(ctx, &M.hcnt, M.n_heavy));
+
+    uint32_t *lkey = nullptr, *lval = nullptr, *hkey = nullptr, *lkey_s = nullptr, *hkey_s = nullptr;
+    uint64_t *hval = nullptr, *hval_s = nullptr;
+    const int64_t nl = M.n_light ? M.n_light : 1, nh = M.n_heavy ? M.n_heavy : 1;
+    SCS_CUDA(cudaMalloc((void**)&lkey, nl * 4));
+    SCS_CUDA(cudaMalloc((void**)&lval, nl * 4));
+    SCS_CUDA(cudaMalloc((void**)&lkey_s, nl * 4));
+    SCS_CUDA(cudaMalloc((void**)&hkey, nh * 4));
+    SCS_CUDA(cudaMalloc((void**)&hkey_s, nh * 4));
+    SCS_CUDA(cudaMalloc((void**)&hval, nh * 8));
+    SCS_CUDA(cudaMalloc((void**)&hval_s, nh * 8));
+    k_fill_M<<<gridPR, WPB * 32, 0, st>>>(V, N, a_ptr, a_idx, a_val, r_ptr, r_idx, r_val, data_bytes, M.lptr, M.hptr,
+                                          M.lcode, M.hcode, M.hcnt, lkey, lval, hkey, hval, ndup, err);
+    ctx->launches++;
+
+    // ---- cell-major stream: stable sort of the SNV-major order by cell
+    Stream& E = ctx->E;
+    E.nrows = N;
+    E.n_light = M.n_light;
+    E.n_heavy = M.n_heavy;
+    SCS_TRY(dev_alloc(ctx, &E.lptr, N + 1));
+    SCS_TRY(dev_alloc(ctx, &E.hptr, N + 1));
+    SCS_TRY(dev_alloc(ctx, &E.lcode, E.n_light));
+    SCS_TRY(dev_alloc(ctx, &E.hcode, E.n_heavy));
+    SCS_TRY(dev_alloc(ctx, &E.hcnt, E.n_heavy));
+    SCS_TRY(stable_sort_by_cell<uint32_t>(ctx, lkey, lkey_s, lval, E.lcode, M.n_light, N));
+    SCS_TRY(stable_sort_by_cell<uint64_t>(ctx, hkey, hkey_s, hval, hval_s, M.n_heavy, N));
+    k_ptr_from_sorted<<<(unsigned)((M.n_light + 256) / 256), 256, 0, st>>>(lkey_s, M.n_light, N, E.lptr);
+    k_ptr_from_sorted<<<(unsigned)((M.n_heavy + 256) / 256), 256, 0, st>>>(hkey_s, M.n_heavy, N, E.hptr);
+    if (M.n_heavy) k_split_heavy<<<(unsigned)((M.n_heavy + 255) / 256), 256, 0, st>>>(hval_s, M.n_heavy, E.hcode, E.hcnt);
+    ctx->launches += 3;
+
+    // ---- integer row sums and k_alt (scSplit:100-103)
+    SCS_TRY(dev_alloc(ctx, &ctx->sum_alt, V));
+    SCS_TRY(dev_alloc(ctx, &ctx->sum_ref, V));
+    SCS_TRY(dev_alloc(ctx, &ctx->kalt, V));
+    k_row_sums<<<(unsigned)((V + 255) / 256), 256, 0, st>>>(V, rowsum, ctx->sum_alt, ctx->sum_ref);
+    k_kalt<<<(unsigned)((V + 255) / 256), 256, 0, st>>>(V, ctx->sum_alt, ctx->sum_ref, ctx->kalt);
+    ctx->launches += 2;
+
+    unsigned long long hdup = 0;
+    SCS_CUDA(cudaMemcpyAsync(&hdup, ndup, sizeof(hdup), cudaMemcpyDeviceToHost, st));
+    SCS_CUDA(cudaMemcpyAsync(&herr, err, sizeof(int), cudaMemcpyDeviceToHost, st));
+    SCS_CUDA(cudaStreamSynchronize(st));
+    SCS_CUDA(cudaGetLastError());
+    cudaFree(a_ptr); cudaFree(r_ptr); cudaFree(a_idx); cudaFree(r_idx); cudaFree(a_val); cudaFree(r_val);
+    cudaFree(cntL); cudaFree(cntH); cudaFree(rowsum); cudaFree(err); cudaFree(ndup);
+    cudaFree(lkey); cudaFree(lval); cudaFree(lkey_s); cudaFree(hkey); cudaFree(hkey_s); cudaFree(hval); cudaFree(hval_s);
+    SCS_CHECK(herr != 2, "column index out of range [0, N)");
+    SCS_CHECK(herr != 3, "CSR column indices must be sorted and duplicate-free within each row");
+    SCS_CHECK(herr == 0, "invalid count matrix (code %d)", herr);
+    ctx->nnz_union = nA + nR - (int64_t)hdup;
+    return 0;
+}
+
+}  // namespace scs

@@ -1,0 +1,208 @@
+"""numpy-in / numpy-out wrapper of one scs_ctx (one GPU, one shard of cells)."""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from ._lib import SCS_L, SCS_LLHIST, SCS_LPS, SCS_P, SCS_STATS, SCS_W, check
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+def _canonical_csr(m):
+    """scipy CSR with sorted, duplicate-free indices and no explicit zeros (what csr_matrix(dense) gives, scSplit:546)."""
+    from scipy.sparse import csr_matrix
+    m = csr_matrix(m)
+    if not m.has_canonical_format:
+        m = m.copy()
+        m.sum_duplicates()
+    if m.nnz and (m.data == 0).any():
+        m = m.copy()
+        m.eliminate_zeros()
+    return m
+
+
+class Engine:
+    """Device-resident count matrices + EM state.  All arrays crossing this boundary are host numpy arrays."""
+
+    def __init__(self, ref, alt, device=0):
+        self.lib = _lib.load()
+        ref, alt = _canonical_csr(ref), _canonical_csr(alt)
+        if ref.shape != alt.shape:
+            raise ValueError("ref and alt matrices differ in shape: %r vs %r" % (ref.shape, alt.shape))
+        self.V, self.N = int(ref.shape[0]), int(ref.shape[1])
+        for m in (ref, alt):
+            if m.dtype.kind not in "iu" and not np.array_equal(m.data, np.rint(m.data)):
+                raise ValueError("allele counts must be integers")
+            if m.nnz and (m.data.min() < 0 or m.data.max() > np.iinfo(np.int32).max):
+                raise ValueError("allele counts must lie in [0, 2^31): never wrapped (scSplit:38-39 uses int16)")
+        top = max([int(m.data.max()) for m in (ref, alt) if m.nnz] + [0])
+        dt = np.dtype(np.int16 if top <= np.iinfo(np.int16).max else np.int32)   # narrowest transfer type that fits
+        arrs = []
+        for m in (ref, alt):
+            arrs += [np.ascontiguousarray(m.indptr, dtype=np.int64), np.ascontiguousarray(m.indices, dtype=np.int32),
+                     np.ascontiguousarray(m.data, dtype=dt)]
+        self._keep = arrs
+        h = ctypes.c_void_p()
+        check(self.lib.scs_create(ctypes.byref(h), int(device), self.V, self.N, _ptr(arrs[0]), _ptr(arrs[1]), _ptr(arrs[2]),
+                                  _ptr(arrs[3]), _ptr(arrs[4]), _ptr(arrs[5]), dt.itemsize))
+        self.h = h
+        self._keep = None
+        self.R = self.K = 0
+        self.max_iter = 0
+
+    # -- lifetime
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.scs_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # -- layout
+    def layout_info(self):
+        out = (ctypes.c_int64 * 6)()
+        check(self.lib.scs_layout_info(self.h, out))
+        return dict(nnz_ref=out[0], nnz_alt=out[1], nnz_union=out[2], light=out[3], heavy=out[4], device_bytes=out[5])
+
+    def kalt(self):
+        out = np.empty(self.V, dtype=np.float64)
+        check(self.lib.scs_kalt(self.h, _ptr(out)))
+        return out
+
+    def seed_af(self, labels, K):
+        labels = np.ascontiguousarray(labels, dtype=np.int32)
+        single = labels.ndim == 1
+        labels = labels.reshape(-1, self.N)
+        R = labels.shape[0]
+        out = np.empty((R, self.V, K), dtype=np.float64)
+        check(self.lib.scs_seed_af(self.h, R, int(K), _ptr(labels), _ptr(out)))
+        return out[0] if single else out
+
+    def pattern_counts(self, keep_rows=None, keep_cols=None):
+        kr = None if keep_rows is None else np.ascontiguousarray(keep_rows, dtype=np.uint8)
+        kc = None if keep_cols is None else np.ascontiguousarray(keep_cols, dtype=np.uint8)
+        rc = np.empty(self.V, dtype=np.int64)
+        cc = np.empty(self.N, dtype=np.int64)
+        check(self.lib.scs_pattern_counts(self.h, _ptr(kr), _ptr(kc), _ptr(rc), _ptr(cc)))
+        return rc, cc
+
+    # -- EM
+    def em_begin(self, P0, max_iter=_lib.SCS_MAX_ITER):
+        P0 = np.ascontiguousarray(P0, dtype=np.float64)
+        if P0.ndim == 2:
+            P0 = P0[None]
+        R, V, K = P0.shape
+        if V != self.V:
+            raise ValueError("P0 has %d SNVs, matrices have %d" % (V, self.V))
+        check(self.lib.scs_em_begin(self.h, R, K, _ptr(P0), int(max_iter)))
+        self.R, self.K, self.max_iter = R, K, int(max_iter)
+
+    def em_iterate(self, n_iter, check_conv=True):
+        check(self.lib.scs_em_iterate(self.h, int(n_iter), 1 if check_conv else 0))
+
+    def em_run(self):
+        check(self.lib.scs_em_run(self.h))
+
+    def estep(self):
+        check(self.lib.scs_estep(self.h))
+
+    def mstep(self):
+        check(self.lib.scs_mstep(self.h))
+
+    def em_status(self):
+        it = np.empty(self.R, dtype=np.int32)
+        cv = np.empty(self.R, dtype=np.int32)
+        ll = np.empty(self.R, dtype=np.float64)
+        check(self.lib.scs_em_status(self.h, _ptr(it), _ptr(cv), _ptr(ll)))
+        return it, cv, ll
+
+    def _shape(self, what):
+        return {SCS_P: (self.V, self.K), SCS_W: (self.N, self.K), SCS_L: (self.N, self.K), SCS_LPS: (self.K,),
+                SCS_LLHIST: (self.max_iter,)}[what]
+
+    def get(self, what, restart=0):
+        out = np.empty(self._shape(what), dtype=np.float64)
+        check(self.lib.scs_em_get(self.h, int(restart), int(what), _ptr(out)))
+        return out
+
+    def set(self, what, value, restart=0):
+        value = np.ascontiguousarray(value, dtype=np.float64)
+        if value.shape != self._shape(what):
+            raise ValueError("expected shape %r, got %r" % (self._shape(what), value.shape))
+        check(self.lib.scs_em_set(self.h, int(restart), int(what), _ptr(value)))
+
+    def stats(self, restart=0):
+        """Packed M-step statistics of one restart: S[2V][KP] (alt rows 2v, ref rows 2v+1), column mass, last E-step LL."""
+        KP = self.K + (self.K & 1)
+        out = np.empty(2 * self.V * KP + KP + 2, dtype=np.float64)
+        check(self.lib.scs_em_get(self.h, int(restart), SCS_STATS, _ptr(out)))
+        n = 2 * self.V * KP
+        return dict(S=out[:n].reshape(2 * self.V, KP), colsum=out[n:n + self.K].copy(), ll=float(out[n + KP]))
+
+    def em_end(self):
+        check(self.lib.scs_em_end(self.h))
+        self.R = self.K = 0
+
+    # -- post-EM
+    def doublet_scores(self, P, mask):
+        P = np.ascontiguousarray(P, dtype=np.float64)
+        mask = np.ascontiguousarray(mask, dtype=np.uint8)
+        out = np.empty(P.shape[1], dtype=np.float64)
+        check(self.lib.scs_doublet_scores(self.h, P.shape[1], _ptr(P), _ptr(mask), _ptr(out)))
+        return out
+
+    def refine_scores(self, P, labels):
+        P = np.ascontiguousarray(P, dtype=np.float64)
+        labels = np.ascontiguousarray(labels, dtype=np.int32)
+        out = np.empty(self.N, dtype=np.float64)
+        check(self.lib.scs_refine_scores(self.h, P.shape[1], _ptr(P), _ptr(labels), _ptr(out)))
+        return out
+
+    def cluster_counts(self, labels, K):
+        labels = np.ascontiguousarray(labels, dtype=np.int32)
+        n_ref = np.empty((self.V, K), dtype=np.int64)
+        n_alt = np.empty((self.V, K), dtype=np.int64)
+        pa = np.empty((self.V, K), dtype=np.int8)
+        check(self.lib.scs_cluster_counts(self.h, int(K), _ptr(labels), _ptr(n_ref), _ptr(n_alt), _ptr(pa)))
+        return n_ref, n_alt, pa
+
+    # -- multi-GPU
+    @staticmethod
+    def comm_unique_id():
+        buf = np.zeros(128, dtype=np.uint8)
+        check(_lib.load().scs_comm_unique_id(_ptr(buf)))
+        return buf
+
+    def comm_init(self, uid, rank, world):
+        uid = np.ascontiguousarray(uid, dtype=np.uint8)
+        check(self.lib.scs_comm_init(self.h, _ptr(uid), int(rank), int(world)))
+
+    # -- instrumentation
+    def launch_count(self):
+        n = ctypes.c_int64(0)
+        check(self.lib.scs_launch_count(self.h, ctypes.byref(n)))
+        return n.value
+
+    def set_timing(self, on=True):
+        check(self.lib.scs_set_timing(self.h, 1 if on else 0))
+
+    def kernel_times(self, reset=False):
+        out = (ctypes.c_double * 4)()
+        check(self.lib.scs_kernel_times(self.h, out, 1 if reset else 0))
+        return dict(e_us=out[0], m_us=out[1], e_n=int(out[2]), m_n=int(out[3]))
+
+    def set_variant(self, v):
+        check(self.lib.scs_set_variant(self.h, int(v)))
