@@ -84,6 +84,8 @@ int scs_em_begin(scs_ctx* ctx, int R, int K, const double* P0, int max_iter);
 /* Run up to n_iter more iterations on every unconverged restart. check_conv=1 applies the reference's
  * stop rule (bitwise-equal consecutive LL, scSplit:156) on the device; 0 runs exactly n_iter (benchmarks). */
 int scs_em_iterate(scs_ctx* ctx, int n_iter, int check_conv);
+/* Device time in milliseconds (CUDA events on the context's stream) of the launches of the last scs_em_iterate. */
+int scs_em_last_ms(scs_ctx* ctx, double* ms);
 /* Run to the reference's stopping rule (cap max_iter). */
 int scs_em_run(scs_ctx* ctx);
 /* One E-step (calculate_cell_likelihood, scSplit:165-188) / one M-step (calculate_model_af,

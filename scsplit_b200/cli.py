@@ -1,0 +1,133 @@
+"""`scSplit run` drop-in: same flags, same input CSVs, same five output files and log lines (scSplit:467-600).
+
+Only the `run` sub-command is in scope; `count` (BAM pile-up, pysam) and `genotype` are not part
+of the EM hot path and are reported as such.
+"""
+import argparse
+import datetime
+import os
+import sys
+
+import numpy as np
+import pandas as pd
+from scipy.sparse import csr_matrix
+
+from . import models as M
+
+
+def _log(out, text):
+    with open(os.path.join(out, r'scSplit.log'), 'a') as logfile:
+        logfile.write(text)
+
+
+def load_counts(ref_path, alt_path):
+    """ref_filtered.csv / alt_filtered.csv -> base_calls_mtx = [csr ref, csr alt, SNV index, barcode index] (scSplit:544-547)."""
+    ref = pd.read_csv(ref_path, header=0, index_col=0)
+    alt = pd.read_csv(alt_path, header=0, index_col=0)
+    ref_s, alt_s = csr_matrix(ref.values), csr_matrix(alt.values)
+    return [ref_s, alt_s, ref.index, ref.columns]
+
+
+def elbow(points):
+    """Elbow of the LL curve, including the reference's quirk that `m` is never updated (scSplit:493-501)."""
+    points = [-x for x in points]
+    p1, p2, m, e = np.array([0, points[0]]), np.array([len(points) - 1, points[-1]]), 0, 0
+    for i in range(1, (len(points) - 1)):
+        p3 = np.array([i, points[i]])
+        a, b = p2 - p1, p1 - p3
+        d = abs(a[0] * b[1] - a[1] * b[0]) / np.linalg.norm(p2 - p1)
+        if d > m:
+            e = i
+    return e
+
+
+def write_outputs(model, num, doublets, out):
+    """scSplit_result.csv, scSplit_P_s_c.csv, scSplit_dist_variants.txt, scSplit_dist_matrix.csv, scSplit_PA_matrix.csv
+    in the reference's formats (scSplit:582-600)."""
+    frames = []
+    for n in range(num):
+        if n != model.doublet:
+            frames.append(pd.DataFrame({'Barcode': model.reassigned[n], 'Cluster': 'SNG-' + str(n)}))
+    if doublets != 0:
+        frames.append(pd.DataFrame({'Barcode': model.reassigned[model.doublet], 'Cluster': 'DBL-' + str(model.doublet)}))
+    frames = [f for f in frames if len(f)] or [pd.DataFrame({'Barcode': [], 'Cluster': []})]
+    pd.concat(frames).to_csv(os.path.join(out, r'scSplit_result.csv'), sep='\t', index=False)
+    model.P_s_c.to_csv(os.path.join(out, r'scSplit_P_s_c.csv'))
+    with open(os.path.join(out, r'scSplit_dist_variants.txt'), 'w') as f:
+        for item in model.dist_variants:
+            f.write(str(item) + '\n')
+    model.dist_matrix.to_csv(os.path.join(out, r'scSplit_dist_matrix.csv'), float_format='%.0f')
+    model.pa_matrix.to_csv(os.path.join(out, r'scSplit_PA_matrix.csv'), float_format='%.0f')
+
+
+def run(argv):
+    parser = argparse.ArgumentParser(prog='scSplit run', description='Demultiplex the scRNA-Seq using REF/ALT count matrices')
+    parser.add_argument('-r', '--ref', required=True, help='REF count CSV input')
+    parser.add_argument('-a', '--alt', required=True, help='ALT count CSV input')
+    parser.add_argument('-n', '--num', type=int, required=True, help='Number of known mixed samples, if set to 0 system will find the most likely number')
+    parser.add_argument('-o', '--out', required=True, help='Output directory')
+    parser.add_argument('-s', '--sub', type=int, required=False, default='10', help='(Optional) Largest possible number of subpopulations, default: 10')
+    parser.add_argument('-e', '--ems', type=int, required=False, default='30', help='(Optional) Number of EM repeats to avoid local maximum, default: 30')
+    parser.add_argument('-d', '--dbl', type=float, required=False, help='(Optional) Doublet proportion')
+    parser.add_argument('-v', '--vcf', required=False, help='(Optional) VCF file for filtering distinguishing variants')
+    parser.add_argument('--device', type=int, default=0, help='CUDA device ordinal (scsplit_b200 extension)')
+    args = parser.parse_args(argv)
+
+    if not os.path.exists(args.out):
+        raise ValueError('Specified output directory does not exist')
+    doublets = float(args.dbl) if args.dbl is not None else -1
+    num = args.num if doublets == 0 else args.num + 1          # additional doublet state, scSplit:535-538
+
+    _log(args.out, '\n' + ' '.join(['scSplit', 'run'] + list(argv)) + '\n')
+    _log(args.out, 'Loading allele count matrices: ' + str(datetime.datetime.now()) + '\n')
+    base_calls_mtx = load_counts(args.ref, args.alt)
+    _log(args.out, 'Allele counts matrices loaded: ' + str(datetime.datetime.now()) + '\n')
+
+    if args.num == 0:                                            # autodetect sweep, scSplit:550-558
+        all_models, LL = [], []
+        for sub in range(2, args.sub + 1):
+            model, _ = M.core_batched(base_calls_mtx, sub, args.out, args.ems, device=args.device)
+            all_models.append(model)
+            LL.append(model.lP_c_s.max(axis=1).sum())
+        elb = elbow(LL)
+        model = all_models[elb]
+        num = elb + 2
+    else:
+        model, _ = M.core_batched(base_calls_mtx, num, args.out, args.ems, device=args.device)
+
+    model.define_doublet()
+    model.refine_doublets(doublets)
+
+    pos = []
+    if args.vcf:
+        try:
+            import vcf                                            # PyVCF, optional exactly as in scSplit:566-575
+            for record in vcf.Reader(open(args.vcf, 'r')):
+                try:
+                    if float(record.INFO['R2'][0]) > 0.9:
+                        pos.append(model.all_POS.index(str(record.CHROM) + ':' + str(record.POS)))
+                except Exception:
+                    continue
+        except Exception:
+            pass
+    model.distinguishing_alleles(pos)
+    write_outputs(model, num, doublets, args.out)
+    M.release_engines()
+    return model
+
+
+def main(argv=None):
+    argv = sys.argv[1:] if argv is None else list(argv)
+    if not argv or argv[0] in ('-h', '--help'):
+        print('usage: scSplit <command> [<args>]\n\nCommands:\n   run       Demultiplex the scRNA-Seq using REF/ALT count matrices (B200 CUDA path)')
+        return 0
+    if argv[0] == 'run':
+        run(argv[1:])
+        return 0
+    if argv[0] in ('count', 'genotype'):
+        raise SystemExit('scsplit_b200 accelerates `scSplit run` only; `%s` is outside the EM hot path (use the reference)' % argv[0])
+    raise SystemExit('unknown command %r' % argv[0])
+
+
+if __name__ == '__main__':
+    sys.exit(main())

@@ -98,6 +98,7 @@ int scs_destroy(scs_ctx* ctx) {
     dev_free(ctx->kalt);
     for (auto& p : ctx->ev_pending) { cudaEventDestroy(p.second.first); cudaEventDestroy(p.second.second); }
     for (auto e : ctx->ev_pool) cudaEventDestroy(e);
+    for (auto e : ctx->ev_iter) if (e) cudaEventDestroy(e);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return 0;

@@ -94,6 +94,8 @@ struct scs_ctx {
     int variant = 0;
     std::vector<cudaEvent_t> ev_pool;
     std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> ev_pending;  // (kind, (start, stop))
+    cudaEvent_t ev_iter[2] = {nullptr, nullptr};   // brackets the launches of the last scs_em_iterate
+    double last_iter_ms = 0.0;
     double t_sum[2] = {0, 0};
     int64_t t_cnt[2] = {0, 0};
 };

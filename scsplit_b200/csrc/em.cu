@@ -202,6 +202,8 @@ int scs_em_iterate(scs_ctx* ctx, int n_iter, int check_conv) {
     const int32_t* done = check_conv ? em.done : nullptr;
     std::vector<int32_t> h_done((size_t)em.R);
     const int POLL = 8;   // iterations between host polls of the device-side convergence flags
+    if (!ctx->ev_iter[0]) { SCS_CUDA(cudaEventCreate(&ctx->ev_iter[0])); SCS_CUDA(cudaEventCreate(&ctx->ev_iter[1])); }
+    SCS_CUDA(cudaEventRecord(ctx->ev_iter[0], ctx->stream));
     for (int i = 0; i < n_iter; ++i) {
         SCS_TRY(run_e(ctx, done));
         SCS_TRY(run_m(ctx, done, 1, check_conv));
@@ -213,7 +215,17 @@ int scs_em_iterate(scs_ctx* ctx, int n_iter, int check_conv) {
             if (all) break;
         }
     }
+    SCS_CUDA(cudaEventRecord(ctx->ev_iter[1], ctx->stream));
     SCS_CUDA(cudaStreamSynchronize(ctx->stream));
+    float ms = 0.f;
+    SCS_CUDA(cudaEventElapsedTime(&ms, ctx->ev_iter[0], ctx->ev_iter[1]));
+    ctx->last_iter_ms = (double)ms;
+    return 0;
+}
+
+int scs_em_last_ms(scs_ctx* ctx, double* ms) {
+    SCS_CHECK(ctx && ms, "null argument");
+    *ms = ctx->last_iter_ms;
     return 0;
 }
 

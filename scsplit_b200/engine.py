@@ -27,8 +27,16 @@ def _canonical_csr(m):
 class Engine:
     """Device-resident count matrices + EM state.  All arrays crossing this boundary are host numpy arrays."""
 
-    def __init__(self, ref, alt, device=0):
+    def __init__(self, ref, alt, device=0, canonicalize=True):
+        """ref, alt: scipy CSR V x N (the reference's base_calls_mtx[0:2], scSplit:546-547).
+
+        canonicalize=False skips the host-side scans (the caller guarantees sorted, duplicate-free indices, no
+        explicit zeros and int16/int32/int64 counts); the device build still validates and raises on violation.
+        """
         self.lib = _lib.load()
+        if not canonicalize:
+            self._create(ref, alt, device, ref.data.dtype)
+            return
         ref, alt = _canonical_csr(ref), _canonical_csr(alt)
         if ref.shape != alt.shape:
             raise ValueError("ref and alt matrices differ in shape: %r vs %r" % (ref.shape, alt.shape))
@@ -40,6 +48,15 @@ class Engine:
                 raise ValueError("allele counts must lie in [0, 2^31): never wrapped (scSplit:38-39 uses int16)")
         top = max([int(m.data.max()) for m in (ref, alt) if m.nnz] + [0])
         dt = np.dtype(np.int16 if top <= np.iinfo(np.int16).max else np.int32)   # narrowest transfer type that fits
+        self._create(ref, alt, device, dt)
+
+    def _create(self, ref, alt, device, dt):
+        dt = np.dtype(dt)
+        if dt not in (np.dtype(np.int16), np.dtype(np.int32), np.dtype(np.int64)):
+            raise ValueError("count dtype must be int16, int32 or int64 (got %s)" % dt)
+        if ref.shape != alt.shape:
+            raise ValueError("ref and alt matrices differ in shape: %r vs %r" % (ref.shape, alt.shape))
+        self.V, self.N = int(ref.shape[0]), int(ref.shape[1])
         arrs = []
         for m in (ref, alt):
             arrs += [np.ascontiguousarray(m.indptr, dtype=np.int64), np.ascontiguousarray(m.indices, dtype=np.int32),
@@ -112,6 +129,12 @@ class Engine:
 
     def em_iterate(self, n_iter, check_conv=True):
         check(self.lib.scs_em_iterate(self.h, int(n_iter), 1 if check_conv else 0))
+
+    def last_ms(self):
+        """Device milliseconds (CUDA events on the library's stream) of the last em_iterate call."""
+        ms = ctypes.c_double(0.0)
+        check(self.lib.scs_em_last_ms(self.h, ctypes.byref(ms)))
+        return ms.value
 
     def em_run(self):
         check(self.lib.scs_em_run(self.h))

@@ -1,0 +1,362 @@
+"""Host-side mirror of the reference's `models` class (scSplit:64-336) on top of the CUDA engine.
+
+Same constructor signature, method names, attribute names and attribute types (pandas frames at the seam) as the
+reference, so `run.core` / `run` (scSplit:470-600) can drive it unchanged; all sparse arithmetic runs in
+libscsplit_b200.so.  `core_batched` is the restart driver (scSplit:470-490) with the restarts batched on the GPU.
+
+Quirks of the reference that are kept on purpose (SURVEY.md sections 3.1, 4, 5.1):
+  * E then M inside an iteration: on exit P_s_c / lP_c_s / lP_c_m belong to the last E-step, model_af / lP_s are one
+    M-step ahead (scSplit:159-161);
+  * assignment is a >= 0.99 threshold, not an argmax (scSplit:207);
+  * `reassigned = assigned.copy()` is shallow, so `reassigned[dbl] += found` also grows `assigned[dbl]` (scSplit:234,252);
+  * SNV ids whose FIRST CHARACTER is X, Y or M are dropped from the P/A matrix (scSplit:283);
+  * `dist_variants` is `list(set(...))` (scSplit:334): order is arbitrary.
+"""
+import datetime
+import os
+
+import numpy as np
+import pandas as pd
+
+from . import initialiser
+from ._lib import SCS_L, SCS_LPS, SCS_P, SCS_W
+from .engine import Engine
+
+_ENGINES = {}
+
+
+def get_engine(base_calls_mtx, device=0):
+    """One device-resident copy of the count matrices per (ref, alt) pair, shared by every restart's `models`."""
+    key = (id(base_calls_mtx[0]), id(base_calls_mtx[1]), device)
+    eng = _ENGINES.get(key)
+    if eng is None or eng.h is None:
+        for k in [k for k in _ENGINES if k[2] == device]:
+            _ENGINES.pop(k).close()
+        eng = Engine(base_calls_mtx[0], base_calls_mtx[1], device=device)
+        _ENGINES[key] = eng
+    return eng
+
+
+def release_engines():
+    for k in list(_ENGINES):
+        _ENGINES.pop(k).close()
+
+
+def _log(output, text):
+    with open(os.path.join(output, r'scSplit.log'), 'a') as logfile:
+        logfile.write(text)
+
+
+class models:
+    """Model state of one restart: SNVs, barcodes, P(s|c), log-likelihoods, allele-fraction model, assignments."""
+
+    def __init__(self, base_calls_mtx, num, output, device=0, _defer_seed=False):
+        self.ref_bc_mtx, self.alt_bc_mtx = base_calls_mtx[0], base_calls_mtx[1]
+        self.all_POS, self.barcodes = base_calls_mtx[2].tolist(), base_calls_mtx[3].tolist()
+        self.num = num
+        self.engine = get_engine(base_calls_mtx, device)
+        self.P_s_c = pd.DataFrame(0.0, index=self.barcodes, columns=range(self.num))
+        self.lP_c_s = pd.DataFrame(0.0, index=self.barcodes, columns=range(self.num))
+        self.lP_s = [np.log2(1 / self.num)] * self.num
+        self.assigned, self.reassigned = [], []
+        self.convergence = 0
+        for _ in range(self.num):
+            self.assigned.append([])
+            self.reassigned.append([])
+        self.model_af = pd.DataFrame(0.0, index=self.all_POS, columns=range(self.num))
+        self.pseudo = 1
+        # background alt fraction (scSplit:100-103); (V,1) matrix like the reference's attribute
+        self.k_alt = np.asmatrix(self.engine.kalt()).T
+        # subset / PCA / KMeans initialisation: same np.random and argsort call sequence as scSplit:106-125
+        irows, icols, nrows, ncols = initialiser.trim_subset(self.engine.pattern_counts, len(self.all_POS),
+                                                             len(self.barcodes), self.num)
+        self._labels = initialiser.initial_labels(self.ref_bc_mtx, self.alt_bc_mtx, irows, icols, nrows, ncols, self.num)
+        if self._labels is None:
+            _log(output, 'Not enough informative cells to support model initialization. \n')
+        else:
+            self.initial = []
+            for n in range(self.num):
+                self.initial.append([self.barcodes[col] for col in icols[self._labels[icols] == n]])
+            if not _defer_seed:
+                self._set_af(self.engine.seed_af(self._labels, self.num))
+        self._em_open = False
+
+    # ---- helpers
+    def _set_af(self, P):
+        self.model_af = pd.DataFrame(P, index=self.all_POS, columns=range(self.num))
+
+    def _open_em(self):
+        """Make this model the engine's single active restart, with this object's model_af / lP_s / P_s_c."""
+        eng = self.engine
+        eng.em_begin(np.ascontiguousarray(self.model_af.values, dtype=np.float64))
+        eng.set(SCS_LPS, np.asarray(self.lP_s, dtype=np.float64))
+        self._em_open = True
+
+    def _pull_e(self):
+        eng = self.engine
+        self.lP_c_s = pd.DataFrame(eng.get(SCS_L), index=self.barcodes, columns=range(self.num))
+        self.P_s_c = pd.DataFrame(eng.get(SCS_W), index=self.barcodes, columns=range(self.num))
+
+    def _pull_m(self):
+        eng = self.engine
+        self._set_af(eng.get(SCS_P))
+        self.lP_s = pd.Series(eng.get(SCS_LPS), index=range(self.num))
+
+    # ---- reference API
+    def run_EM(self, output):
+        """Expectation-Maximisation to the reference's stop rule (scSplit:148-162), entirely on the device."""
+        eng = self.engine
+        self._open_em()
+        eng.em_run()
+        it, conv, ll = eng.em_status()
+        iterations = int(it[0])
+        hist = eng.get(4)[:iterations]
+        now = str(datetime.datetime.now())
+        _log(output, ''.join('E-M Iteration ' + str(i + 1) + '   ' + now + '\n' for i in range(iterations)))
+        self.sum_log_likelihood = [1, 2] + hist.tolist()
+        self.lP_c_m = float(ll[0])
+        self._pull_e()
+        self._pull_m()
+        if iterations < 300:
+            self.convergence = 1
+
+    def calculate_cell_likelihood(self):
+        """One E-step (scSplit:165-188) from this object's model_af and lP_s."""
+        self._open_em()
+        self.engine.estep()
+        self._pull_e()
+        self.lP_c_m = self.engine.stats()["ll"]
+
+    def calculate_model_af(self):
+        """One M-step (scSplit:191-198) from this object's P_s_c."""
+        if not self._em_open:
+            self._open_em()
+        self.engine.set(SCS_W, np.ascontiguousarray(self.P_s_c.values, dtype=np.float64))
+        self.engine.mstep()
+        self._pull_m()
+
+    def assign_cells(self):
+        """Cells with P(s|c) >= 0.99, sorted by barcode, per state (scSplit:201-207)."""
+        W = self.P_s_c.values
+        bc = np.asarray(self.barcodes, dtype=object)
+        with np.errstate(invalid='ignore'):
+            hit = W >= 0.99
+        for n in range(self.num):
+            self.assigned[n] = sorted(bc[hit[:, n]].tolist())
+
+    def _index_lists(self, lists):
+        pos = {b: i for i, b in enumerate(self.barcodes)}
+        return [[pos[b] for b in lst] for lst in lists]
+
+    def define_doublet(self):
+        """Doublet state = first argmax_i of sum over assigned cells of L_i(c) with the post-M model (scSplit:210-225)."""
+        weight = np.zeros(len(self.barcodes), dtype=np.int64)
+        for lst in self._index_lists(self.assigned):
+            np.add.at(weight, lst, 1)          # cross_state sums every (cluster j, cell) pair once (scSplit:219-223)
+        if weight.max(initial=0) > 255:
+            raise ValueError('a barcode is listed more than 255 times in `assigned`')
+        scores = self.engine.doublet_scores(self.model_af.values, weight.astype(np.uint8))
+        result = scores.tolist()
+        self.doublet = result.index(max(result))
+
+    def refine_doublets(self, doublets):
+        """Top up the doublet cluster to the expected proportion (scSplit:228-252)."""
+        found = []
+        self.reassigned = self.assigned.copy()
+        if doublets == 0:
+            self.doublet = -1
+        elif doublets > 0:
+            W = self.P_s_c.values
+            with np.errstate(invalid='ignore'):
+                hit = W >= 0.99
+            hit[:, self.doublet] = False                       # rpc = rps.drop(doublet, axis=1), scSplit:244
+            # (W>=0.99) can hold for one state only, so the row sum of rps has a single non-zero term
+            labels = np.where(hit.any(axis=1), hit.argmax(axis=1), -1).astype(np.int32)
+            if (hit.sum(axis=1) > 1).any():
+                raise ValueError('a cell is assigned to two states')
+            score = self.engine.refine_scores(self.model_af.values, labels)
+            lack = len(self.barcodes) * doublets - len(self.assigned[self.doublet])
+            if lack > 0:
+                n = len(self.barcodes)
+                order = pd.Series(score, index=self.barcodes).argsort()       # scSplit:247 (quicksort, like the reference)
+                found = pd.Index(self.barcodes)[order[int(n - lack):n]]
+                fset = set(found.tolist())
+                for k in range(self.num):
+                    if k != self.doublet:
+                        self.reassigned[k] = [x for x in self.assigned[k] if x not in fset]
+                    else:
+                        self.reassigned[k] += found.tolist()
+
+    def distinguishing_alleles(self, pos=[]):
+        """Per-cluster hard allele sums on the GPU, then the reference's variant selection on the host (scSplit:255-336)."""
+        self.dist_variants, ncols = [], self.num - 1 + (self.doublet < 0) * 1
+        # ---- reductions (device): N_ref / N_alt per cluster and the ternary presence/absence code, scSplit:269-282
+        idx_lists = self._index_lists(self.reassigned)
+        N = len(self.barcodes)
+        labels = np.full(N, -1, dtype=np.int32)
+        overlap = False
+        for n, lst in enumerate(idx_lists):
+            arr = np.asarray(lst, dtype=np.int64)
+            if arr.size and (labels[arr] >= 0).any() and (labels[arr][labels[arr] >= 0] != n).any():
+                overlap = True
+            labels[arr] = n
+        if not overlap:
+            _, _, code = self.engine.cluster_counts(labels, self.num)
+        else:   # a barcode listed under two clusters: one masked pass per cluster keeps the membership semantics
+            code = np.zeros((len(self.all_POS), self.num), dtype=np.int8)
+            for n, lst in enumerate(idx_lists):
+                lab = np.full(N, -1, dtype=np.int32)
+                lab[np.asarray(lst, dtype=np.int64)] = 0
+                _, _, c1 = self.engine.cluster_counts(lab, 1)
+                code[:, n] = c1[:, 0]
+        snv = self.all_POS if len(pos) == 0 else [self.all_POS[i] for i in pos]
+        if len(pos) != 0:
+            code = code[np.asarray(pos, dtype=np.int64)]
+        alt_or_ref = pd.DataFrame(code, index=snv, columns=range(self.num))
+        if self.doublet != -1:
+            alt_or_ref = alt_or_ref.drop(self.doublet, axis=1)
+        alt_or_ref = alt_or_ref.astype(np.float64)
+        vals = alt_or_ref.values.copy()
+        vals[code_is(alt_or_ref.values, 0)] = np.nan          # unknown
+        vals[code_is(alt_or_ref.values, -1)] = 0              # REF only -> ALT absent
+        alt_or_ref = pd.DataFrame(vals, index=alt_or_ref.index, columns=alt_or_ref.columns)
+        alt_or_ref = alt_or_ref.loc[[x for x in alt_or_ref.index if x[0] not in ['X', 'Y', 'M']]]
+        # ---- selection (host, tiny): scSplit:284-336
+        self.dist_variants = select_distinguishing(alt_or_ref, self.num, ncols)
+        self.dist_variants = list(set(self.dist_variants))
+        self.dist_matrix = alt_or_ref.reindex(self.dist_variants)
+        self.pa_matrix = alt_or_ref
+
+
+def code_is(values, c):
+    return values == c
+
+
+def _row_var(frame):
+    return frame.var(axis=1)
+
+
+def select_distinguishing(alt_or_ref, num, ncols):
+    """Variant selection of scSplit:284-333 on the ternary matrix (rows = SNVs, columns = non-doublet clusters).
+
+    Greedy search, window by window of the leading `ncols` columns, for rows that are fully observed and together
+    have rank `ncols`; clusters that stay identical on the chosen rows form the next window.  Same numpy / pandas
+    primitives in the same order as the reference so that ties resolve identically.
+    """
+    dist_variants = []
+    submatrix = alt_or_ref.copy()
+    while len(dist_variants) < num - 1:
+        found, todo = [], []
+        while len(found) < ncols - 1:
+            selected = []
+            informative_sub = submatrix[(_row_var(submatrix) > 0) & (submatrix.count(axis=1) == ncols)]
+            if informative_sub.index.values.size > 0:
+                patt = informative_sub.astype(str).values.sum(axis=1)
+                unq = np.unique(patt, return_inverse=True)
+                inverse = np.asarray(unq[1]).ravel()
+                for j in range(len(unq[0])):
+                    members = informative_sub.index[np.flatnonzero(inverse == j)]
+                    # per pattern: the row with most observed clusters in the ORIGINAL matrix, first on ties
+                    selected.append(alt_or_ref.loc[members].count(axis=1).idxmax())
+                subt = submatrix.reindex(np.unique(selected)).iloc[:, 0:ncols]
+                subt = subt.fillna(-1)
+                d = np.linalg.svd(subt, full_matrices=False)[1]
+                if sum(d > 1e-10) >= ncols:
+                    rs = subt.sum(axis=1)
+                    found = [subt[rs == min(rs)].index[0]]
+                    while len(found) < ncols:                      # greedy orthogonal completion
+                        basis = subt.reindex(found).transpose()
+                        svd = np.linalg.svd(basis, full_matrices=False)
+                        U, Vt = svd[0], svd[2]
+                        D = np.asmatrix(svd[1]) if len(found) == 1 else np.diag(svd[1])
+                        colU = U.shape[1]
+                        Vinv = np.linalg.solve(Vt, np.diag([1] * len(Vt)))
+                        Dinv = np.linalg.solve(D, np.diag([1] * len(D)))
+                        proj = np.asmatrix(np.zeros((colU, subt.shape[0])))
+                        for j in range(subt.shape[0]):
+                            row = subt.iloc[j]
+                            for i in range(colU):
+                                proj[i, j] = np.dot(U[:, i], row)
+                        Wc = np.dot(np.dot(Vinv, Dinv), proj)
+                        R = np.dot(basis, Wc)
+                        diff = (subt.transpose() - R).transpose()
+                        dv = diff.var(axis=1)
+                        subt1 = subt.reindex(diff[dv > (0.5 * max(dv))].index)
+                        rs1 = subt1.sum(axis=1)
+                        found += [subt1[rs1 == min(rs1)].index[0]]
+            ncols -= 1
+            submatrix = submatrix.iloc[:, 0:ncols]
+        dist_variants += found
+        if len(found) == 0:
+            with open('scSplit_dist_variants.txt', 'w') as logfile:     # CWD, like scSplit:323
+                logfile.write('Not all clusters can be distinguished. \n')
+            break
+        chosen = alt_or_ref.reindex(dist_variants)
+        for i in range(1, len(alt_or_ref.columns)):
+            for j in range(i):
+                if (chosen.iloc[:, [i, j]].var(axis=1)).sum() == 0:
+                    todo.extend([i, j])
+        submatrix = alt_or_ref.iloc[:, sorted(set(todo))]
+        ncols = len(submatrix.columns)
+    return dist_variants
+
+
+def core_batched(base_calls_mtx, num, output, ems, device=0, chunk=64):
+    """Restart driver (run.core, scSplit:470-490): `ems` restarts, first strictly greatest LL wins.
+
+    The R initialisations are generated serially on the host first -- they share one `np.random` stream and never read
+    EM results (hard part 6) -- then the R EM runs execute as one batch on the GPU.
+    Returns (model, chosen_index); raises ValueError like scSplit:486 when no restart could be initialised.
+    """
+    max_likelihood = -1e50
+    built = []
+    for i in range(ems):
+        _log(output, 'Repeat ' + str(i + 1) + ' of ' + str(ems) + ' in demultiplexing ' + str(num) +
+             ' subpopulations (including doublets if expected)' + '\n')
+        _log(output, 'Building model... \n')
+        built.append(models(base_calls_mtx, num, output, device=device, _defer_seed=True))
+    model = built[-1]
+    eng = model.engine
+    live = [i for i, m in enumerate(built) if m._labels is not None]
+    best = None
+    for c0 in range(0, len(live), chunk):
+        part = live[c0:c0 + chunk]
+        labels = np.stack([built[i]._labels for i in part])
+        P0 = eng.seed_af(labels, num)
+        if P0.ndim == 2:
+            P0 = P0[None]
+        keep = [r for r in range(len(part)) if P0[r].sum() > 0]           # scSplit:478 gate
+        if not keep:
+            continue
+        eng.em_begin(np.ascontiguousarray(P0[keep]))
+        eng.em_run()
+        it, conv, ll = eng.em_status()
+        for r, pr in enumerate(keep):
+            i = part[pr]
+            m = built[i]
+            m._set_af(P0[pr])
+            iterations = int(it[r])
+            now = str(datetime.datetime.now())
+            _log(output, ''.join('E-M Iteration ' + str(t + 1) + '   ' + now + '\n' for t in range(iterations)))
+            m.lP_c_m = float(ll[r])
+            m.convergence = int(iterations < 300)
+            _log(output, 'Model Log-Likelihood = ' + str(m.lP_c_m) + '\n')
+            if m.lP_c_m > max_likelihood:
+                max_likelihood = m.lP_c_m
+                hist = eng.get(4, r)[:iterations]
+                m.sum_log_likelihood = [1, 2] + hist.tolist()
+                m.lP_c_s = pd.DataFrame(eng.get(SCS_L, r), index=m.barcodes, columns=range(num))
+                m.P_s_c = pd.DataFrame(eng.get(SCS_W, r), index=m.barcodes, columns=range(num))
+                m._set_af(eng.get(SCS_P, r))
+                m.lP_s = pd.Series(eng.get(SCS_LPS, r), index=range(num))
+                m.assign_cells()
+                best = i
+    if max_likelihood == -1e50:
+        raise ValueError('Model not converged, please allow more repeats!')
+    chosen = built[best]
+    # the reference grafts four attributes of the best restart onto the LAST model object (scSplit:488)
+    model.assigned, model.initial, model.model_af, model.P_s_c = chosen.assigned, chosen.initial, chosen.model_af, chosen.P_s_c
+    if model is not chosen and not hasattr(model, 'lP_c_m'):
+        model.lP_c_m = chosen.lP_c_m
+    print('Repeat ' + str(best + 1) + ' was chosen.')
+    return model, best

@@ -51,3 +51,17 @@ def golden(request):
     d = load_golden(request.param)
     d["name"] = request.param
     return d
+
+
+def scipy_count_fn(ref, alt):
+    """Host stand-in for Engine.pattern_counts (scs_pattern_counts) so the initialiser's loop logic can be tested on CPU."""
+    U = ((ref != 0).astype(np.int8) + (alt != 0).astype(np.int8)).tocsr()
+    U.data[:] = 1
+    U = U.astype(np.int64)
+    Ut = U.T.tocsr()
+
+    def fn(keep_r, keep_c):
+        kr = np.ones(U.shape[0], dtype=np.int64) if keep_r is None else keep_r.astype(np.int64)
+        kc = np.ones(U.shape[1], dtype=np.int64) if keep_c is None else keep_c.astype(np.int64)
+        return U @ kc, Ut @ kr
+    return fn
