@@ -48,9 +48,9 @@ def main():
                 log = f.read()
             with open(os.path.join(tmp, "scSplit_result.csv")) as f:
                 head = f.readline()
-            out = dict(params=np.array([str(c)]), result_barcode=res["Barcode"].values.astype(str), result_cluster=res["Cluster"].values.astype(str),
-                       result_header=np.array([head]), psc=psc.values, psc_index=psc.index.values.astype(str), psc_columns=psc.columns.values.astype(str),
-                       pa=pa.values.astype(np.float64), pa_index=pa.index.values.astype(str), pa_columns=pa.columns.values.astype(str),
+            out = dict(params=np.array([str(c)]), result_barcode=np.array(res["Barcode"].tolist(), dtype=str), result_cluster=np.array(res["Cluster"].tolist(), dtype=str),
+                       result_header=np.array([head]), psc=psc.values, psc_index=np.array(list(map(str, psc.index.tolist())), dtype=str), psc_columns=np.array(list(map(str, psc.columns.tolist())), dtype=str),
+                       pa=pa.values.astype(np.float64), pa_index=np.array(list(map(str, pa.index.tolist())), dtype=str), pa_columns=np.array(list(map(str, pa.columns.tolist())), dtype=str),
                        dist_variants=np.array(sorted(dv)), log=np.array([log]))
             np.savez_compressed(os.path.join(ROOT, "tests", "golden", name + ".npz"), **out)
             print(name, res["Cluster"].value_counts().to_dict(), len(dv), "variants")

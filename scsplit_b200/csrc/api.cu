@@ -69,6 +69,11 @@ int scs_create(scs_ctx** out, int device, int64_t V, int64_t N, const int64_t* r
     ctx->N = N;
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        uint64_t keep = ~0ull;   // keep freed blocks cached: contexts are created once per restart batch in `scSplit run`
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
         set_error("cudaStreamCreate failed");
         delete ctx;
@@ -91,11 +96,15 @@ int scs_destroy(scs_ctx* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     em_free(ctx);
     comm_destroy(ctx);
-    free_stream(ctx->E);
-    free_stream(ctx->M);
-    dev_free(ctx->sum_alt);
-    dev_free(ctx->sum_ref);
-    dev_free(ctx->kalt);
+    free_stream(ctx, ctx->E);
+    free_stream(ctx, ctx->M);
+    free_tiled(ctx, ctx->TE);
+    free_tiled(ctx, ctx->TM);
+    dev_free(ctx, ctx->part);
+    dev_free(ctx, ctx->sum_alt);
+    dev_free(ctx, ctx->sum_ref);
+    dev_free(ctx, ctx->kalt);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (auto& p : ctx->ev_pending) { cudaEventDestroy(p.second.first); cudaEventDestroy(p.second.second); }
     for (auto e : ctx->ev_pool) cudaEventDestroy(e);
     for (auto e : ctx->ev_iter) if (e) cudaEventDestroy(e);

@@ -35,13 +35,16 @@ void set_error(const char* fmt, ...);
         if (_r) return _r;   \
     } while (0)
 
-// Entry code word of both orientations: (index << 2) | (sel << 1) | dup
-//   sel = 0: alt-allele entry, 1: ref-allele entry
-//   dup = 1: a ref entry whose (SNV, cell) also has an alt entry (skipped by pattern counts)
-// cell-major ("E") stream: index = SNV; gather row of the log table = code >> 1 = 2*v + sel
-// SNV-major  ("M") stream: index = cell; gather row of W          = code >> 2 = c
+// Entry code word of both orientations: (index << 1) | dup
+//   dup = 1: a ref-allele entry whose (SNV, cell) also has an alt-allele entry (skipped by pattern counts)
+// "sel-major" numbering: pseudo-row / gather row g = sel * V + v with sel = 0 (alt) or 1 (ref).
+// cell-major ("E") stream: rows = N cells, index = g; gather row of the log table T[2V][KP] = code >> 1
+//                          (T[v] = log2 P[v], T[V+v] = log2(1-P[v])); entries of a cell ascend in g.
+// SNV-major  ("M") stream: rows = 2V pseudo-rows g (alt rows first), index = cell; gather row of W[N][KP] = code >> 1;
+//                          entries of a pseudo-row ascend in cell.  S[g] = sum of W rows: S[v] = altW, S[V+v] = refW.
 struct Stream {
-    int64_t nrows = 0;     // E: N cells;  M: 2V pseudo-rows (2v = alt entries of SNV v, 2v+1 = ref entries)
+    int64_t nrows = 0;
+    int64_t xrows = 0;     // rows of the gathered operand (E: 2V, M: N)
     int64_t n_light = 0;   // entries with count == 1 (4 bytes each)
     int64_t n_heavy = 0;   // entries with count  > 1 (8 bytes each)
     int64_t* lptr = nullptr;   // [nrows+1]
@@ -49,6 +52,18 @@ struct Stream {
     uint32_t* lcode = nullptr; // [n_light]
     uint32_t* hcode = nullptr; // [n_heavy]
     int32_t* hcnt = nullptr;   // [n_heavy]
+};
+
+// Tile-major copy of a stream's count-1 entries for one table width KP (built on first use, DESIGN.md "v2"):
+// the gathered operand is cut into tiles of TR rows that fit shared memory; unit u = tile * nrows + row owns the
+// entries tcode[tptr[u] .. tptr[u+1]) of `row` that fall into `tile`, stored as 16-bit row offsets inside the tile.
+struct TiledStream {
+    int KP = 0;
+    int TR = 0;            // operand rows per tile
+    int ntiles = 0;
+    int64_t nunits = 0;    // ntiles * nrows
+    int64_t* tptr = nullptr;   // [nunits + 1]
+    uint16_t* tcode = nullptr; // [n_light]
 };
 
 struct NcclApi;  // dlopen'ed function table (comm.cu)
@@ -81,6 +96,9 @@ struct scs_ctx {
     int64_t device_bytes = 0;
     scs::Stream E;   // cell-major
     scs::Stream M;   // SNV-major (2V pseudo-rows)
+    scs::TiledStream TE, TM;   // tile-major copies for the current KP
+    double* part = nullptr;    // per-(tile,row) partial sums of the tiled SpMM
+    int64_t part_doubles = 0;
     int64_t* sum_alt = nullptr;  // [V] integer row sums (global after comm_init)
     int64_t* sum_ref = nullptr;  // [V]
     double* kalt = nullptr;      // [V]
@@ -102,17 +120,19 @@ struct scs_ctx {
 
 namespace scs {
 
+// All device memory comes from the device's default stream-ordered pool on the context's stream (the release
+// threshold is raised in scs_create), so creating and destroying contexts back to back does not pay cudaMalloc.
 template <typename T>
 int dev_alloc(scs_ctx* ctx, T** p, int64_t n) {
     *p = nullptr;
     if (n <= 0) n = 1;
-    SCS_CUDA(cudaMalloc((void**)p, (size_t)n * sizeof(T)));
+    SCS_CUDA(cudaMallocAsync((void**)p, (size_t)n * sizeof(T), ctx->stream));
     ctx->device_bytes += n * (int64_t)sizeof(T);
     return 0;
 }
 template <typename T>
-void dev_free(T*& p) {
-    if (p) cudaFree(p);
+void dev_free(scs_ctx* ctx, T*& p) {
+    if (p) cudaFreeAsync(p, ctx->stream);
     p = nullptr;
 }
 
@@ -121,7 +141,9 @@ inline int round_even(int k) { return (k + 1) & ~1; }
 // layout.cu
 int build_layout(scs_ctx* ctx, const int64_t* ref_indptr, const int32_t* ref_indices, const void* ref_data,
                  const int64_t* alt_indptr, const int32_t* alt_indices, const void* alt_data, int data_bytes);
-void free_stream(Stream& s);
+void free_stream(scs_ctx* ctx, Stream& s);
+void free_tiled(scs_ctx* ctx, TiledStream& t);
+int build_tiled(scs_ctx* ctx, const Stream& s, TiledStream& t, int KP, int TR);
 
 // em.cu
 int launch_spmm(scs_ctx* ctx, int kind /*0=E,1=M*/, int KP, int R, const double* X, int64_t x_stride, double* Y,

@@ -55,14 +55,8 @@ int launch_spmm(scs_ctx* ctx, int kind, int KP, int R, const double* X, int64_t 
     } else {
         const int WPB = 8;
         dim3 grid((unsigned)((s.nrows + WPB - 1) / WPB), (unsigned)R);
-        SCS_DISPATCH_KP(KP, {
-            if (kind == 0)
-                k_spmm_rows<KPc, 1><<<grid, WPB * 32, 0, ctx->stream>>>(s.nrows, s.lptr, s.lcode, s.hptr, s.hcode, s.hcnt, X,
-                                                                     x_stride, Y, y_stride, done);
-            else
-                k_spmm_rows<KPc, 2><<<grid, WPB * 32, 0, ctx->stream>>>(s.nrows, s.lptr, s.lcode, s.hptr, s.hcode, s.hcnt, X,
-                                                                     x_stride, Y, y_stride, done);
-        });
+        SCS_DISPATCH_KP(KP, (k_spmm_rows<KPc><<<grid, WPB * 32, 0, ctx->stream>>>(s.nrows, s.lptr, s.lcode, s.hptr, s.hcode, s.hcnt, X,
+                                                                                  x_stride, Y, y_stride, done)));
         ctx->launches++;
     }
     SCS_TRY(timing_end(ctx, kind, ea, eb));
@@ -70,10 +64,44 @@ int launch_spmm(scs_ctx* ctx, int kind, int KP, int R, const double* X, int64_t 
     return 0;
 }
 
+bool tiled_supported(scs_ctx*, int, int KP) { return KP >= 2 && KP <= 32 && (KP % 2) == 0; }
+
+int launch_spmm_tiled(scs_ctx* ctx, int kind, int KP, int R, const double* X, int64_t x_stride, double* Y, int64_t y_stride,
+                      const int32_t* done) {
+    const Stream& s = kind == 0 ? ctx->E : ctx->M;
+    TiledStream& t = kind == 0 ? ctx->TE : ctx->TM;
+    const int TR = tile_rows_for(KP, s.xrows);
+    if (t.KP != KP || t.TR != TR) SCS_TRY(build_tiled(ctx, s, t, KP, TR));
+    const int64_t part_stride = t.nunits * KP;
+    if (ctx->part_doubles < part_stride * R) {
+        SCS_CUDA(cudaStreamSynchronize(ctx->stream));
+        dev_free(ctx, ctx->part);
+        SCS_TRY(dev_alloc(ctx, &ctx->part, part_stride * R));
+        ctx->part_doubles = part_stride * R;
+    }
+    const size_t smem = ((((size_t)(TR + 1) * KP * 8) + 127) & ~(size_t)127) + 16;
+    const int ctas = ctx->sm_count > 0 ? ctx->sm_count : 148;
+    dim3 grid((unsigned)ctas, (unsigned)R);
+    dim3 cgrid((unsigned)((s.nrows * (KP / 2) + 255) / 256), (unsigned)R);
+    SCS_DISPATCH_KP(KP, {
+        static bool attr_set = false;
+        if (!attr_set) {
+            SCS_CUDA(cudaFuncSetAttribute(k_spmm_tiled<KPc>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_BYTES + 1024));
+            attr_set = true;
+        }
+        k_spmm_tiled<KPc><<<grid, TILED_THREADS, smem, ctx->stream>>>(s.nrows, t.ntiles, TR, s.xrows, t.tptr, t.tcode, X, x_stride,
+                                                                   ctx->part, part_stride, done);
+        k_spmm_combine<KPc><<<cgrid, 256, 0, ctx->stream>>>(s.nrows, t.ntiles, ctx->part, part_stride, s.hptr, s.hcode, s.hcnt, X,
+                                                          x_stride, Y, y_stride, done);
+    });
+    ctx->launches += 2;
+    return 0;
+}
+
 int em_free(scs_ctx* ctx) {
     EmState& em = ctx->em;
-    dev_free(em.T); dev_free(em.P); dev_free(em.L); dev_free(em.W); dev_free(em.stats); dev_free(em.lps);
-    dev_free(em.partial); dev_free(em.hist); dev_free(em.ll_prev); dev_free(em.iters); dev_free(em.done);
+    dev_free(ctx, em.T); dev_free(ctx, em.P); dev_free(ctx, em.L); dev_free(ctx, em.W); dev_free(ctx, em.stats); dev_free(ctx, em.lps);
+    dev_free(ctx, em.partial); dev_free(ctx, em.hist); dev_free(ctx, em.ll_prev); dev_free(ctx, em.iters); dev_free(ctx, em.done);
     em = EmState();
     return 0;
 }

@@ -17,7 +17,7 @@ __device__ __forceinline__ double2 ldg2(const double* p) { return __ldg(reinterp
 // ---------------------------------------------------------------------------------------------------------
 // v1: one warp per row, lanes stride over the row's entries, gathers straight from global memory (L1/L2).
 // ---------------------------------------------------------------------------------------------------------
-template <int KP, int SHIFT>
+template <int KP>
 __global__ void __launch_bounds__(256) k_spmm_rows(int64_t nrows, const int64_t* __restrict__ lptr,
                                                    const uint32_t* __restrict__ lcode, const int64_t* __restrict__ hptr,
                                                    const uint32_t* __restrict__ hcode, const int32_t* __restrict__ hcnt,
@@ -38,8 +38,8 @@ __global__ void __launch_bounds__(256) k_spmm_rows(int64_t nrows, const int64_t*
     int64_t e = lb + lane;
     for (; e + 32 < le; e += 64) {  // two independent gathers in flight per lane
         const uint32_t c0 = __ldg(lcode + e), c1 = __ldg(lcode + e + 32);
-        const double* x0 = X + (int64_t)(c0 >> SHIFT) * KP;
-        const double* x1 = X + (int64_t)(c1 >> SHIFT) * KP;
+        const double* x0 = X + (int64_t)(c0 >> 1) * KP;
+        const double* x1 = X + (int64_t)(c1 >> 1) * KP;
         double2 t0[KP / 2], t1[KP / 2];
 #pragma unroll
         for (int j = 0; j < KP / 2; ++j) { t0[j] = ldg2(x0 + 2 * j); t1[j] = ldg2(x1 + 2 * j); }
@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(256) k_spmm_rows(int64_t nrows, const int64_t*
     }
     if (e < le) {
         const uint32_t c0 = __ldg(lcode + e);
-        const double* x0 = X + (int64_t)(c0 >> SHIFT) * KP;
+        const double* x0 = X + (int64_t)(c0 >> 1) * KP;
 #pragma unroll
         for (int j = 0; j < KP / 2; ++j) { double2 t = ldg2(x0 + 2 * j); acc[2 * j] += t.x; acc[2 * j + 1] += t.y; }
     }
@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(256) k_spmm_rows(int64_t nrows, const int64_t*
     for (int64_t h = hb + lane; h < he; h += 32) {
         const uint32_t c0 = __ldg(hcode + h);
         const double cnt = (double)__ldg(hcnt + h);
-        const double* x0 = X + (int64_t)(c0 >> SHIFT) * KP;
+        const double* x0 = X + (int64_t)(c0 >> 1) * KP;
 #pragma unroll
         for (int j = 0; j < KP / 2; ++j) {
             double2 t = ldg2(x0 + 2 * j);
@@ -198,7 +198,7 @@ static __global__ void __launch_bounds__(256) k_reduce_stats(int KP, const doubl
     }
 }
 
-// P = (altW + k_alt) / ((altW + refW) + 1);  T[2v] = log2 P, T[2v+1] = log2(1 - P)   (scSplit:196, 176-177)
+// P = (altW + k_alt) / ((altW + refW) + 1);  T[v] = log2 P, T[V+v] = log2(1 - P)   (scSplit:196, 176-177)
 static __global__ void __launch_bounds__(256) k_finalize(int64_t V, int K, int KP, const double* __restrict__ stats, int64_t stats_stride,
                                                   const double* __restrict__ kalt, double* __restrict__ P, double* __restrict__ T,
                                                   const int32_t* __restrict__ done) {
@@ -211,15 +211,15 @@ static __global__ void __launch_bounds__(256) k_finalize(int64_t V, int K, int K
     const double* S = stats + (int64_t)r * stats_stride;
     double p = 0.0, lp = 0.0, lq = 0.0;
     if (k < K) {
-        const double a = S[(2 * v) * KP + k], rf = S[(2 * v + 1) * KP + k];
+        const double a = S[v * KP + k], rf = S[(V + v) * KP + k];
         p = (a + kalt[v]) / ((a + rf) + 1.0);
         lp = log2(p);
         lq = log2(1.0 - p);
     }
     P[((int64_t)r * V + v) * KP + k] = p;
     if (T) {
-        T[((int64_t)r * 2 * V + 2 * v) * KP + k] = lp;
-        T[((int64_t)r * 2 * V + 2 * v + 1) * KP + k] = lq;
+        T[((int64_t)r * 2 * V + v) * KP + k] = lp;
+        T[((int64_t)r * 2 * V + V + v) * KP + k] = lq;
     }
 }
 
@@ -236,8 +236,8 @@ static __global__ void __launch_bounds__(256) k_tables_from_P(int64_t V, int K, 
         lp = log2(p);
         lq = log2(1.0 - p);
     }
-    T[((int64_t)r * 2 * V + 2 * v) * KP + k] = lp;
-    T[((int64_t)r * 2 * V + 2 * v + 1) * KP + k] = lq;
+    T[((int64_t)r * 2 * V + v) * KP + k] = lp;
+    T[((int64_t)r * 2 * V + V + v) * KP + k] = lq;
 }
 
 // numpy's pairwise add.reduce for n < 128 contiguous doubles (what pandas Series.sum() runs for K values)

@@ -17,14 +17,14 @@ __device__ __forceinline__ int64_t load_count(const void* data, int64_t i, int b
     return ((const int64_t*)data)[i];
 }
 
-// one warp per pseudo-row pr = 2v + sel: number of count==1 / count>1 entries and the integer row sum
+// one warp per pseudo-row pr = sel*V + v: number of count==1 / count>1 entries and the integer row sum
 __global__ void k_count_rows(int64_t V, const int64_t* a_ptr, const void* a_val, const int64_t* r_ptr, const void* r_val,
                              int bytes, int64_t* cntL, int64_t* cntH, int64_t* rowsum, int* err) {
     int64_t pr = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     int lane = threadIdx.x & 31;
     if (pr >= 2 * V) return;
-    int64_t v = pr >> 1;
-    int sel = (int)(pr & 1);
+    const int sel = pr >= V ? 1 : 0;
+    const int64_t v = pr - (int64_t)sel * V;
     const int64_t* ptr = sel ? r_ptr : a_ptr;
     const void* val = sel ? r_val : a_val;
     int64_t b = ptr[v], e = ptr[v + 1];
@@ -58,8 +58,8 @@ __global__ void k_fill_M(int64_t V, int64_t N, const int64_t* a_ptr, const int32
     int64_t pr = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     int lane = threadIdx.x & 31;
     if (pr >= 2 * V) return;
-    int64_t v = pr >> 1;
-    int sel = (int)(pr & 1);
+    const int sel = pr >= V ? 1 : 0;
+    const int64_t v = pr - (int64_t)sel * V;
     const int64_t* ptr = sel ? r_ptr : a_ptr;
     const int32_t* idx = sel ? r_idx : a_idx;
     const void* val = sel ? r_val : a_val;
@@ -87,8 +87,8 @@ __global__ void k_fill_M(int64_t V, int64_t N, const int64_t* a_ptr, const int32
         bool light = valid && c == 1, heavy = valid && c > 1;
         unsigned ml = __ballot_sync(0xffffffffu, light), mh = __ballot_sync(0xffffffffu, heavy);
         unsigned lt = (1u << lane) - 1u;
-        uint32_t codeM = ((uint32_t)cell << 2) | ((uint32_t)sel << 1) | dup;
-        uint32_t codeE = ((uint32_t)v << 2) | ((uint32_t)sel << 1) | dup;
+        uint32_t codeM = ((uint32_t)cell << 1) | dup;
+        uint32_t codeE = ((uint32_t)pr << 1) | dup;
         if (light) {
             int64_t p = lpos + __popc(ml & lt);
             lcode[p] = codeM;
@@ -129,8 +129,8 @@ __global__ void k_split_heavy(const uint64_t* hval, int64_t n, uint32_t* hcode, 
 __global__ void k_row_sums(int64_t V, const int64_t* rowsum, int64_t* sum_alt, int64_t* sum_ref) {
     int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= V) return;
-    sum_alt[v] = rowsum[2 * v];
-    sum_ref[v] = rowsum[2 * v + 1];
+    sum_alt[v] = rowsum[v];
+    sum_ref[v] = rowsum[V + v];
 }
 
 // k_alt, scSplit:100-103: N_alt / (N_ref + N_alt) with N_x = row sum + 1; integer-exact operands
@@ -141,12 +141,12 @@ __global__ void k_kalt(int64_t V, const int64_t* sum_alt, const int64_t* sum_ref
     kalt[v] = (double)na / (double)(nr + na);
 }
 
-void free_stream(Stream& s) {
-    dev_free(s.lptr);
-    dev_free(s.hptr);
-    dev_free(s.lcode);
-    dev_free(s.hcode);
-    dev_free(s.hcnt);
+void free_stream(scs_ctx* ctx, Stream& s) {
+    dev_free(ctx, s.lptr);
+    dev_free(ctx, s.hptr);
+    dev_free(ctx, s.lcode);
+    dev_free(ctx, s.hcode);
+    dev_free(ctx, s.hcnt);
 }
 
 static int bits_for(int64_t n) {
@@ -163,10 +163,10 @@ static int stable_sort_by_cell(scs_ctx* ctx, const uint32_t* kin, uint32_t* kout
     int eb = bits_for(nrows);
     SCS_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, kin, kout, vin, vout, n, 0, eb, ctx->stream));
     void* tmp = nullptr;
-    SCS_CUDA(cudaMalloc(&tmp, tb ? tb : 1));
+    SCS_CUDA(cudaMallocAsync(&tmp, tb ? tb : 1, ctx->stream));
     cudaError_t e = cub::DeviceRadixSort::SortPairs(tmp, tb, kin, kout, vin, vout, n, 0, eb, ctx->stream);
     cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
-    cudaFree(tmp);
+    cudaFreeAsync(tmp, ctx->stream);
     SCS_CUDA(e);
     SCS_CUDA(e2);
     ctx->launches += 4;
@@ -178,13 +178,88 @@ static int inclusive_scan_into_ptr(scs_ctx* ctx, const int64_t* cnt, int64_t* pt
     size_t tb = 0;
     SCS_CUDA(cub::DeviceScan::InclusiveSum(nullptr, tb, cnt, ptr + 1, n, ctx->stream));
     void* tmp = nullptr;
-    SCS_CUDA(cudaMalloc(&tmp, tb ? tb : 1));
+    SCS_CUDA(cudaMallocAsync(&tmp, tb ? tb : 1, ctx->stream));
     cudaError_t e = cub::DeviceScan::InclusiveSum(tmp, tb, cnt, ptr + 1, n, ctx->stream);
     cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
-    cudaFree(tmp);
+    cudaFreeAsync(tmp, ctx->stream);
     SCS_CUDA(e);
     SCS_CUDA(e2);
     ctx->launches += 2;
+    return 0;
+}
+
+// ---- tile-major copy of the count-1 entries (v2 SpMM) -----------------------------------------------------
+
+__device__ __forceinline__ int64_t row_lower_bound(const uint32_t* __restrict__ code, int64_t b, int64_t e, int64_t key) {
+    while (b < e) {   // first position whose gather row (code >> 1) is >= key
+        int64_t mid = (b + e) >> 1;
+        if ((int64_t)(code[mid] >> 1) < key) b = mid + 1; else e = mid;
+    }
+    return b;
+}
+
+// one thread per unit u = tile * nrows + row: entries of `row` inside `tile`, padded to an even count
+__global__ void k_tile_counts(int64_t nrows, int ntiles, int TR, const int64_t* __restrict__ lptr, const uint32_t* __restrict__ lcode,
+                              int64_t* __restrict__ cnt) {
+    const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= nrows * ntiles) return;
+    const int64_t t = u / nrows, row = u - t * nrows;
+    const int64_t b = lptr[row], e = lptr[row + 1];
+    const int64_t lo = row_lower_bound(lcode, b, e, t * TR), hi = row_lower_bound(lcode, b, e, (t + 1) * (int64_t)TR);
+    cnt[u] = ((hi - lo) + 1) & ~(int64_t)1;
+}
+
+// one warp per row: scatter its entries to their units as 16-bit in-tile offsets; odd units get one zero-row pad
+__global__ void k_tile_scatter(int64_t nrows, int ntiles, int TR, const int64_t* __restrict__ lptr, const uint32_t* __restrict__ lcode,
+                               const int64_t* __restrict__ tptr, uint16_t* __restrict__ tcode) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= nrows) return;
+    const int64_t b = lptr[row], e = lptr[row + 1];
+    for (int64_t i = b + lane; i < e; i += 32) {
+        const int64_t g = (int64_t)(lcode[i] >> 1);
+        const int64_t t = g / TR;
+        const int64_t lo = row_lower_bound(lcode, b, e, t * TR);
+        tcode[tptr[t * nrows + row] + (i - lo)] = (uint16_t)(g - t * TR);
+    }
+    for (int64_t t = lane; t < ntiles; t += 32) {   // pad slot: the last position of a unit whose true count is odd
+        const int64_t lo = row_lower_bound(lcode, b, e, t * TR), hi = row_lower_bound(lcode, b, e, (t + 1) * (int64_t)TR);
+        if ((hi - lo) & 1) tcode[tptr[t * nrows + row] + (hi - lo)] = (uint16_t)TR;
+    }
+}
+
+void free_tiled(scs_ctx* ctx, TiledStream& t) {
+    dev_free(ctx, t.tptr);
+    dev_free(ctx, t.tcode);
+    t = TiledStream();
+}
+
+int build_tiled(scs_ctx* ctx, const Stream& s, TiledStream& t, int KP, int TR) {
+    free_tiled(ctx, t);
+    t.KP = KP;
+    t.TR = TR;
+    t.ntiles = (int)((s.xrows + TR - 1) / TR);
+    t.nunits = (int64_t)t.ntiles * s.nrows;
+    cudaStream_t st = ctx->stream;
+    SCS_TRY(dev_alloc(ctx, &t.tptr, t.nunits + 1));
+    SCS_CUDA(cudaMemsetAsync(t.tptr, 0, sizeof(int64_t), st));
+    k_tile_counts<<<(unsigned)((t.nunits + 255) / 256), 256, 0, st>>>(s.nrows, t.ntiles, TR, s.lptr, s.lcode, t.tptr + 1);
+    ctx->launches++;
+    size_t tb = 0;
+    SCS_CUDA(cub::DeviceScan::InclusiveSum(nullptr, tb, t.tptr + 1, t.tptr + 1, t.nunits, st));
+    void* tmp = nullptr;
+    SCS_CUDA(cudaMallocAsync(&tmp, tb ? tb : 1, ctx->stream));
+    cudaError_t e = cub::DeviceScan::InclusiveSum(tmp, tb, t.tptr + 1, t.tptr + 1, t.nunits, st);
+    int64_t total = 0;
+    cudaError_t e2 = cudaMemcpyAsync(&total, t.tptr + t.nunits, sizeof(int64_t), cudaMemcpyDeviceToHost, st);
+    cudaError_t e3 = cudaStreamSynchronize(st);
+    cudaFreeAsync(tmp, ctx->stream);
+    SCS_CUDA(e); SCS_CUDA(e2); SCS_CUDA(e3);
+    ctx->launches += 2;
+    SCS_TRY(dev_alloc(ctx, &t.tcode, total + 2));
+    k_tile_scatter<<<(unsigned)((s.nrows + 7) / 8), 256, 0, st>>>(s.nrows, t.ntiles, TR, s.lptr, s.lcode, t.tptr, t.tcode);
+    ctx->launches++;
+    SCS_CUDA(cudaGetLastError());
     return 0;
 }
 
@@ -193,7 +268,7 @@ int build_layout(scs_ctx* ctx, const int64_t* ref_indptr, const int32_t* ref_ind
     const int64_t V = ctx->V, N = ctx->N;
     SCS_CHECK(data_bytes == 2 || data_bytes == 4 || data_bytes == 8, "data_bytes must be 2, 4 or 8 (got %d)", data_bytes);
     SCS_CHECK(V > 0 && N > 0, "empty matrix: V=%lld N=%lld", (long long)V, (long long)N);
-    SCS_CHECK(V < (1LL << 29) && N < (1LL << 29), "V and N must be below 2^29");
+    SCS_CHECK(V < (1LL << 29) && N < (1LL << 30), "V must be below 2^29 and N below 2^30");
     SCS_CHECK(ref_indptr[0] == 0 && alt_indptr[0] == 0, "indptr[0] must be 0");
     const int64_t nR = ref_indptr[V], nA = alt_indptr[V];
     SCS_CHECK(nR >= 0 && nA >= 0, "negative nnz");
@@ -205,12 +280,12 @@ int build_layout(scs_ctx* ctx, const int64_t* ref_indptr, const int32_t* ref_ind
     int64_t *a_ptr = nullptr, *r_ptr = nullptr;
     int32_t *a_idx = nullptr, *r_idx = nullptr;
     void *a_val = nullptr, *r_val = nullptr;
-    SCS_CUDA(cudaMalloc((void**)&a_ptr, (V + 1) * sizeof(int64_t)));
-    SCS_CUDA(cudaMalloc((void**)&r_ptr, (V + 1) * sizeof(int64_t)));
-    SCS_CUDA(cudaMalloc((void**)&a_idx, (size_t)(nA ? nA : 1) * 4));
-    SCS_CUDA(cudaMalloc((void**)&r_idx, (size_t)(nR ? nR : 1) * 4));
-    SCS_CUDA(cudaMalloc(&a_val, (size_t)(nA ? nA : 1) * data_bytes));
-    SCS_CUDA(cudaMalloc(&r_val, (size_t)(nR ? nR : 1) * data_bytes));
+    SCS_CUDA(cudaMallocAsync((void**)&a_ptr, (V + 1) * sizeof(int64_t), ctx->stream));
+    SCS_CUDA(cudaMallocAsync((void**)&r_ptr, (V + 1) * sizeof(int64_t), ctx->stream));
+    SCS_CUDA(cudaMallocAsync((void**)&a_idx, (size_t)(nA ? nA : 1) * 4, ctx->stream));
+    SCS_CUDA(cudaMallocAsync((void**)&r_idx, (size_t)(nR ? nR : 1) * 4, ctx->stream));
+    SCS_CUDA(cudaMallocAsync(&a_val, (size_t)(nA ? nA : 1) * data_bytes, ctx->stream));
+    SCS_CUDA(cudaMallocAsync(&r_val, (size_t)(nR ? nR : 1) * data_bytes, ctx->stream));
     SCS_CUDA(cudaMemcpyAsync(a_ptr, alt_indptr, (V + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
     SCS_CUDA(cudaMemcpyAsync(r_ptr, ref_indptr, (V + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
     if (nA) SCS_CUDA(cudaMemcpyAsync(a_idx, alt_indices, (size_t)nA * 4, cudaMemcpyHostToDevice, st));
@@ -220,18 +295,19 @@ int build_layout(scs_ctx* ctx, const int64_t* ref_indptr, const int32_t* ref_ind
 
     int* err = nullptr;
     unsigned long long* ndup = nullptr;
-    SCS_CUDA(cudaMalloc((void**)&err, sizeof(int)));
-    SCS_CUDA(cudaMalloc((void**)&ndup, sizeof(unsigned long long)));
+    SCS_CUDA(cudaMallocAsync((void**)&err, sizeof(int), ctx->stream));
+    SCS_CUDA(cudaMallocAsync((void**)&ndup, sizeof(unsigned long long), ctx->stream));
     SCS_CUDA(cudaMemsetAsync(err, 0, sizeof(int), st));
     SCS_CUDA(cudaMemsetAsync(ndup, 0, sizeof(unsigned long long), st));
 
     // ---- SNV-major stream (2V pseudo-rows)
     Stream& M = ctx->M;
     M.nrows = 2 * V;
+    M.xrows = N;
     int64_t *cntL = nullptr, *cntH = nullptr, *rowsum = nullptr;
-    SCS_CUDA(cudaMalloc((void**)&cntL, 2 * V * sizeof(int64_t)));
-    SCS_CUDA(cudaMalloc((void**)&cntH, 2 * V * sizeof(int64_t)));
-    SCS_CUDA(cudaMalloc((void**)&rowsum, 2 * V * sizeof(int64_t)));
+    SCS_CUDA(cudaMallocAsync((void**)&cntL, 2 * V * sizeof(int64_t), ctx->stream));
+    SCS_CUDA(cudaMallocAsync((void**)&cntH, 2 * V * sizeof(int64_t), ctx->stream));
+    SCS_CUDA(cudaMallocAsync((void**)&rowsum, 2 * V * sizeof(int64_t), ctx->stream));
     const int WPB = 8;  // warps per block
     unsigned gridPR = (unsigned)((2 * V + WPB - 1) / WPB);
     k_count_rows<<<gridPR, WPB * 32, 0, st>>>(V, a_ptr, a_val, r_ptr, r_val, data_bytes, cntL, cntH, rowsum, err);
@@ -253,13 +329,13 @@ int build_layout(scs_ctx* ctx, const int64_t* ref_indptr, const int32_t* ref_ind
     uint32_t *lkey = nullptr, *lval = nullptr, *hkey = nullptr, *lkey_s = nullptr, *hkey_s = nullptr;
     uint64_t *hval = nullptr, *hval_s = nullptr;
     const int64_t nl = M.n_light ? M.n_light : 1, nh = M.n_heavy ? M.n_heavy : 1;
-    SCS_CUDA(cudaMalloc((void**)&lkey, nl * 4));
-    SCS_CUDA(cudaMalloc((void**)&lval, nl * 4));
-    SCS_CUDA(cudaMalloc((void**)&lkey_s, nl * 4));
-    SCS_CUDA(cudaMalloc((void**)&hkey, nh * 4));
-    SCS_CUDA(cudaMalloc((void**)&hkey_s, nh * 4));
-    SCS_CUDA(cudaMalloc((void**)&hval, nh * 8));
-    SCS_CUDA(cudaMalloc((void**)&hval_s, nh * 8));
+    SCS_CUDA(cudaMallocAsync((void**)&lkey, nl * 4, ctx->stream));
+    SCS_CUDA(cudaMallocAsync((void**)&lval, nl * 4, ctx->stream));
+    SCS_CUDA(cudaMallocAsync((void**)&lkey_s, nl * 4, ctx->stream));
+    SCS_CUDA(cudaMallocAsync((void**)&hkey, nh * 4, ctx->stream));
+    SCS_CUDA(cudaMallocAsync((void**)&hkey_s, nh * 4, ctx->stream));
+    SCS_CUDA(cudaMallocAsync((void**)&hval, nh * 8, ctx->stream));
+    SCS_CUDA(cudaMallocAsync((void**)&hval_s, nh * 8, ctx->stream));
     k_fill_M<<<gridPR, WPB * 32, 0, st>>>(V, N, a_ptr, a_idx, a_val, r_ptr, r_idx, r_val, data_bytes, M.lptr, M.hptr,
                                           M.lcode, M.hcode, M.hcnt, lkey, lval, hkey, hval, ndup, err);
     ctx->launches++;
@@ -267,6 +343,7 @@ int build_layout(scs_ctx* ctx, const int64_t* ref_indptr, const int32_t* ref_ind
     // ---- cell-major stream: stable sort of the SNV-major order by cell
     Stream& E = ctx->E;
     E.nrows = N;
+    E.xrows = 2 * V;
     E.n_light = M.n_light;
     E.n_heavy = M.n_heavy;
     SCS_TRY(dev_alloc(ctx, &E.lptr, N + 1));
@@ -294,9 +371,9 @@ int build_layout(scs_ctx* ctx, const int64_t* ref_indptr, const int32_t* ref_ind
     SCS_CUDA(cudaMemcpyAsync(&herr, err, sizeof(int), cudaMemcpyDeviceToHost, st));
     SCS_CUDA(cudaStreamSynchronize(st));
     SCS_CUDA(cudaGetLastError());
-    cudaFree(a_ptr); cudaFree(r_ptr); cudaFree(a_idx); cudaFree(r_idx); cudaFree(a_val); cudaFree(r_val);
-    cudaFree(cntL); cudaFree(cntH); cudaFree(rowsum); cudaFree(err); cudaFree(ndup);
-    cudaFree(lkey); cudaFree(lval); cudaFree(lkey_s); cudaFree(hkey); cudaFree(hkey_s); cudaFree(hval); cudaFree(hval_s);
+    cudaFreeAsync(a_ptr, ctx->stream); cudaFreeAsync(r_ptr, ctx->stream); cudaFreeAsync(a_idx, ctx->stream); cudaFreeAsync(r_idx, ctx->stream); cudaFreeAsync(a_val, ctx->stream); cudaFreeAsync(r_val, ctx->stream);
+    cudaFreeAsync(cntL, ctx->stream); cudaFreeAsync(cntH, ctx->stream); cudaFreeAsync(rowsum, ctx->stream); cudaFreeAsync(err, ctx->stream); cudaFreeAsync(ndup, ctx->stream);
+    cudaFreeAsync(lkey, ctx->stream); cudaFreeAsync(lval, ctx->stream); cudaFreeAsync(lkey_s, ctx->stream); cudaFreeAsync(hkey, ctx->stream); cudaFreeAsync(hkey_s, ctx->stream); cudaFreeAsync(hval, ctx->stream); cudaFreeAsync(hval_s, ctx->stream);
     SCS_CHECK(herr != 2, "column index out of range [0, N)");
     SCS_CHECK(herr != 3, "CSR column indices must be sorted and duplicate-free within each row");
     SCS_CHECK(herr == 0, "invalid count matrix (code %d)", herr);

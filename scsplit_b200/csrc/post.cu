@@ -17,7 +17,7 @@ __global__ void k_onehot(int64_t n, int KP, const int32_t* __restrict__ labels, 
 }
 
 // out[c] = sum over alt entries of cell c: cnt * (1 - P[v, label[c]])
-__global__ void __launch_bounds__(256) k_refine_scores(int64_t N, int K, const int64_t* __restrict__ lptr, const uint32_t* __restrict__ lcode,
+__global__ void __launch_bounds__(256) k_refine_scores(int64_t N, int64_t V, int K, const int64_t* __restrict__ lptr, const uint32_t* __restrict__ lcode,
                                                        const int64_t* __restrict__ hptr, const uint32_t* __restrict__ hcode,
                                                        const int32_t* __restrict__ hcnt, const double* __restrict__ P,
                                                        const int32_t* __restrict__ labels, double* __restrict__ out) {
@@ -28,12 +28,12 @@ __global__ void __launch_bounds__(256) k_refine_scores(int64_t N, int K, const i
     double acc = 0.0;
     if (lab >= 0 && lab < K) {
         for (int64_t e = lptr[c] + lane; e < lptr[c + 1]; e += 32) {
-            const uint32_t code = lcode[e];
-            if (!(code & 2u)) acc += 1.0 - P[(int64_t)(code >> 2) * K + lab];
+            const int64_t g = (int64_t)(lcode[e] >> 1);          // alt entries are the gather rows g < V
+            if (g < V) acc += 1.0 - P[g * K + lab];
         }
         for (int64_t h = hptr[c] + lane; h < hptr[c + 1]; h += 32) {
-            const uint32_t code = hcode[h];
-            if (!(code & 2u)) acc += (double)hcnt[h] * (1.0 - P[(int64_t)(code >> 2) * K + lab]);
+            const int64_t g = (int64_t)(hcode[h] >> 1);
+            if (g < V) acc += (double)hcnt[h] * (1.0 - P[g * K + lab]);
         }
     }
     for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
@@ -65,20 +65,23 @@ __global__ void __launch_bounds__(256) k_row_pattern_counts(int64_t V, const int
     const int64_t v = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (v >= V) return;
     int64_t n = 0;
-    for (int64_t e = lptr[2 * v] + lane; e < lptr[2 * v + 2]; e += 32) {
-        const uint32_t code = lcode[e];
-        n += !(code & 1u) && (!keep_cols || keep_cols[code >> 2]);
-    }
-    for (int64_t e = hptr[2 * v] + lane; e < hptr[2 * v + 2]; e += 32) {
-        const uint32_t code = hcode[e];
-        n += !(code & 1u) && (!keep_cols || keep_cols[code >> 2]);
+    for (int sel = 0; sel < 2; ++sel) {
+        const int64_t pr = (int64_t)sel * V + v;
+        for (int64_t e = lptr[pr] + lane; e < lptr[pr + 1]; e += 32) {
+            const uint32_t code = lcode[e];
+            n += !(code & 1u) && (!keep_cols || keep_cols[code >> 1]);
+        }
+        for (int64_t e = hptr[pr] + lane; e < hptr[pr + 1]; e += 32) {
+            const uint32_t code = hcode[e];
+            n += !(code & 1u) && (!keep_cols || keep_cols[code >> 1]);
+        }
     }
     for (int o = 16; o; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
     if (lane == 0) out[v] = n;
 }
 
 // one warp per cell: union-pattern entries whose SNV is kept
-__global__ void __launch_bounds__(256) k_col_pattern_counts(int64_t N, const int64_t* __restrict__ lptr, const uint32_t* __restrict__ lcode,
+__global__ void __launch_bounds__(256) k_col_pattern_counts(int64_t N, int64_t V, const int64_t* __restrict__ lptr, const uint32_t* __restrict__ lcode,
                                                             const int64_t* __restrict__ hptr, const uint32_t* __restrict__ hcode,
                                                             const uint8_t* __restrict__ keep_rows, int64_t* __restrict__ out) {
     const int lane = threadIdx.x & 31;
@@ -87,17 +90,19 @@ __global__ void __launch_bounds__(256) k_col_pattern_counts(int64_t N, const int
     int64_t n = 0;
     for (int64_t e = lptr[c] + lane; e < lptr[c + 1]; e += 32) {
         const uint32_t code = lcode[e];
-        n += !(code & 1u) && (!keep_rows || keep_rows[code >> 2]);
+        const int64_t g = (int64_t)(code >> 1);
+        n += !(code & 1u) && (!keep_rows || keep_rows[g >= V ? g - V : g]);
     }
     for (int64_t e = hptr[c] + lane; e < hptr[c + 1]; e += 32) {
         const uint32_t code = hcode[e];
-        n += !(code & 1u) && (!keep_rows || keep_rows[code >> 2]);
+        const int64_t g = (int64_t)(code >> 1);
+        n += !(code & 1u) && (!keep_rows || keep_rows[g >= V ? g - V : g]);
     }
     for (int o = 16; o; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
     if (lane == 0) out[c] = n;
 }
 
-// one warp per SNV: integer per-cluster sums of alt (pseudo-row 2v) and ref (2v+1) counts over labelled cells
+// one warp per SNV: integer per-cluster sums of alt (pseudo-row v) and ref (V+v) counts over labelled cells
 __global__ void __launch_bounds__(256) k_cluster_counts(int64_t V, int K, const int64_t* __restrict__ lptr, const uint32_t* __restrict__ lcode,
                                                         const int64_t* __restrict__ hptr, const uint32_t* __restrict__ hcode,
                                                         const int32_t* __restrict__ hcnt, const int32_t* __restrict__ labels,
@@ -109,13 +114,13 @@ __global__ void __launch_bounds__(256) k_cluster_counts(int64_t V, int K, const 
     __syncwarp();
     if (v < V) {
         for (int sel = 0; sel < 2; ++sel) {
-            const int64_t pr = 2 * v + sel;
+            const int64_t pr = (int64_t)sel * V + v;
             for (int64_t e = lptr[pr] + lane; e < lptr[pr + 1]; e += 32) {
-                const int lab = labels[lcode[e] >> 2];
+                const int lab = labels[lcode[e] >> 1];
                 if (lab >= 0 && lab < K) atomicAdd(&cnt[warp][sel][lab], 1ull);
             }
             for (int64_t e = hptr[pr] + lane; e < hptr[pr + 1]; e += 32) {
-                const int lab = labels[hcode[e] >> 2];
+                const int lab = labels[hcode[e] >> 1];
                 if (lab >= 0 && lab < K) atomicAdd(&cnt[warp][sel][lab], (unsigned long long)hcnt[e]);
             }
         }
@@ -155,13 +160,15 @@ __global__ void k_pa_codes(int64_t n, const int64_t* __restrict__ n_ref, const i
         default: scs::set_error("unsupported KP=%d", KP_); return 1; \
     }
 
-struct Scratch {   // frees its device buffers on scope exit
+struct Scratch {   // stream-ordered scratch buffers, returned to the pool on scope exit
+    cudaStream_t st;
     std::vector<void*> ptrs;
-    ~Scratch() { for (void* p : ptrs) cudaFree(p); }
+    explicit Scratch(scs_ctx* ctx) : st(ctx->stream) {}
+    ~Scratch() { for (void* p : ptrs) cudaFreeAsync(p, st); }
     template <typename T>
     int get(T** p, int64_t n) {
         *p = nullptr;
-        cudaError_t e = cudaMalloc((void**)p, (size_t)(n > 0 ? n : 1) * sizeof(T));
+        cudaError_t e = cudaMallocAsync((void**)p, (size_t)(n > 0 ? n : 1) * sizeof(T), st);
         if (e != cudaSuccess) { set_error("cudaMalloc of %lld bytes failed: %s", (long long)(n * sizeof(T)), cudaGetErrorString(e)); return 1; }
         ptrs.push_back(*p);
         return 0;
@@ -183,7 +190,7 @@ int scs_seed_af(scs_ctx* ctx, int R, int K, const int32_t* labels, double* P0_ou
     const int KP = round_even(K);
     const int64_t stride = 2 * V * KP;
     cudaStream_t st = ctx->stream;
-    Scratch s;
+    Scratch s(ctx);
     int32_t* d_lab; double *d_W, *d_S, *d_P;
     SCS_TRY(s.get(&d_lab, (int64_t)R * N));
     SCS_TRY(s.get(&d_W, (int64_t)R * N * KP));
@@ -208,7 +215,7 @@ int scs_pattern_counts(scs_ctx* ctx, const uint8_t* keep_rows, const uint8_t* ke
     SCS_CUDA(cudaSetDevice(ctx->device));
     const int64_t V = ctx->V, N = ctx->N;
     cudaStream_t st = ctx->stream;
-    Scratch s;
+    Scratch s(ctx);
     uint8_t *d_kr = nullptr, *d_kc = nullptr;
     int64_t *d_rc, *d_cc;
     SCS_TRY(s.get(&d_rc, V));
@@ -222,7 +229,7 @@ int scs_pattern_counts(scs_ctx* ctx, const uint8_t* keep_rows, const uint8_t* ke
         SCS_CUDA(cudaMemcpyAsync(row_cnt, d_rc, (size_t)V * 8, cudaMemcpyDeviceToHost, st));
     }
     if (col_cnt) {
-        k_col_pattern_counts<<<(unsigned)((N + 7) / 8), 256, 0, st>>>(N, ctx->E.lptr, ctx->E.lcode, ctx->E.hptr, ctx->E.hcode, d_kr, d_cc);
+        k_col_pattern_counts<<<(unsigned)((N + 7) / 8), 256, 0, st>>>(N, V, ctx->E.lptr, ctx->E.lcode, ctx->E.hptr, ctx->E.hcode, d_kr, d_cc);
         ctx->launches++;
         SCS_CUDA(cudaMemcpyAsync(col_cnt, d_cc, (size_t)N * 8, cudaMemcpyDeviceToHost, st));
     }
@@ -240,7 +247,7 @@ int scs_doublet_scores(scs_ctx* ctx, int K, const double* P, const uint8_t* mask
     const int KP = round_even(K);
     const int nblk = (int)((N + 255) / 256);
     cudaStream_t st = ctx->stream;
-    Scratch s;
+    Scratch s(ctx);
     double *d_P, *d_T, *d_L, *d_part, *d_out;
     uint8_t* d_mask;
     SCS_TRY(s.get(&d_P, V * KP));
@@ -273,7 +280,7 @@ int scs_refine_scores(scs_ctx* ctx, int K, const double* P, const int32_t* label
     SCS_CUDA(cudaSetDevice(ctx->device));
     const int64_t V = ctx->V, N = ctx->N;
     cudaStream_t st = ctx->stream;
-    Scratch s;
+    Scratch s(ctx);
     double *d_P, *d_out;
     int32_t* d_lab;
     SCS_TRY(s.get(&d_P, V * K));
@@ -281,7 +288,7 @@ int scs_refine_scores(scs_ctx* ctx, int K, const double* P, const int32_t* label
     SCS_TRY(s.get(&d_lab, N));
     SCS_CUDA(cudaMemcpyAsync(d_P, P, (size_t)V * K * 8, cudaMemcpyHostToDevice, st));
     SCS_CUDA(cudaMemcpyAsync(d_lab, labels, (size_t)N * 4, cudaMemcpyHostToDevice, st));
-    k_refine_scores<<<(unsigned)((N + 7) / 8), 256, 0, st>>>(N, K, ctx->E.lptr, ctx->E.lcode, ctx->E.hptr, ctx->E.hcode, ctx->E.hcnt,
+    k_refine_scores<<<(unsigned)((N + 7) / 8), 256, 0, st>>>(N, V, K, ctx->E.lptr, ctx->E.lcode, ctx->E.hptr, ctx->E.hcode, ctx->E.hcnt,
                                                              d_P, d_lab, d_out);
     ctx->launches++;
     SCS_CUDA(cudaMemcpyAsync(out, d_out, (size_t)N * 8, cudaMemcpyDeviceToHost, st));
@@ -297,7 +304,7 @@ int scs_cluster_counts(scs_ctx* ctx, int K, const int32_t* labels, int64_t* n_re
     SCS_CUDA(cudaSetDevice(ctx->device));
     const int64_t V = ctx->V, N = ctx->N;
     cudaStream_t st = ctx->stream;
-    Scratch s;
+    Scratch s(ctx);
     int64_t* d_cnt;   // [2][V][K]: ref then alt, contiguous for one all-reduce
     int32_t* d_lab;
     int8_t* d_pa;

@@ -44,7 +44,7 @@ def test_layout_kalt_seed(golden, E):
         assert np.array_equal(eng.seed_af(lab, g["K"]), g["P0"])            # scSplit:137-145, bit-exact
 
 
-@pytest.mark.parametrize("variant", [1])
+@pytest.mark.parametrize("variant", [1, 2])
 def test_step_trace(golden, E, variant):
     from oracle import em_oracle as O
     from scsplit_b200._lib import SCS_L, SCS_LPS, SCS_P, SCS_W
