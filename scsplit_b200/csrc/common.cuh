@@ -143,7 +143,7 @@ int build_layout(scs_ctx* ctx, const int64_t* ref_indptr, const int32_t* ref_ind
                  const int64_t* alt_indptr, const int32_t* alt_indices, const void* alt_data, int data_bytes);
 void free_stream(scs_ctx* ctx, Stream& s);
 void free_tiled(scs_ctx* ctx, TiledStream& t);
-int build_tiled(scs_ctx* ctx, const Stream& s, TiledStream& t, int KP, int TR);
+int build_tiled(scs_ctx* ctx, const Stream& s, TiledStream& t, int KP, int TR, int pad);
 
 // em.cu
 int launch_spmm(scs_ctx* ctx, int kind /*0=E,1=M*/, int KP, int R, const double* X, int64_t x_stride, double* Y,

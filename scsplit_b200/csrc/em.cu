@@ -71,7 +71,7 @@ int launch_spmm_tiled(scs_ctx* ctx, int kind, int KP, int R, const double* X, in
     const Stream& s = kind == 0 ? ctx->E : ctx->M;
     TiledStream& t = kind == 0 ? ctx->TE : ctx->TM;
     const int TR = tile_rows_for(KP, s.xrows);
-    if (t.KP != KP || t.TR != TR) SCS_TRY(build_tiled(ctx, s, t, KP, TR));
+    if (t.KP != KP || t.TR != TR) SCS_TRY(build_tiled(ctx, s, t, KP, TR, unit_pad_for(KP)));
     const int64_t part_stride = t.nunits * KP;
     if (ctx->part_doubles < part_stride * R) {
         SCS_CUDA(cudaStreamSynchronize(ctx->stream));

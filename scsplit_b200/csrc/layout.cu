@@ -198,18 +198,18 @@ __device__ __forceinline__ int64_t row_lower_bound(const uint32_t* __restrict__ 
     return b;
 }
 
-// one thread per unit u = tile * nrows + row: entries of `row` inside `tile`, padded to an even count
-__global__ void k_tile_counts(int64_t nrows, int ntiles, int TR, const int64_t* __restrict__ lptr, const uint32_t* __restrict__ lcode,
-                              int64_t* __restrict__ cnt) {
+// one thread per unit u = tile * nrows + row: entries of `row` inside `tile`, padded to a multiple of `pad`
+__global__ void k_tile_counts(int64_t nrows, int ntiles, int TR, int pad, const int64_t* __restrict__ lptr,
+                              const uint32_t* __restrict__ lcode, int64_t* __restrict__ cnt) {
     const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (u >= nrows * ntiles) return;
     const int64_t t = u / nrows, row = u - t * nrows;
     const int64_t b = lptr[row], e = lptr[row + 1];
     const int64_t lo = row_lower_bound(lcode, b, e, t * TR), hi = row_lower_bound(lcode, b, e, (t + 1) * (int64_t)TR);
-    cnt[u] = ((hi - lo) + 1) & ~(int64_t)1;
+    cnt[u] = ((hi - lo) + pad - 1) / pad * pad;
 }
 
-// one warp per row: scatter its entries to their units as 16-bit in-tile offsets; odd units get one zero-row pad
+// one warp per row: scatter its entries to their units as 16-bit in-tile offsets; pad slots point at the zero row
 __global__ void k_tile_scatter(int64_t nrows, int ntiles, int TR, const int64_t* __restrict__ lptr, const uint32_t* __restrict__ lcode,
                                const int64_t* __restrict__ tptr, uint16_t* __restrict__ tcode) {
     const int lane = threadIdx.x & 31;
@@ -222,9 +222,10 @@ __global__ void k_tile_scatter(int64_t nrows, int ntiles, int TR, const int64_t*
         const int64_t lo = row_lower_bound(lcode, b, e, t * TR);
         tcode[tptr[t * nrows + row] + (i - lo)] = (uint16_t)(g - t * TR);
     }
-    for (int64_t t = lane; t < ntiles; t += 32) {   // pad slot: the last position of a unit whose true count is odd
+    for (int64_t t = lane; t < ntiles; t += 32) {   // pad slots: from the unit's true count up to its padded length
         const int64_t lo = row_lower_bound(lcode, b, e, t * TR), hi = row_lower_bound(lcode, b, e, (t + 1) * (int64_t)TR);
-        if ((hi - lo) & 1) tcode[tptr[t * nrows + row] + (hi - lo)] = (uint16_t)TR;
+        const int64_t u = t * nrows + row, base = tptr[u], plen = tptr[u + 1] - base;
+        for (int64_t k = hi - lo; k < plen; ++k) tcode[base + k] = (uint16_t)TR;
     }
 }
 
@@ -234,7 +235,7 @@ void free_tiled(scs_ctx* ctx, TiledStream& t) {
     t = TiledStream();
 }
 
-int build_tiled(scs_ctx* ctx, const Stream& s, TiledStream& t, int KP, int TR) {
+int build_tiled(scs_ctx* ctx, const Stream& s, TiledStream& t, int KP, int TR, int pad) {
     free_tiled(ctx, t);
     t.KP = KP;
     t.TR = TR;
@@ -243,7 +244,7 @@ int build_tiled(scs_ctx* ctx, const Stream& s, TiledStream& t, int KP, int TR) {
     cudaStream_t st = ctx->stream;
     SCS_TRY(dev_alloc(ctx, &t.tptr, t.nunits + 1));
     SCS_CUDA(cudaMemsetAsync(t.tptr, 0, sizeof(int64_t), st));
-    k_tile_counts<<<(unsigned)((t.nunits + 255) / 256), 256, 0, st>>>(s.nrows, t.ntiles, TR, s.lptr, s.lcode, t.tptr + 1);
+    k_tile_counts<<<(unsigned)((t.nunits + 255) / 256), 256, 0, st>>>(s.nrows, t.ntiles, TR, pad, s.lptr, s.lcode, t.tptr + 1);
     ctx->launches++;
     size_t tb = 0;
     SCS_CUDA(cub::DeviceScan::InclusiveSum(nullptr, tb, t.tptr + 1, t.tptr + 1, t.nunits, st));

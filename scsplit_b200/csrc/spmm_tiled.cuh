@@ -11,6 +11,9 @@ namespace scs {
 constexpr int TILE_BYTES = 208 * 1024;       // table tile resident in shared memory (of 227 KB usable per CTA)
 constexpr int TILED_THREADS = 1024;
 
+// padding granule of a unit in the tile-major stream (entries); 2 keeps the 32-bit words aligned
+inline int unit_pad_for(int /*KP*/) { return 2; }
+
 inline int tile_rows_for(int KP, int64_t xrows) {
     int64_t tr = TILE_BYTES / (KP * 8);
     if (tr > 65534) tr = 65534;              // 16-bit in-tile row offsets; 65535 would collide with the zero row
@@ -44,6 +47,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ double2 lds_f64x2(uint32_t addr) {
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+    return v;
+}
 
 template <int KP>
 struct TileCfg {
@@ -83,6 +92,9 @@ k_spmm_tiled(int64_t nrows, int ntiles, int TR, int64_t xrows, const int64_t* __
     const int li = lane & (C::GS - 1);          // lane inside its row group: owns columns 2*li, 2*li+1
     const int g = lane / C::GS;                 // row group inside the warp
     const int64_t nunits = (int64_t)ntiles * nrows;
+    // 32-bit shared address of this lane's 16-byte column pair inside table row 0; lanes beyond the last chunk
+    // re-read the last chunk (same address inside the quarter-warp -> broadcast, no extra wavefront), results unused
+    const uint32_t lane_base = smem_u32(smem) + (uint32_t)(li < C::CH ? li : C::CH - 1) * 16u;
 
     if (tid == 0) {
         const int64_t total = tptr[nunits];
@@ -113,46 +125,56 @@ k_spmm_tiled(int64_t nrows, int ntiles, int TR, int64_t xrows, const int64_t* __
         mbar_wait(bar, phase);
         phase ^= 1u;
 
-        // ---- every row group takes one unit (one row's entries inside this tile) at a time
-        for (int64_t base = ua + (int64_t)warp * C::GPW; base < ub; base += (int64_t)nwarps * C::GPW) {
-            const int64_t u = base + g;
-            const bool valid = u < ub;
-            const int64_t s = valid ? tptr[u] : 0;
-            const int len = valid ? (int)(tptr[u + 1] - s) : 0;
-            int maxlen = len;
-#pragma unroll
-            for (int o = 16; o >= C::GS; o >>= 1) maxlen = max(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, o));
-            double2 acc0 = make_double2(0.0, 0.0), acc1 = make_double2(0.0, 0.0);
-            // units are padded to an even number of entries (pad = zero row), so s is even and words are aligned
-            const uint32_t* words = reinterpret_cast<const uint32_t*>(tcode + s);
-            const uint32_t zero_pair = (uint32_t)TR | ((uint32_t)TR << 16);
-            for (int b = 0; b < maxlen; b += 2 * C::GS) {
-                // one 32-bit word = two 16-bit in-tile row offsets per lane, broadcast inside the group
-                const uint32_t mine = (b + 2 * li < len) ? __ldg(words + (b >> 1) + li) : zero_pair;
-                // UW words (2*UW table rows) are loaded back to back before their adds: 2*UW LDS.128 in flight per lane
-                constexpr int UW = C::GS < 4 ? C::GS : 4;
-#pragma unroll
-                for (int j0 = 0; j0 < C::GS; j0 += UW) {
-                    double2 v[2 * UW];
-#pragma unroll
-                    for (int jj = 0; jj < UW; ++jj) {
-                        const uint32_t w = __shfl_sync(0xffffffffu, mine, j0 + jj, C::GS);
-                        if (li < C::CH) {
-                            v[2 * jj] = *reinterpret_cast<const double2*>(smem + (w & 0xffffu) * (KP * 8) + li * 16);
-                            v[2 * jj + 1] = *reinterpret_cast<const double2*>(smem + (w >> 16) * (KP * 8) + li * 16);
-                        }
-                    }
-                    if (li < C::CH) {
-#pragma unroll
-                        for (int jj = 0; jj < UW; ++jj) {
-                            acc0.x += v[2 * jj].x; acc0.y += v[2 * jj].y;
-                            acc1.x += v[2 * jj + 1].x; acc1.y += v[2 * jj + 1].y;
-                        }
-                    }
+        // ---- the CTA's units of this tile are dealt to its row groups in equal contiguous runs; every group walks
+        // its run on its own (flush the finished unit, start the next), so the groups of a warp stay busy together
+        // although their units differ in length.  The next unit's bounds are prefetched one unit ahead.
+        const int64_t ngroups = (int64_t)nwarps * C::GPW, G = (int64_t)warp * C::GPW + g, n = ub - ua;
+        int64_t u = ua + (n / ngroups) * G + min(G, n % ngroups);            // first unit of this group
+        const int64_t uend = u + n / ngroups + (G < n % ngroups ? 1 : 0);
+        int64_t ucur = 0;
+        int64_t e_next = (u < uend) ? __ldg(tptr + u) : 0;
+        const uint32_t* words = nullptr;
+        int len = 0, pos = 0;
+        bool have = false;
+        double2 acc0 = make_double2(0.0, 0.0), acc1 = make_double2(0.0, 0.0);
+        const uint32_t zero_pair = (uint32_t)TR | ((uint32_t)TR << 16);
+        while (true) {
+            if (pos >= len) {                         // this group's unit is finished (or it has none yet)
+                if (have && li < C::CH)
+                    *reinterpret_cast<double2*>(part + ucur * KP + 2 * li) = make_double2(acc0.x + acc1.x, acc0.y + acc1.y);
+                have = u < uend;
+                len = 0;
+                pos = 0;
+                if (have) {
+                    const int64_t s = e_next;         // tptr[u]
+                    e_next = __ldg(tptr + u + 1);
+                    len = (int)(e_next - s);          // a multiple of the padding granule (zero-row entries fill it up)
+                    words = reinterpret_cast<const uint32_t*>(tcode + s);
+                    ucur = u++;
+                    acc0 = make_double2(0.0, 0.0);
+                    acc1 = make_double2(0.0, 0.0);
                 }
             }
-            if (valid && li < C::CH)
-                *reinterpret_cast<double2*>(part + u * KP + 2 * li) = make_double2(acc0.x + acc1.x, acc0.y + acc1.y);
+            if (!__any_sync(0xffffffffu, have)) break;
+            // one 32-bit word = two 16-bit in-tile row offsets per lane; past the unit's end -> the zero row
+            const uint32_t mine = (pos + 2 * li < len) ? __ldg(words + (pos >> 1) + li) : zero_pair;
+            pos += 2 * C::GS;
+            constexpr int UW = C::GS < 4 ? C::GS : 4;
+#pragma unroll
+            for (int j0 = 0; j0 < C::GS; j0 += UW) {
+                double2 v[2 * UW];
+#pragma unroll
+                for (int jj = 0; jj < UW; ++jj) {     // 2*UW LDS.128 in flight per lane before the adds
+                    const uint32_t w = __shfl_sync(0xffffffffu, mine, j0 + jj, C::GS);
+                    v[2 * jj] = lds_f64x2(lane_base + (w & 0xffffu) * (KP * 8));
+                    v[2 * jj + 1] = lds_f64x2(lane_base + (w >> 16) * (KP * 8));
+                }
+#pragma unroll
+                for (int jj = 0; jj < UW; ++jj) {
+                    acc0.x += v[2 * jj].x; acc0.y += v[2 * jj].y;
+                    acc1.x += v[2 * jj + 1].x; acc1.y += v[2 * jj + 1].y;
+                }
+            }
         }
     }
 }
