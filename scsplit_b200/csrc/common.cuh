@@ -63,7 +63,13 @@ struct TiledStream {
     int ntiles = 0;
     int64_t nunits = 0;    // ntiles * nrows
     int64_t* tptr = nullptr;   // [nunits + 1]
-    uint16_t* tcode = nullptr; // [n_light]
+    uint16_t* tcode = nullptr; // [n_light (+pad)]
+    // static work plan of k_spmm_tiled (built once per KP): CTA j runs the segments seg_ptr[j]..seg_ptr[j+1]); a segment
+    // is a run of units inside ONE tile; gb cuts it into `ngroups` contiguous runs of equal cost for the row groups
+    int ncta = 0, ngroups = 0, nseg = 0;
+    int32_t* seg_ptr = nullptr;   // [ncta + 1]
+    int32_t* seg_tile = nullptr;  // [nseg]
+    int64_t* gb = nullptr;        // [nseg][ngroups + 1] unit boundaries
 };
 
 struct NcclApi;  // dlopen'ed function table (comm.cu)
@@ -143,7 +149,7 @@ int build_layout(scs_ctx* ctx, const int64_t* ref_indptr, const int32_t* ref_ind
                  const int64_t* alt_indptr, const int32_t* alt_indices, const void* alt_data, int data_bytes);
 void free_stream(scs_ctx* ctx, Stream& s);
 void free_tiled(scs_ctx* ctx, TiledStream& t);
-int build_tiled(scs_ctx* ctx, const Stream& s, TiledStream& t, int KP, int TR, int pad);
+int build_tiled(scs_ctx* ctx, const Stream& s, TiledStream& t, int KP, int TR, int pad, int ncta, int ngroups);
 
 // em.cu
 int launch_spmm(scs_ctx* ctx, int kind /*0=E,1=M*/, int KP, int R, const double* X, int64_t x_stride, double* Y,

@@ -71,16 +71,17 @@ int launch_spmm_tiled(scs_ctx* ctx, int kind, int KP, int R, const double* X, in
     const Stream& s = kind == 0 ? ctx->E : ctx->M;
     TiledStream& t = kind == 0 ? ctx->TE : ctx->TM;
     const int TR = tile_rows_for(KP, s.xrows);
-    if (t.KP != KP || t.TR != TR) SCS_TRY(build_tiled(ctx, s, t, KP, TR, unit_pad_for(KP)));
+    const int ctas = ctx->sm_count > 0 ? ctx->sm_count : 148;
+    const int ngroups = (TILED_THREADS / 32) * groups_per_warp_for(KP);
+    if (t.KP != KP || t.TR != TR || t.ncta != ctas || t.ngroups != ngroups)
+        SCS_TRY(build_tiled(ctx, s, t, KP, TR, unit_pad_for(KP), ctas, ngroups));
     const int64_t part_stride = t.nunits * KP;
     if (ctx->part_doubles < part_stride * R) {
-        SCS_CUDA(cudaStreamSynchronize(ctx->stream));
         dev_free(ctx, ctx->part);
         SCS_TRY(dev_alloc(ctx, &ctx->part, part_stride * R));
         ctx->part_doubles = part_stride * R;
     }
     const size_t smem = ((((size_t)(TR + 1) * KP * 8) + 127) & ~(size_t)127) + 16;
-    const int ctas = ctx->sm_count > 0 ? ctx->sm_count : 148;
     dim3 grid((unsigned)ctas, (unsigned)R);
     dim3 cgrid((unsigned)((s.nrows * (KP / 2) + 255) / 256), (unsigned)R);
     SCS_DISPATCH_KP(KP, {
@@ -89,8 +90,8 @@ int launch_spmm_tiled(scs_ctx* ctx, int kind, int KP, int R, const double* X, in
             SCS_CUDA(cudaFuncSetAttribute(k_spmm_tiled<KPc>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_BYTES + 1024));
             attr_set = true;
         }
-        k_spmm_tiled<KPc><<<grid, TILED_THREADS, smem, ctx->stream>>>(s.nrows, t.ntiles, TR, s.xrows, t.tptr, t.tcode, X, x_stride,
-                                                                   ctx->part, part_stride, done);
+        k_spmm_tiled<KPc><<<grid, TILED_THREADS, smem, ctx->stream>>>(s.nrows, TR, s.xrows, t.tptr, t.tcode, t.seg_ptr, t.seg_tile, t.gb,
+                                                                   X, x_stride, ctx->part, part_stride, done);
         k_spmm_combine<KPc><<<cgrid, 256, 0, ctx->stream>>>(s.nrows, t.ntiles, ctx->part, part_stride, s.hptr, s.hcode, s.hcnt, X,
                                                           x_stride, Y, y_stride, done);
     });

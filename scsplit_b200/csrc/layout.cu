@@ -7,6 +7,8 @@
 // cub (part of the CUDA toolkit) is used for the one-time scan/sort only, never on the per-iteration path.
 #include <cub/cub.cuh>
 
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace scs {
@@ -229,13 +231,47 @@ __global__ void k_tile_scatter(int64_t nrows, int ntiles, int TR, const int64_t*
     }
 }
 
+// cost of the units [lo, u): entries plus a fixed charge per unit (flush + bounds), in entry units
+constexpr int64_t UNIT_COST = 8;
+__device__ __forceinline__ int64_t plan_cost(const int64_t* __restrict__ tptr, int64_t lo, int64_t u) {
+    return (tptr[u] - tptr[lo]) + UNIT_COST * (u - lo);
+}
+__device__ __forceinline__ int64_t plan_cut(const int64_t* __restrict__ tptr, int64_t lo, int64_t hi, int64_t part, int64_t nparts) {
+    if (part <= 0) return lo;
+    if (part >= nparts) return hi;
+    const int64_t total = plan_cost(tptr, lo, hi);
+    const int64_t target = (total / nparts) * part + ((total % nparts) * part) / nparts;
+    int64_t a = lo, b = hi;
+    while (a < b) {          // first unit u with cost(lo, u) >= target
+        const int64_t mid = (a + b) >> 1;
+        if (plan_cost(tptr, lo, mid) < target) a = mid + 1; else b = mid;
+    }
+    return a;
+}
+// cu[j] = first unit of CTA j (equal-cost split of all units)
+__global__ void k_plan_ctas(const int64_t* __restrict__ tptr, int64_t nunits, int ncta, int64_t* __restrict__ cu) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j > ncta) return;
+    cu[j] = plan_cut(tptr, 0, nunits, j, ncta);
+}
+// gb[seg][G] = first unit of row group G inside segment [lo, hi)
+__global__ void k_plan_groups(const int64_t* __restrict__ tptr, const int64_t* __restrict__ seg_lo, const int64_t* __restrict__ seg_hi,
+                              int ngroups, int64_t* __restrict__ gb) {
+    const int seg = blockIdx.x;
+    for (int G = threadIdx.x; G <= ngroups; G += blockDim.x)
+        gb[(int64_t)seg * (ngroups + 1) + G] = plan_cut(tptr, seg_lo[seg], seg_hi[seg], G, ngroups);
+}
+
 void free_tiled(scs_ctx* ctx, TiledStream& t) {
     dev_free(ctx, t.tptr);
     dev_free(ctx, t.tcode);
+    dev_free(ctx, t.seg_ptr);
+    dev_free(ctx, t.seg_tile);
+    dev_free(ctx, t.gb);
     t = TiledStream();
 }
 
-int build_tiled(scs_ctx* ctx, const Stream& s, TiledStream& t, int KP, int TR, int pad) {
+int build_tiled(scs_ctx* ctx, const Stream& s, TiledStream& t, int KP, int TR, int pad, int ncta, int ngroups) {
     free_tiled(ctx, t);
     t.KP = KP;
     t.TR = TR;
@@ -260,6 +296,49 @@ int build_tiled(scs_ctx* ctx, const Stream& s, TiledStream& t, int KP, int TR, i
     SCS_TRY(dev_alloc(ctx, &t.tcode, total + 2));
     k_tile_scatter<<<(unsigned)((s.nrows + 7) / 8), 256, 0, st>>>(s.nrows, t.ntiles, TR, s.lptr, s.lcode, t.tptr, t.tcode);
     ctx->launches++;
+    // ---- static work plan: CTA ranges (device), tile segments (host, <= ncta + ntiles of them), group cuts (device)
+    t.ncta = ncta;
+    t.ngroups = ngroups;
+    int64_t* d_cu = nullptr;
+    SCS_CUDA(cudaMallocAsync((void**)&d_cu, (size_t)(ncta + 1) * 8, st));
+    k_plan_ctas<<<(ncta + 1 + 127) / 128, 128, 0, st>>>(t.tptr, t.nunits, ncta, d_cu);
+    ctx->launches++;
+    std::vector<int64_t> cu((size_t)ncta + 1);
+    SCS_CUDA(cudaMemcpyAsync(cu.data(), d_cu, cu.size() * 8, cudaMemcpyDeviceToHost, st));
+    SCS_CUDA(cudaStreamSynchronize(st));
+    cudaFreeAsync(d_cu, st);
+    std::vector<int32_t> seg_ptr((size_t)ncta + 1, 0), seg_tile;
+    std::vector<int64_t> seg_lo, seg_hi;
+    for (int j = 0; j < ncta; ++j) {
+        seg_ptr[j] = (int32_t)seg_tile.size();
+        for (int64_t tt = cu[j] / s.nrows; tt * s.nrows < cu[j + 1]; ++tt) {
+            const int64_t lo = std::max(cu[j], tt * s.nrows), hi = std::min(cu[j + 1], (tt + 1) * s.nrows);
+            if (lo >= hi) continue;
+            seg_tile.push_back((int32_t)tt);
+            seg_lo.push_back(lo);
+            seg_hi.push_back(hi);
+        }
+    }
+    seg_ptr[ncta] = (int32_t)seg_tile.size();
+    t.nseg = (int)seg_tile.size();
+    const int64_t ns = t.nseg ? t.nseg : 1;
+    int64_t *d_lo = nullptr, *d_hi = nullptr;
+    SCS_TRY(dev_alloc(ctx, &t.seg_ptr, ncta + 1));
+    SCS_TRY(dev_alloc(ctx, &t.seg_tile, ns));
+    SCS_TRY(dev_alloc(ctx, &t.gb, ns * (ngroups + 1)));
+    SCS_CUDA(cudaMallocAsync((void**)&d_lo, (size_t)ns * 8, st));
+    SCS_CUDA(cudaMallocAsync((void**)&d_hi, (size_t)ns * 8, st));
+    SCS_CUDA(cudaMemcpyAsync(t.seg_ptr, seg_ptr.data(), seg_ptr.size() * 4, cudaMemcpyHostToDevice, st));
+    if (t.nseg) {
+        SCS_CUDA(cudaMemcpyAsync(t.seg_tile, seg_tile.data(), seg_tile.size() * 4, cudaMemcpyHostToDevice, st));
+        SCS_CUDA(cudaMemcpyAsync(d_lo, seg_lo.data(), seg_lo.size() * 8, cudaMemcpyHostToDevice, st));
+        SCS_CUDA(cudaMemcpyAsync(d_hi, seg_hi.data(), seg_hi.size() * 8, cudaMemcpyHostToDevice, st));
+        k_plan_groups<<<t.nseg, 256, 0, st>>>(t.tptr, d_lo, d_hi, ngroups, t.gb);
+        ctx->launches++;
+    }
+    SCS_CUDA(cudaStreamSynchronize(st));   // host vectors above must outlive the copies
+    cudaFreeAsync(d_lo, st);
+    cudaFreeAsync(d_hi, st);
     SCS_CUDA(cudaGetLastError());
     return 0;
 }

@@ -14,6 +14,12 @@ constexpr int TILED_THREADS = 1024;
 // padding granule of a unit in the tile-major stream (entries); 2 keeps the 32-bit words aligned
 inline int unit_pad_for(int /*KP*/) { return 2; }
 
+inline int groups_per_warp_for(int KP) {
+    const int ch = KP / 2;
+    const int gs = ch <= 1 ? 1 : ch <= 2 ? 2 : ch <= 4 ? 4 : ch <= 8 ? 8 : 16;
+    return 32 / gs;
+}
+
 inline int tile_rows_for(int KP, int64_t xrows) {
     int64_t tr = TILE_BYTES / (KP * 8);
     if (tr > 65534) tr = 65534;              // 16-bit in-tile row offsets; 65535 would collide with the zero row
@@ -61,119 +67,110 @@ struct TileCfg {
     static constexpr int GPW = 32 / GS;                                                     // row groups per warp
 };
 
-// first unit whose tptr is >= target
-__device__ __forceinline__ int64_t unit_lower_bound(const int64_t* __restrict__ tptr, int64_t nunits, int64_t target) {
-    int64_t lo = 0, hi = nunits;
-    while (lo < hi) {
-        int64_t mid = (lo + hi) >> 1;
-        if (tptr[mid] < target) lo = mid + 1; else hi = mid;
-    }
-    return lo;
-}
-
-// grid = (CTAs, R).  CTA j owns the units [u_j, u_{j+1}) that split the tile-major entry stream into equal shares.
+// grid = (CTAs, R).  CTA j runs its segments of the static work plan (TiledStream::seg_ptr / seg_tile / gb).
+//
+// Inside a segment (a run of units of ONE tile) every row group owns a contiguous run of units whose entries are
+// contiguous in the tile-major stream, and consumes them as one continuous stream of 2*GS-entry batches: there is no
+// per-unit padding of the batches and the four (GPW) groups of a warp never wait for each other's unit ends.  Entries
+// before the current unit's end go to `cur`, entries after it to `nxt` (predicated DADDs); when the stream passes a unit
+// end the unit is flushed and nxt becomes cur.  A batch never crosses a second unit end (it is cut there), so two
+// accumulator sets suffice.  Unit bounds are prefetched two units ahead.
 template <int KP>
 __global__ void __launch_bounds__(TILED_THREADS, 1)
-k_spmm_tiled(int64_t nrows, int ntiles, int TR, int64_t xrows, const int64_t* __restrict__ tptr,
-             const uint16_t* __restrict__ tcode, const double* __restrict__ X, int64_t x_stride, double* __restrict__ part,
-             int64_t part_stride, const int32_t* __restrict__ done) {
+k_spmm_tiled(int64_t nrows, int TR, int64_t xrows, const int64_t* __restrict__ tptr, const uint16_t* __restrict__ tcode,
+             const int32_t* __restrict__ seg_ptr, const int32_t* __restrict__ seg_tile, const int64_t* __restrict__ gb,
+             const double* __restrict__ X, int64_t x_stride, double* __restrict__ part, int64_t part_stride,
+             const int32_t* __restrict__ done) {
     using C = TileCfg<KP>;
     extern __shared__ __align__(128) unsigned char smem[];
     double* tile = reinterpret_cast<double*>(smem);                           // [(TR + 1) * KP], row TR is all zeros
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + (((size_t)(TR + 1) * KP * 8 + 127) & ~(size_t)127));
-    __shared__ int64_t s_range[2];
 
     const int r = blockIdx.y;
     if (done && done[r]) return;
     X += (int64_t)r * x_stride;
     part += (int64_t)r * part_stride;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int nwarps = blockDim.x >> 5;
     const int li = lane & (C::GS - 1);          // lane inside its row group: owns columns 2*li, 2*li+1
     const int g = lane / C::GS;                 // row group inside the warp
-    const int64_t nunits = (int64_t)ntiles * nrows;
+    const int ngroups = (int)(blockDim.x >> 5) * C::GPW;
+    const int G = warp * C::GPW + g;
     // 32-bit shared address of this lane's 16-byte column pair inside table row 0; lanes beyond the last chunk
     // re-read the last chunk (same address inside the quarter-warp -> broadcast, no extra wavefront), results unused
     const uint32_t lane_base = smem_u32(smem) + (uint32_t)(li < C::CH ? li : C::CH - 1) * 16u;
+    const uint32_t zero_pair = (uint32_t)TR | ((uint32_t)TR << 16);
+    constexpr int BE = 2 * C::GS;               // entries per batch of one group
 
-    if (tid == 0) {
-        const int64_t total = tptr[nunits];
-        const int64_t G = gridDim.x, j = blockIdx.x;
-        s_range[0] = (j == 0) ? 0 : unit_lower_bound(tptr, nunits, (total / G) * j + ((total % G) * j) / G);
-        s_range[1] = (j == G - 1) ? nunits : unit_lower_bound(tptr, nunits, (total / G) * (j + 1) + ((total % G) * (j + 1)) / G);
-        mbar_init(bar, 1);
-    }
+    if (tid == 0) mbar_init(bar, 1);
     for (int k = tid; k < KP; k += blockDim.x) tile[(size_t)TR * KP + k] = 0.0;
     __syncthreads();
-    const int64_t u0 = s_range[0], u1 = s_range[1];
-    if (u0 >= u1) return;
     uint32_t phase = 0;
+    int loaded_tile = -1;
 
-    for (int64_t t = u0 / nrows; t * nrows < u1; ++t) {
-        const int64_t ua = max(u0, t * nrows), ub = min(u1, (t + 1) * nrows);
-        // ---- stage tile t of the operand: rows [t*TR, t*TR + rows_t) are contiguous in global memory
-        __syncthreads();                                  // every warp is done reading the previous tile
-        if (tid == 0) {
-            const int64_t rows_t = min((int64_t)TR, xrows - t * TR);
-            const uint32_t bytes = (uint32_t)(rows_t * KP * 8);
-            const char* src = reinterpret_cast<const char*>(X + t * TR * KP);
-            fence_proxy_async();                          // order the generic-proxy reads above before the async writes
-            mbar_expect_tx(bar, bytes);
-            for (uint32_t off = 0; off < bytes; off += 32768u)
-                bulk_g2s(smem + off, src + off, min(32768u, bytes - off), bar);
-        }
-        mbar_wait(bar, phase);
-        phase ^= 1u;
-
-        // ---- the CTA's units of this tile are dealt to its row groups in equal contiguous runs; every group walks
-        // its run on its own (flush the finished unit, start the next), so the groups of a warp stay busy together
-        // although their units differ in length.  The next unit's bounds are prefetched one unit ahead.
-        const int64_t ngroups = (int64_t)nwarps * C::GPW, G = (int64_t)warp * C::GPW + g, n = ub - ua;
-        int64_t u = ua + (n / ngroups) * G + min(G, n % ngroups);            // first unit of this group
-        const int64_t uend = u + n / ngroups + (G < n % ngroups ? 1 : 0);
-        int64_t ucur = 0;
-        int64_t e_next = (u < uend) ? __ldg(tptr + u) : 0;
-        const uint32_t* words = nullptr;
-        int len = 0, pos = 0;
-        bool have = false;
-        double2 acc0 = make_double2(0.0, 0.0), acc1 = make_double2(0.0, 0.0);
-        const uint32_t zero_pair = (uint32_t)TR | ((uint32_t)TR << 16);
-        while (true) {
-            if (pos >= len) {                         // this group's unit is finished (or it has none yet)
-                if (have && li < C::CH)
-                    *reinterpret_cast<double2*>(part + ucur * KP + 2 * li) = make_double2(acc0.x + acc1.x, acc0.y + acc1.y);
-                have = u < uend;
-                len = 0;
-                pos = 0;
-                if (have) {
-                    const int64_t s = e_next;         // tptr[u]
-                    e_next = __ldg(tptr + u + 1);
-                    len = (int)(e_next - s);          // a multiple of the padding granule (zero-row entries fill it up)
-                    words = reinterpret_cast<const uint32_t*>(tcode + s);
-                    ucur = u++;
-                    acc0 = make_double2(0.0, 0.0);
-                    acc1 = make_double2(0.0, 0.0);
-                }
+    const int seg_end = seg_ptr[blockIdx.x + 1];
+    for (int seg = seg_ptr[blockIdx.x]; seg < seg_end; ++seg) {
+        const int t = seg_tile[seg];
+        if (t != loaded_tile) {
+            // ---- stage tile t of the operand: rows [t*TR, t*TR + rows_t) are contiguous in global memory
+            __syncthreads();                              // every warp is done reading the previous tile
+            if (tid == 0) {
+                const int64_t rows_t = min((int64_t)TR, xrows - (int64_t)t * TR);
+                const uint32_t bytes = (uint32_t)(rows_t * KP * 8);
+                const char* src = reinterpret_cast<const char*>(X + (int64_t)t * TR * KP);
+                fence_proxy_async();                      // order the generic-proxy reads above before the async writes
+                mbar_expect_tx(bar, bytes);
+                for (uint32_t off = 0; off < bytes; off += 32768u)
+                    bulk_g2s(smem + off, src + off, min(32768u, bytes - off), bar);
             }
-            if (!__any_sync(0xffffffffu, have)) break;
-            // one 32-bit word = two 16-bit in-tile row offsets per lane; past the unit's end -> the zero row
-            const uint32_t mine = (pos + 2 * li < len) ? __ldg(words + (pos >> 1) + li) : zero_pair;
-            pos += 2 * C::GS;
+            mbar_wait(bar, phase);
+            phase ^= 1u;
+            loaded_tile = t;
+        }
+        const int64_t* gbs = gb + (int64_t)seg * (ngroups + 1);
+        int64_t u = __ldg(gbs + G);                       // current unit
+        const int64_t uend = __ldg(gbs + G + 1);
+        const bool act = u < uend;                        // (a group without units still takes part in the warp's shuffles)
+        int64_t e = act ? __ldg(tptr + u) : 0;            // stream position (entries); even
+        const int64_t eend = act ? __ldg(tptr + uend) : 0;
+        // ends of units u, u+1, u+2 (clamped to the end of this group's run)
+        int64_t b1 = act ? __ldg(tptr + u + 1) : 0;
+        int64_t b2 = (u + 2 <= uend) ? __ldg(tptr + u + 2) : eend;
+        int64_t b3 = (u + 3 <= uend) ? __ldg(tptr + u + 3) : eend;
+        double2 c0 = make_double2(0.0, 0.0), c1 = make_double2(0.0, 0.0);   // current unit (even / odd entries)
+        double2 n0 = make_double2(0.0, 0.0), n1 = make_double2(0.0, 0.0);   // next unit
+        // all GPW groups of the warp iterate together; a group that has finished feeds zero rows until the others end
+        while (__any_sync(0xffffffffu, u < uend)) {
+            const int64_t lim = min(e + BE, b2);          // never past the end of unit u+1
+            const int nvalid = (u < uend) ? (int)(lim - e) : 0;
+            const int ncur = (int)min((int64_t)nvalid, max((int64_t)0, b1 - e));   // entries of this batch that belong to unit u
+            const uint32_t mine = (2 * li < nvalid) ? __ldg(reinterpret_cast<const uint32_t*>(tcode + e) + li) : zero_pair;
             constexpr int UW = C::GS < 4 ? C::GS : 4;
 #pragma unroll
             for (int j0 = 0; j0 < C::GS; j0 += UW) {
                 double2 v[2 * UW];
 #pragma unroll
-                for (int jj = 0; jj < UW; ++jj) {     // 2*UW LDS.128 in flight per lane before the adds
+                for (int jj = 0; jj < UW; ++jj) {         // 2*UW LDS.128 in flight per lane before the adds
                     const uint32_t w = __shfl_sync(0xffffffffu, mine, j0 + jj, C::GS);
                     v[2 * jj] = lds_f64x2(lane_base + (w & 0xffffu) * (KP * 8));
                     v[2 * jj + 1] = lds_f64x2(lane_base + (w >> 16) * (KP * 8));
                 }
 #pragma unroll
                 for (int jj = 0; jj < UW; ++jj) {
-                    acc0.x += v[2 * jj].x; acc0.y += v[2 * jj].y;
-                    acc1.x += v[2 * jj + 1].x; acc1.y += v[2 * jj + 1].y;
+                    const int p0 = 2 * (j0 + jj);
+                    if (p0 < ncur) { c0.x += v[2 * jj].x; c0.y += v[2 * jj].y; } else { n0.x += v[2 * jj].x; n0.y += v[2 * jj].y; }
+                    if (p0 + 1 < ncur) { c1.x += v[2 * jj + 1].x; c1.y += v[2 * jj + 1].y; } else { n1.x += v[2 * jj + 1].x; n1.y += v[2 * jj + 1].y; }
                 }
+            }
+            e = (u < uend) ? lim : e;
+            // flush every unit the stream has passed (an empty unit is passed immediately and stores zeros)
+            while (u < uend && e >= b1) {
+                if (li < C::CH)
+                    *reinterpret_cast<double2*>(part + u * KP + 2 * li) = make_double2(c0.x + c1.x, c0.y + c1.y);
+                c0 = n0; c1 = n1;
+                n0 = make_double2(0.0, 0.0); n1 = make_double2(0.0, 0.0);
+                ++u;
+                b1 = b2; b2 = b3;
+                b3 = (u + 3 <= uend) ? __ldg(tptr + u + 3) : eend;
             }
         }
     }
