@@ -266,3 +266,79 @@ def test_full_size_properties(E):
         n_ref, n_alt, _ = eng.cluster_counts(labels, K)
         assert np.array_equal(n_ref.sum(axis=1), np.asarray(pool.ref.sum(axis=1)).ravel())
         assert np.array_equal(n_alt.sum(axis=1), np.asarray(pool.alt.sum(axis=1)).ravel())
+
+
+@pytest.mark.parametrize("K", [1, 3, 7, 8, 11, 12, 16, 17, 24, 32])
+@pytest.mark.parametrize("variant", [1, 2])
+def test_state_count_sweep(K, variant, E):
+    """Every compiled table width (KP = 2..32: row groups of 1, 2, 4, 8 and 16 lanes) against the oracle, incl. K = 17 of
+    BASELINE config 4; the pool is sized so that the E-step operand spans several shared-memory tiles (2V*KP*8 > 208 KB)."""
+    from oracle import em_oracle as O
+    from scsplit_b200 import synth
+    from scsplit_b200._lib import SCS_L, SCS_LPS, SCS_P, SCS_W
+    V, N = 4000, 700
+    pool = synth.make_pool(V, N, 4, 0.05, 0.12, seed=77 + K)
+    rng = np.random.default_rng(K)
+    lab = np.full(N, -1, dtype=np.int32)
+    pick = rng.choice(N, 2 * K, replace=False)
+    lab[pick] = np.arange(2 * K) % K
+    with E(pool.ref, pool.alt) as eng:
+        eng.set_variant(variant)
+        k_alt = eng.kalt()
+        P0 = eng.seed_af(lab, K)
+        assert np.array_equal(P0, O.seed_af(pool.ref, pool.alt, k_alt, lab, K))
+        eng.em_begin(P0)
+        P, lPs = P0, np.array([np.log2(1 / K)] * K)
+        for t in range(2):
+            eng.set(SCS_P, P)
+            eng.set(SCS_LPS, lPs)
+            eng.estep()
+            L_o, W_o, LL_o = O.estep(pool.ref, pool.alt, P, lPs)
+            L = eng.get(SCS_L)
+            assert_close(L, L_o, RTOL, "L K=%d" % K)
+            assert_close(eng.get(SCS_W), O.posterior(L, lPs), RTOL, "W K=%d" % K)
+            assert_close(eng.stats()["ll"], LL_o, RTOL, "LL K=%d" % K)
+            eng.set(SCS_W, W_o)
+            eng.mstep()
+            P_o, lPs_o = O.mstep(pool.ref, pool.alt, W_o, k_alt)
+            assert_close(eng.get(SCS_P), P_o, RTOL, "P K=%d" % K)
+            assert_close(eng.get(SCS_LPS), lPs_o, RTOL, "lPs K=%d" % K)
+            P, lPs = P_o, lPs_o
+
+
+def test_config3_full_size_properties(E):
+    """BASELINE config 3 (30k x 20k, K = 9): the metric's own configuration, checked through size-independent properties
+    and against the oracle on a column sample (the oracle's full E-step takes ~5 s, so one step is affordable)."""
+    from oracle import em_oracle as O
+    from scsplit_b200 import synth
+    from scsplit_b200._lib import SCS_L, SCS_LLHIST, SCS_P, SCS_W
+    pool = synth.make_config("c3")
+    K = 9
+    with E(pool.ref, pool.alt) as eng:
+        V, N = eng.V, eng.N
+        info = eng.layout_info()
+        assert info["nnz_union"] == 29264030                       # the figure SURVEY.md section 8d quotes
+        rng = np.random.default_rng(0)
+        lab = np.full(N, -1, dtype=np.int32)
+        lab[rng.choice(N, 27, replace=False)] = np.arange(27) % K
+        k_alt = eng.kalt()
+        assert np.array_equal(k_alt, O.kalt(pool.ref, pool.alt))
+        P0 = eng.seed_af(lab, K)
+        eng.em_begin(P0)
+        eng.estep()
+        L = eng.get(SCS_L)
+        L_o = O.loglik_matrix(pool.ref, pool.alt, P0)
+        assert_close(L, L_o, RTOL, "L at config 3")
+        W = eng.get(SCS_W)
+        assert np.allclose(np.nansum(W, axis=1), 1.0, rtol=0, atol=1e-9)
+        eng.mstep()
+        P1_o, lPs_o = O.mstep(pool.ref, pool.alt, W, k_alt)
+        assert_close(eng.get(SCS_P), P1_o, RTOL, "P at config 3")
+        eng.em_begin(P0)
+        eng.em_iterate(10, check_conv=False)
+        hist = eng.get(SCS_LLHIST)[:10]
+        assert (np.diff(hist) >= -1e-9 * np.abs(hist[:-1])).all()   # EM never decreases the likelihood
+        labels = rng.integers(0, K, N).astype(np.int32)
+        n_ref, n_alt, _ = eng.cluster_counts(labels, K)
+        assert np.array_equal(n_ref.sum(axis=1), np.asarray(pool.ref.sum(axis=1)).ravel())
+        assert np.array_equal(n_alt.sum(axis=1), np.asarray(pool.alt.sum(axis=1)).ravel())
