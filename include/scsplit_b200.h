@@ -118,6 +118,17 @@ int scs_comm_unique_id(uint8_t id[128]);
  * all-reduced (sum) over ranks inside the calls above.  Every rank must make the same calls. */
 int scs_comm_init(scs_ctx* ctx, const uint8_t id[128], int rank, int world);
 
+/* ---- input (host only): the reference's dense count CSV straight to CSR ----
+ * Replaces pd.read_csv(header=0, index_col=0) + csr_matrix(frame.values), scSplit:544-546, without the dense V x N
+ * int64 intermediate.  Plain non-negative integer fields only; returns 2 for anything else (quotes, floats, blanks) so
+ * that the caller can fall back to a general CSV reader.  ids / barcodes are '\n'-joined byte strings. */
+typedef struct scs_csv scs_csv;
+int scs_csv_parse(const char* path, int threads, scs_csv** out);
+/* out[0]=V out[1]=N out[2]=nnz out[3]=bytes of ids out[4]=bytes of barcodes */
+int scs_csv_shape(scs_csv* csv, int64_t out[5]);
+int scs_csv_fetch(scs_csv* csv, int64_t* indptr, int32_t* indices, int32_t* data, char* ids, char* barcodes);
+int scs_csv_free(scs_csv* csv);
+
 /* ---- instrumentation ---- */
 
 /* number of kernels this context has launched (for bench.py's gpu_launches) */

@@ -41,6 +41,10 @@ SIGNATURES = {
     "scs_cluster_counts": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "scs_comm_unique_id": (c_int, [c_void_p]),
     "scs_comm_init": (c_int, [c_void_p, c_void_p, c_int, c_int]),
+    "scs_csv_parse": (c_int, [c_char_p, c_int, POINTER(c_void_p)]),
+    "scs_csv_shape": (c_int, [c_void_p, POINTER(c_int64)]),
+    "scs_csv_fetch": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "scs_csv_free": (c_int, [c_void_p]),
     "scs_launch_count": (c_int, [c_void_p, POINTER(c_int64)]),
     "scs_set_timing": (c_int, [c_void_p, c_int]),
     "scs_kernel_times": (c_int, [c_void_p, POINTER(c_double), c_int]),

@@ -20,12 +20,40 @@ def _log(out, text):
         logfile.write(text)
 
 
+def read_count_csv(path, threads=0):
+    """One dense count CSV -> (csr int32 V x N, SNV index, barcode index) through the library's streaming parser
+    (csrc/csv.cu); files it declines (quoted / non-integer fields) go through pandas exactly like scSplit:544-546."""
+    import ctypes
+    from . import _lib
+    lib = _lib.load()
+    h = ctypes.c_void_p()
+    rc = lib.scs_csv_parse(os.fsencode(path), int(threads), ctypes.byref(h))
+    if rc == 2:
+        frame = pd.read_csv(path, header=0, index_col=0)
+        return csr_matrix(frame.values), frame.index, frame.columns
+    _lib.check(rc)
+    try:
+        shp = (ctypes.c_int64 * 5)()
+        _lib.check(lib.scs_csv_shape(h, shp))
+        V, N, nnz, nid, nbc = (int(x) for x in shp)
+        indptr, indices, data = np.empty(V + 1, np.int64), np.empty(nnz, np.int32), np.empty(nnz, np.int32)
+        ids, bcs = ctypes.create_string_buffer(max(nid, 1)), ctypes.create_string_buffer(max(nbc, 1))
+        vp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+        _lib.check(lib.scs_csv_fetch(h, vp(indptr), vp(indices), vp(data), ids, bcs))
+    finally:
+        lib.scs_csv_free(h)
+    snv = ids.raw[:nid].decode().split('\n')[:-1] if nid else []
+    barcodes = bcs.raw[:nbc].decode().split('\n')[:-1] if nbc else []
+    m = csr_matrix((data, indices, indptr), shape=(V, N))
+    m.has_sorted_indices = True
+    return m, pd.Index(snv, name='SNV'), pd.Index(barcodes)
+
+
 def load_counts(ref_path, alt_path):
     """ref_filtered.csv / alt_filtered.csv -> base_calls_mtx = [csr ref, csr alt, SNV index, barcode index] (scSplit:544-547)."""
-    ref = pd.read_csv(ref_path, header=0, index_col=0)
-    alt = pd.read_csv(alt_path, header=0, index_col=0)
-    ref_s, alt_s = csr_matrix(ref.values), csr_matrix(alt.values)
-    return [ref_s, alt_s, ref.index, ref.columns]
+    ref_s, ref_index, ref_columns = read_count_csv(ref_path)
+    alt_s, _, _ = read_count_csv(alt_path)
+    return [ref_s, alt_s, ref_index, ref_columns]
 
 
 def elbow(points):

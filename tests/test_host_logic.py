@@ -96,3 +96,37 @@ def test_synth_is_shard_consistent():
     assert np.array_equal(full.truth[700:1900], part.truth)
     dens = (full.ref + full.alt).nnz / (300 * 2500)
     assert abs(dens - (1 - np.exp(-0.05))) < 0.01
+
+
+def test_csv_parser_matches_pandas(tmp_path):
+    """csrc/csv.cu against pd.read_csv + csr_matrix (scSplit:544-546) on the reference's own file format."""
+    from scipy.sparse import csr_matrix
+    from scsplit_b200 import cli, synth
+    pool = synth.make_pool(700, 257, 3, 0.05, 0.3, seed=3)
+    rp, ap = str(tmp_path / "ref.csv"), str(tmp_path / "alt.csv")
+    synth.write_csv(pool, rp, ap)
+    for path in (rp, ap):
+        frame = pd.read_csv(path, header=0, index_col=0)
+        want = csr_matrix(frame.values)
+        for threads in (1, 3):
+            got, idx, cols = cli.read_count_csv(path, threads)
+            assert got.shape == want.shape and (got != want).nnz == 0
+            assert np.array_equal(got.indptr, want.indptr) and np.array_equal(got.indices, want.indices)
+            assert idx.tolist() == frame.index.tolist() and cols.tolist() == frame.columns.tolist()
+    # a bigger file exercises the multi-threaded row split (> 1 MB), CRLF line ends and blanks around fields
+    big = synth.make_pool(3000, 900, 3, 0.0, 0.2, seed=4)
+    bp = str(tmp_path / "big.csv")
+    synth.write_csv(big, bp, str(tmp_path / "big_alt.csv"))
+    txt = open(bp).read().replace("\n", "\r\n").replace(",1,", ", 1 ,", 50)
+    open(bp, "w", newline="").write(txt)
+    got, idx, cols = cli.read_count_csv(bp, 4)
+    assert (got != big.ref).nnz == 0 and idx.tolist() == big.snv_ids and cols.tolist() == big.barcodes
+    # declined inputs fall back to pandas (floats), malformed ones raise
+    fp = str(tmp_path / "float.csv")
+    open(fp, "w").write("SNV,a,b\n1:5,1.0,0\n1:9,0,2\n")
+    got, idx, cols = cli.read_count_csv(fp)
+    assert got.toarray().tolist() == [[1.0, 0.0], [0.0, 2.0]]
+    rg = str(tmp_path / "ragged.csv")
+    open(rg, "w").write("SNV,a,b\n1:5,1\n")
+    with pytest.raises(Exception):
+        cli.read_count_csv(rg)
