@@ -12,6 +12,10 @@
 
 namespace scs {
 
+// threads per block of the per-cell kernels (k_bayes, k_colsum_partial, k_masked_colsum): small blocks so that even
+// 20k cells give >2 CTAs per SM; the block count fixes the order of the two-level column-mass / LL reduction
+constexpr int CELL_BLOCK = 64;
+
 __device__ __forceinline__ double2 ldg2(const double* p) { return __ldg(reinterpret_cast<const double2*>(p)); }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -106,7 +110,7 @@ __device__ __forceinline__ void block_reduce_store(double (&v)[NV], double* smem
 // ll_c   = log2( sum_k 2^((L_k - max_k L) + s_k) ) + max_k L   with pandas skipna  (scSplit:188)
 // partial[r][blk][0..KP) = sum over the block's cells of W[c,k] (NaN skipped, scSplit:198), [KP] = sum of ll_c
 template <int KP>
-__global__ void __launch_bounds__(256) k_bayes(int64_t N, int K, const double* __restrict__ L, double* __restrict__ W,
+__global__ void __launch_bounds__(CELL_BLOCK) k_bayes(int64_t N, int K, const double* __restrict__ L, double* __restrict__ W,
                                                const double* __restrict__ lps, double* __restrict__ partial, int nblk,
                                                const int32_t* __restrict__ done) {
     const int r = blockIdx.y;
@@ -164,7 +168,7 @@ __global__ void __launch_bounds__(256) k_bayes(int64_t N, int K, const double* _
 
 // column mass of an arbitrary W (step-level M-step entry): same block mapping and order as k_bayes
 template <int KP>
-__global__ void __launch_bounds__(256) k_colsum_partial(int64_t N, const double* __restrict__ W, double* __restrict__ partial,
+__global__ void __launch_bounds__(CELL_BLOCK) k_colsum_partial(int64_t N, const double* __restrict__ W, double* __restrict__ partial,
                                                         int nblk) {
     const int r = blockIdx.y;
     __shared__ double s_red[8 * (KP + 1)];

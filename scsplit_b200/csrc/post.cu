@@ -42,7 +42,7 @@ __global__ void __launch_bounds__(256) k_refine_scores(int64_t N, int64_t V, int
 
 // partial[blk][k] = sum over the block's cells of mask[c] * L[c,k]   (fixed order)
 template <int KP>
-__global__ void __launch_bounds__(256) k_masked_colsum(int64_t N, const double* __restrict__ L, const uint8_t* __restrict__ mask,
+__global__ void __launch_bounds__(CELL_BLOCK) k_masked_colsum(int64_t N, const double* __restrict__ L, const uint8_t* __restrict__ mask,
                                                        double* __restrict__ partial) {
     __shared__ double s_red[8 * (KP + 1)];
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -245,7 +245,7 @@ int scs_doublet_scores(scs_ctx* ctx, int K, const double* P, const uint8_t* mask
     SCS_CUDA(cudaSetDevice(ctx->device));
     const int64_t V = ctx->V, N = ctx->N;
     const int KP = round_even(K);
-    const int nblk = (int)((N + 255) / 256);
+    const int nblk = (int)((N + CELL_BLOCK - 1) / CELL_BLOCK);
     cudaStream_t st = ctx->stream;
     Scratch s(ctx);
     double *d_P, *d_T, *d_L, *d_part, *d_out;
@@ -263,7 +263,7 @@ int scs_doublet_scores(scs_ctx* ctx, int K, const double* P, const uint8_t* mask
     k_tables_from_P<<<grid, 256, 0, st>>>(V, K, KP, d_P, d_T);
     ctx->launches++;
     SCS_TRY(launch_spmm(ctx, 0, KP, 1, d_T, 2 * V * KP, d_L, N * KP, nullptr));
-    SCS_DISPATCH_KP2(KP, (k_masked_colsum<KPc><<<nblk, 256, 0, st>>>(N, d_L, d_mask, d_part)));
+    SCS_DISPATCH_KP2(KP, (k_masked_colsum<KPc><<<nblk, CELL_BLOCK, 0, st>>>(N, d_L, d_mask, d_part)));
     k_reduce_stats<<<1, 256, 0, st>>>(KP, d_part, nblk, d_out, KP + 2, 0, 1, nullptr);
     ctx->launches += 2;
     if (ctx->world > 1) SCS_TRY(comm_allreduce_f64(ctx, d_out, KP));
