@@ -141,11 +141,28 @@ def union_nnz(ref, alt):
 
 
 def write_csv(pool, ref_path, alt_path):
-    """Dense CSVs in the reference's input format (scSplit:59, 462-463, 544-545)."""
-    header = "SNV," + ",".join(pool.barcodes) + "\n"
+    """Dense CSVs in the reference's input format (scSplit:59, 462-463, 544-545): header `SNV,<barcodes>`, rows `<id>,<ints>`.
+
+    Rows are rendered from a `0,0,...,0` byte template with the single-digit counts patched in (rows holding a count
+    >= 10 take the generic path), so the 2 x 1.2 GB files of config 3 are written in seconds.
+    """
+    header = ("SNV," + ",".join(pool.barcodes) + "\n").encode()
+    N = len(pool.barcodes)
+    template = np.frombuffer(b"0," * N, dtype=np.uint8).copy()
+    template[-1] = ord("\n")
     for mat, path in ((pool.ref, ref_path), (pool.alt, alt_path)):
-        dense = np.asarray(mat.todense())
-        with open(path, "w") as f:
+        mat = mat.tocsr()
+        with open(path, "wb") as f:
             f.write(header)
             for i, sid in enumerate(pool.snv_ids):
-                f.write(sid + "," + ",".join(map(str, dense[i].tolist())) + "\n")
+                lo, hi = mat.indptr[i], mat.indptr[i + 1]
+                cols, vals = mat.indices[lo:hi], mat.data[lo:hi]
+                f.write(sid.encode() + b",")
+                if vals.size and vals.max() >= 10:
+                    dense = np.zeros(N, dtype=np.int64)
+                    dense[cols] = vals
+                    f.write((",".join(map(str, dense.tolist())) + "\n").encode())
+                    continue
+                line = template.copy()
+                line[2 * cols.astype(np.int64)] = ord("0") + vals.astype(np.uint8)
+                f.write(line.tobytes())
