@@ -192,7 +192,7 @@ def run_reference_arm(args):
         "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 / base["value"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "%s: %d SNVs x %d cells, K=%d states (8 samples + doublet), Poisson lam=0.05" % (args.workload, V, N, K),
+        "config": {"workload": "%s: %d SNVs x %d cells, K=%d states incl. doublet state, Poisson lam=0.05" % (args.workload, V, N, K),
                    "host_cores_available": os.cpu_count(), "note": "the reference is single-threaded on this path (scipy sparsetools, pandas)"},
         "cpu_baseline": base,
         "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -266,6 +266,11 @@ def run_cuda_arm(args):
         eng.comm_init(uid.cpu().numpy(), rank, world)
     info = eng.layout_info()
     assert info["nnz_union"] == nnzU_local
+    nnzU_total = nnzU_local
+    if cells_mode:
+        tt = torch.tensor([nnzU_local], dtype=torch.int64, device="cuda")
+        dist.all_reduce(tt)
+        nnzU_total = int(tt[0])
     # restart-sharded: every rank starts from its own initialisation; cell-sharded: same seed, local slice of labels
     lab = random_seed_labels(N_total, K, 0 if cells_mode else rank)
     if cells_mode:
@@ -348,8 +353,8 @@ def run_cuda_arm(args):
         "ms_per_step": 1000.0 * dev_s / args.steps, "higher_is_better": True,
         "scaling": "strong" if cells_mode else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {
-            "workload": "%s: %d SNVs x %d cells, K=%d states (8 samples + doublet), Poisson lam=0.05, nnz(union)=%d" % (
-                args.workload, V, N_total, K, nnzU_local if not cells_mode else -1),
+            "workload": "%s: %d SNVs x %d cells, K=%d states incl. doublet state, Poisson lam=0.05, nnz(union)=%d" % (
+                args.workload, V, N_total, K, nnzU_total),
             "parallelism": ("cells sharded over %d GPUs, NCCL all-reduce of 2VK+K+1 doubles per iteration" % world) if cells_mode
             else ("%d independent restarts, one per GPU, no collective" % world if world > 1 else "single GPU, one restart"),
             "l2": "inputs larger than L2: two entry streams of %.0f MB each are read per step vs %.0f MB of L2; no flush" % (
