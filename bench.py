@@ -343,7 +343,7 @@ def run_cuda_arm(args):
     dom_bytes, dom_us = (eb, kt["e_us"]) if dom == "E" else (mb, kt["m_us"])
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tpath):
+    if os.path.exists(tpath) and args.workload == "c3" and not cells_mode:   # the capture is of this configuration only
         with open(tpath) as f:
             traffic = json.load(f).get(dom)
     iters_total = world * args.steps if not cells_mode else args.steps
