@@ -83,7 +83,9 @@ struct EmState {
     double* W = nullptr;        // [R][N][KP]
     double* stats = nullptr;    // [R][2V*KP + KP + 2]: S (alt/ref posterior-weighted sums), colsum[KP], LL, pad
     double* lps = nullptr;      // [R][KP]
-    double* partial = nullptr;  // [R][nblk][KP+1] per-block column mass + LL (fixed-order reduction)
+    double* partial = nullptr;  // [R][nblk][KP+2] per-block column mass, LL, dense-path cell count (fixed-order reduction)
+    uint32_t* hq = nullptr;     // [R][h_stride] packed (state, 1 - weight) of a saturated posterior row, or SPARSE_DENSE
+    int64_t h_stride = 0;       // N rounded up to 4 (16-byte multiples for the bulk copy)
     double* hist = nullptr;     // [R][max_iter]
     double* ll_prev = nullptr;  // [R]
     int32_t* iters = nullptr;   // [R]
@@ -120,8 +122,8 @@ struct scs_ctx {
     std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> ev_pending;  // (kind, (start, stop))
     cudaEvent_t ev_iter[2] = {nullptr, nullptr};   // brackets the launches of the last scs_em_iterate
     double last_iter_ms = 0.0;
-    double t_sum[2] = {0, 0};
-    int64_t t_cnt[2] = {0, 0};
+    double t_sum[3] = {0, 0, 0};      // E SpMM, M tiled SpMM, M sparse kernel
+    int64_t t_cnt[3] = {0, 0, 0};
 };
 
 namespace scs {
@@ -153,7 +155,7 @@ int build_tiled(scs_ctx* ctx, const Stream& s, TiledStream& t, int KP, int TR, i
 
 // em.cu
 int launch_spmm(scs_ctx* ctx, int kind /*0=E,1=M*/, int KP, int R, const double* X, int64_t x_stride, double* Y,
-                int64_t y_stride, const int32_t* done);
+                int64_t y_stride, const int32_t* done, const double* gate = nullptr, int64_t gate_stride = 0, double gate_thr = 0.0);
 int em_free(scs_ctx* ctx);
 
 // comm.cu

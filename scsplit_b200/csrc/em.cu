@@ -1,7 +1,10 @@
 // EM driver: restart-batched run_EM (scSplit:148-162) with the stop rule evaluated on the device, plus the
 // step-level E/M entry points used by the parity tests.
+#include <algorithm>
+
 #include "em_kernels.cuh"
 #include "spmm_tiled.cuh"
+#include "mstep_sparse.cuh"
 
 namespace scs {
 
@@ -44,14 +47,14 @@ static int timing_end(scs_ctx* ctx, int kind, cudaEvent_t a, cudaEvent_t b) {
 }
 
 int launch_spmm(scs_ctx* ctx, int kind, int KP, int R, const double* X, int64_t x_stride, double* Y, int64_t y_stride,
-                const int32_t* done) {
+                const int32_t* done, const double* gate, int64_t gate_stride, double gate_thr) {
     const Stream& s = kind == 0 ? ctx->E : ctx->M;
     cudaEvent_t ea, eb;
     SCS_TRY(timing_begin(ctx, &ea, &eb));
     int variant = ctx->variant;
     if (variant == 0) variant = tiled_supported(ctx, kind, KP) ? 2 : 1;
     if (variant == 2) {
-        SCS_TRY(launch_spmm_tiled(ctx, kind, KP, R, X, x_stride, Y, y_stride, done));
+        SCS_TRY(launch_spmm_tiled(ctx, kind, KP, R, X, x_stride, Y, y_stride, done, gate, gate_stride, gate_thr));
     } else {
         const int WPB = 8;
         dim3 grid((unsigned)((s.nrows + WPB - 1) / WPB), (unsigned)R);
@@ -67,7 +70,7 @@ int launch_spmm(scs_ctx* ctx, int kind, int KP, int R, const double* X, int64_t 
 bool tiled_supported(scs_ctx*, int, int KP) { return KP >= 2 && KP <= 32 && (KP % 2) == 0; }
 
 int launch_spmm_tiled(scs_ctx* ctx, int kind, int KP, int R, const double* X, int64_t x_stride, double* Y, int64_t y_stride,
-                      const int32_t* done) {
+                      const int32_t* done, const double* gate, int64_t gate_stride, double gate_thr) {
     const Stream& s = kind == 0 ? ctx->E : ctx->M;
     TiledStream& t = kind == 0 ? ctx->TE : ctx->TM;
     const int TR = tile_rows_for(KP, s.xrows);
@@ -91,9 +94,9 @@ int launch_spmm_tiled(scs_ctx* ctx, int kind, int KP, int R, const double* X, in
             attr_set = true;
         }
         k_spmm_tiled<KPc><<<grid, TILED_THREADS, smem, ctx->stream>>>(s.nrows, TR, s.xrows, t.tptr, t.tcode, t.seg_ptr, t.seg_tile, t.gb,
-                                                                   X, x_stride, ctx->part, part_stride, done);
+                                                                   X, x_stride, ctx->part, part_stride, done, gate, gate_stride, gate_thr);
         k_spmm_combine<KPc><<<cgrid, 256, 0, ctx->stream>>>(s.nrows, t.ntiles, ctx->part, part_stride, s.hptr, s.hcode, s.hcnt, X,
-                                                          x_stride, Y, y_stride, done);
+                                                          x_stride, Y, y_stride, done, gate, gate_stride, gate_thr);
     });
     ctx->launches += 2;
     return 0;
@@ -102,6 +105,7 @@ int launch_spmm_tiled(scs_ctx* ctx, int kind, int KP, int R, const double* X, in
 int em_free(scs_ctx* ctx) {
     EmState& em = ctx->em;
     dev_free(ctx, em.T); dev_free(ctx, em.P); dev_free(ctx, em.L); dev_free(ctx, em.W); dev_free(ctx, em.stats); dev_free(ctx, em.lps);
+    dev_free(ctx, em.hq);
     dev_free(ctx, em.partial); dev_free(ctx, em.hist); dev_free(ctx, em.ll_prev); dev_free(ctx, em.iters); dev_free(ctx, em.done);
     em = EmState();
     return 0;
@@ -123,8 +127,9 @@ static int run_e(scs_ctx* ctx, const int32_t* done) {
     const int64_t V = ctx->V, N = ctx->N;
     SCS_TRY(launch_spmm(ctx, 0, em.KP, em.R, em.T, 2 * V * em.KP, em.L, N * em.KP, done));
     dim3 grid((unsigned)em.nblk, (unsigned)em.R);
-    SCS_DISPATCH_KP(em.KP, (k_bayes<KPc><<<grid, CELL_BLOCK, 0, ctx->stream>>>(N, em.K, em.L, em.W, em.lps, em.partial, em.nblk, done)));
-    k_reduce_stats<<<em.R, 256, 0, ctx->stream>>>(em.KP, em.partial, em.nblk, em.stats, em.stats_stride, 2 * V * em.KP, 1, done);
+    SCS_DISPATCH_KP(em.KP, (k_bayes<KPc><<<grid, CELL_BLOCK, 0, ctx->stream>>>(N, em.K, em.L, em.W, em.lps, em.partial, em.nblk, em.hq,
+                                                                              em.h_stride, done)));
+    k_reduce_stats<<<em.R, 256, 0, ctx->stream>>>(em.KP, em.KP + 2, em.partial, em.nblk, em.stats, em.stats_stride, 2 * V * em.KP, 1, done);
     ctx->launches += 2;
     SCS_CUDA(cudaGetLastError());
     return 0;
@@ -133,7 +138,30 @@ static int run_e(scs_ctx* ctx, const int32_t* done) {
 static int run_m(scs_ctx* ctx, const int32_t* done, int track, int check_conv) {
     EmState& em = ctx->em;
     const int64_t V = ctx->V, N = ctx->N;
-    SCS_TRY(launch_spmm(ctx, 1, em.KP, em.R, em.W, N * em.KP, em.stats, em.stats_stride, done));
+    // M-step sums: the sparse kernel when (nearly) all posterior rows are saturated, else the tiled SpMM; both are launched
+    // and the dense-path cell count in the statistics tail (written by k_reduce_stats) gates which one does the work
+    const bool sparse = ctx->variant == 0 && sparse_fits(N, em.KP);
+    const double* gate = sparse ? em.stats + 2 * V * em.KP + em.KP + 1 : nullptr;
+    const double gate_thr = (double)std::max<int64_t>(16, N / 32);
+    if (sparse) {
+        cudaEvent_t ea = nullptr, eb = nullptr;
+        SCS_TRY(timing_begin(ctx, &ea, &eb));
+        const size_t smem = sparse_smem_bytes(em.h_stride, em.KP);
+        dim3 grid((unsigned)(ctx->sm_count > 0 ? ctx->sm_count : 148), (unsigned)em.R);
+        SCS_DISPATCH_KP(em.KP, {
+            static bool attr_set = false;
+            if (!attr_set) {
+                SCS_CUDA(cudaFuncSetAttribute(k_mstep_sparse<KPc>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_BYTES + 1024));
+                attr_set = true;
+            }
+            k_mstep_sparse<KPc><<<grid, SPARSE_THREADS, smem, ctx->stream>>>(ctx->M.nrows, N, em.K, ctx->M.lptr, ctx->M.lcode, ctx->M.hptr,
+                                                                           ctx->M.hcode, ctx->M.hcnt, em.hq, em.h_stride, em.W, em.stats,
+                                                                           em.stats_stride, gate, em.stats_stride, gate_thr, done);
+        });
+        ctx->launches++;
+        SCS_TRY(timing_end(ctx, 2, ea, eb));
+    }
+    SCS_TRY(launch_spmm(ctx, 1, em.KP, em.R, em.W, N * em.KP, em.stats, em.stats_stride, done, gate, em.stats_stride, gate_thr));
     if (ctx->world > 1) SCS_TRY(comm_allreduce_f64(ctx, em.stats, (int64_t)em.R * em.stats_stride));
     dim3 grid((unsigned)((V * em.KP + 255) / 256), (unsigned)em.R);
     k_finalize<<<grid, 256, 0, ctx->stream>>>(V, em.K, em.KP, em.stats, em.stats_stride, ctx->kalt, em.P, em.T, done);
@@ -176,7 +204,10 @@ int scs_em_begin(scs_ctx* ctx, int R, int K, const double* P0, int max_iter) {
     SCS_TRY(dev_alloc(ctx, &em.W, (int64_t)R * N * KP));
     SCS_TRY(dev_alloc(ctx, &em.stats, (int64_t)R * em.stats_stride));
     SCS_TRY(dev_alloc(ctx, &em.lps, (int64_t)R * KP));
-    SCS_TRY(dev_alloc(ctx, &em.partial, (int64_t)R * em.nblk * (KP + 1)));
+    SCS_TRY(dev_alloc(ctx, &em.partial, (int64_t)R * em.nblk * (KP + 2)));
+    em.h_stride = (N + 3) / 4 * 4;
+    SCS_TRY(dev_alloc(ctx, &em.hq, (int64_t)R * em.h_stride));
+    SCS_CUDA(cudaMemsetAsync(em.hq, 255, (size_t)R * em.h_stride * 4, ctx->stream));
     SCS_TRY(dev_alloc(ctx, &em.hist, (int64_t)R * max_iter));
     SCS_TRY(dev_alloc(ctx, &em.ll_prev, R));
     SCS_TRY(dev_alloc(ctx, &em.iters, R));
@@ -216,8 +247,9 @@ int scs_mstep(scs_ctx* ctx) {
     EmState& em = ctx->em;
     // column mass of whatever W currently holds (it may have been injected with scs_em_set)
     dim3 grid((unsigned)em.nblk, (unsigned)em.R);
-    SCS_DISPATCH_KP(em.KP, (k_colsum_partial<KPc><<<grid, CELL_BLOCK, 0, ctx->stream>>>(ctx->N, em.W, em.partial, em.nblk)));
-    k_reduce_stats<<<em.R, 256, 0, ctx->stream>>>(em.KP, em.partial, em.nblk, em.stats, em.stats_stride, 2 * ctx->V * em.KP, 0, nullptr);
+    SCS_DISPATCH_KP(em.KP, (k_colsum_partial<KPc><<<grid, CELL_BLOCK, 0, ctx->stream>>>(ctx->N, em.K, em.W, em.partial, em.nblk, em.hq,
+                                                                                       em.h_stride)));
+    k_reduce_stats<<<em.R, 256, 0, ctx->stream>>>(em.KP, em.KP + 2, em.partial, em.nblk, em.stats, em.stats_stride, 2 * ctx->V * em.KP, 0, nullptr);
     ctx->launches += 2;
     SCS_TRY(run_m(ctx, nullptr, 0, 0));
     SCS_CUDA(cudaStreamSynchronize(ctx->stream));

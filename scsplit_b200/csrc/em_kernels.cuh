@@ -106,23 +106,50 @@ __device__ __forceinline__ void block_reduce_store(double (&v)[NV], double* smem
     }
 }
 
+// Posterior rows saturate: after a few iterations almost every cell has one state with W = 1 - O(1e-13) and all others
+// below 1e-40.  Such a row is packed into ONE 32-bit word: the state in the low 5 bits and eps = 1 - W as a float whose low
+// 5 mantissa bits are zero.  W near 1 is a multiple of 2^-53 (2^-52 above 1), so eps = +-m * 2^-53 is exact in float whenever
+// m < 2^19 (|eps| < 5.8e-11), and 1.0 - (double)eps gives W back bit for bit.  The entries dropped (< 1e-40) are invisible to
+// the M-step, where the sums only ever enter (S + k_alt) and (S + 1) with k_alt >= 1e-10: 2^31 such terms stay under half
+// an ulp.  Rows that do not fit the format (soft, NaN) are marked SPARSE_DENSE and take the dense path.
+constexpr double SPARSE_TINY = 1e-40;
+constexpr uint32_t SPARSE_DENSE = 0xffffffffu;
+template <int KP>
+__device__ __forceinline__ uint32_t sparsify_row(const double (&w)[KP], int K) {
+    int im = 0;
+    double wm = w[0];
+#pragma unroll
+    for (int k = 1; k < KP; ++k)
+        if (k < K && w[k] > wm) { wm = w[k]; im = k; }
+    // the reference's own rounding puts the winning posterior at 1 +- O(1e-13), on either side of 1; NaN rows are never sparse
+    bool ok = (wm == wm) && wm >= 0.5 && wm <= 1.5;
+#pragma unroll
+    for (int k = 0; k < KP; ++k)
+        if (k < K && k != im) ok = ok && (w[k] < SPARSE_TINY);
+    const double eps = 1.0 - wm;                      // exact (Sterbenz)
+    const float ef = (float)eps;
+    const uint32_t bits = __float_as_uint(ef);
+    ok = ok && ((double)ef == eps) && ((bits & 31u) == 0u);
+    return ok ? (bits | (uint32_t)im) : SPARSE_DENSE;
+}
+
 // W[c,i] = 1 / sum_j 2^(((L_j + s_j) - L_i) - s_i)   (scSplit:181-185, j ascending, left-to-right)
 // ll_c   = log2( sum_k 2^((L_k - max_k L) + s_k) ) + max_k L   with pandas skipna  (scSplit:188)
 // partial[r][blk][0..KP) = sum over the block's cells of W[c,k] (NaN skipped, scSplit:198), [KP] = sum of ll_c
 template <int KP>
 __global__ void __launch_bounds__(CELL_BLOCK) k_bayes(int64_t N, int K, const double* __restrict__ L, double* __restrict__ W,
                                                const double* __restrict__ lps, double* __restrict__ partial, int nblk,
-                                               const int32_t* __restrict__ done) {
+                                               uint32_t* __restrict__ hq, int64_t h_stride, const int32_t* __restrict__ done) {
     const int r = blockIdx.y;
     if (done && done[r]) return;
     __shared__ double s_lps[KP];
-    __shared__ double s_red[8 * (KP + 1)];
+    __shared__ double s_red[8 * (KP + 2)];
     if (threadIdx.x < KP) s_lps[threadIdx.x] = lps[(int64_t)r * KP + threadIdx.x];
     __syncthreads();
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    double v[KP + 1];
+    double v[KP + 2];
 #pragma unroll
-    for (int k = 0; k <= KP; ++k) v[k] = 0.0;
+    for (int k = 0; k <= KP + 1; ++k) v[k] = 0.0;
     if (c < N) {
         const double* l = L + ((int64_t)r * N + c) * KP;
         double Lr[KP], t[KP];
@@ -162,43 +189,50 @@ __global__ void __launch_bounds__(CELL_BLOCK) k_bayes(int64_t N, int K, const do
 #pragma unroll
         for (int k = 0; k < KP; ++k) v[k] = (w[k] == w[k]) ? w[k] : 0.0;
         v[KP] = (ll == ll) ? ll : 0.0;
+        const uint32_t q = sparsify_row<KP>(w, K);
+        hq[(int64_t)r * h_stride + c] = q;
+        v[KP + 1] = q == SPARSE_DENSE ? 1.0 : 0.0;       // number of cells that need the dense M-step path
     }
-    block_reduce_store<KP + 1>(v, s_red, partial + ((int64_t)r * nblk + blockIdx.x) * (KP + 1));
+    block_reduce_store<KP + 2>(v, s_red, partial + ((int64_t)r * nblk + blockIdx.x) * (KP + 2));
 }
 
-// column mass of an arbitrary W (step-level M-step entry): same block mapping and order as k_bayes
+// column mass and (state, weight) form of an arbitrary W (step-level M-step entry): same block mapping and order as k_bayes
 template <int KP>
-__global__ void __launch_bounds__(CELL_BLOCK) k_colsum_partial(int64_t N, const double* __restrict__ W, double* __restrict__ partial,
-                                                        int nblk) {
+__global__ void __launch_bounds__(CELL_BLOCK) k_colsum_partial(int64_t N, int K, const double* __restrict__ W, double* __restrict__ partial,
+                                                        int nblk, uint32_t* __restrict__ hq, int64_t h_stride) {
     const int r = blockIdx.y;
-    __shared__ double s_red[8 * (KP + 1)];
+    __shared__ double s_red[8 * (KP + 2)];
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    double v[KP + 1];
+    double v[KP + 2];
 #pragma unroll
-    for (int k = 0; k <= KP; ++k) v[k] = 0.0;
+    for (int k = 0; k <= KP + 1; ++k) v[k] = 0.0;
     if (c < N) {
-        const double* w = W + ((int64_t)r * N + c) * KP;
+        const double* wp = W + ((int64_t)r * N + c) * KP;
+        double w[KP];
 #pragma unroll
-        for (int k = 0; k < KP; ++k) { double x = w[k]; v[k] = (x == x) ? x : 0.0; }
+        for (int k = 0; k < KP; ++k) { w[k] = wp[k]; v[k] = (w[k] == w[k]) ? w[k] : 0.0; }
+        const uint32_t q = sparsify_row<KP>(w, K);
+        hq[(int64_t)r * h_stride + c] = q;
+        v[KP + 1] = q == SPARSE_DENSE ? 1.0 : 0.0;
     }
-    // [KP] (LL) is left untouched by the caller's reduce (mask below)
-    block_reduce_store<KP + 1>(v, s_red, partial + ((int64_t)r * nblk + blockIdx.x) * (KP + 1));
+    // [KP] (LL) is left untouched by the caller's reduce (with_ll = 0)
+    block_reduce_store<KP + 2>(v, s_red, partial + ((int64_t)r * nblk + blockIdx.x) * (KP + 2));
 }
 
-// partial[r][blk][KP+1] -> tail[r][0..KP] (colsum, LL); one block of 256 threads per restart, fixed order.
-static __global__ void __launch_bounds__(256) k_reduce_stats(int KP, const double* __restrict__ partial, int nblk, double* __restrict__ stats,
-                                                      int64_t stats_stride, int64_t tail_off, int with_ll,
+// partial[r][blk][NV] -> tail[r][0..NV): column mass [0,KP), LL [KP] (if with_ll), dense-path cell count [KP+1] (if NV = KP+2);
+// one block of 256 threads per restart, fixed order.
+static __global__ void __launch_bounds__(256) k_reduce_stats(int KP, int NV, const double* __restrict__ partial, int nblk,
+                                                      double* __restrict__ stats, int64_t stats_stride, int64_t tail_off, int with_ll,
                                                       const int32_t* __restrict__ done) {
     const int r = blockIdx.x;
     if (done && done[r]) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int NV = KP + 1;
     for (int k = warp; k < NV; k += 8) {
         double s = 0.0;
         for (int b = lane; b < nblk; b += 32) s += partial[((int64_t)r * nblk + b) * NV + k];
 #pragma unroll
         for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (lane == 0 && (k < KP || with_ll)) stats[(int64_t)r * stats_stride + tail_off + k] = s;
+        if (lane == 0 && (k != KP || with_ll)) stats[(int64_t)r * stats_stride + tail_off + k] = s;
     }
 }
 

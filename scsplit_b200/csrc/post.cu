@@ -264,7 +264,7 @@ int scs_doublet_scores(scs_ctx* ctx, int K, const double* P, const uint8_t* mask
     ctx->launches++;
     SCS_TRY(launch_spmm(ctx, 0, KP, 1, d_T, 2 * V * KP, d_L, N * KP, nullptr));
     SCS_DISPATCH_KP2(KP, (k_masked_colsum<KPc><<<nblk, CELL_BLOCK, 0, st>>>(N, d_L, d_mask, d_part)));
-    k_reduce_stats<<<1, 256, 0, st>>>(KP, d_part, nblk, d_out, KP + 2, 0, 1, nullptr);
+    k_reduce_stats<<<1, 256, 0, st>>>(KP, KP + 1, d_part, nblk, d_out, KP + 2, 0, 1, nullptr);
     ctx->launches += 2;
     if (ctx->world > 1) SCS_TRY(comm_allreduce_f64(ctx, d_out, KP));
     SCS_CUDA(cudaMemcpyAsync(out, d_out, (size_t)K * 8, cudaMemcpyDeviceToHost, st));

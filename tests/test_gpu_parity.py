@@ -44,7 +44,7 @@ def test_layout_kalt_seed(golden, E):
         assert np.array_equal(eng.seed_af(lab, g["K"]), g["P0"])            # scSplit:137-145, bit-exact
 
 
-@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("variant", [0, 1, 2])
 def test_step_trace(golden, E, variant):
     from oracle import em_oracle as O
     from scsplit_b200._lib import SCS_L, SCS_LPS, SCS_P, SCS_W
@@ -189,6 +189,37 @@ def test_post_em(golden, E):
         assert_close(paf[keep], g["pa_matrix"], 0, "pa_matrix")
 
 
+def test_sparse_mstep_matches_dense(E):
+    """The saturated-posterior M-step kernel (variant 0) against the tiled SpMM (variant 2) and the oracle on posteriors that
+    are (a) fully saturated, (b) saturated with a few soft cells (gathered as dense rows), (c) mostly soft (gate -> dense)."""
+    from oracle import em_oracle as O
+    from scsplit_b200._lib import SCS_LPS, SCS_P, SCS_W
+    g = load_golden("k5_d025")
+    K, N = g["K"], int(g["N"])
+    rng = np.random.default_rng(3)
+    lab = rng.integers(0, K, N)
+    hard = np.full((N, K), 1e-120)
+    hard[np.arange(N), lab] = 1.0 - rng.random(N) * 1e-13
+    few = hard.copy()
+    soft_rows = rng.choice(N, 7, replace=False)
+    few[soft_rows] = rng.dirichlet(np.ones(K), 7)
+    mostly = rng.dirichlet(np.ones(K), N)
+    for name, W in (("saturated", hard), ("few soft", few), ("mostly soft", mostly)):
+        out = {}
+        for variant in (0, 2):
+            with E(g["ref"], g["alt"]) as eng:
+                eng.set_variant(variant)
+                eng.em_begin(g["P0"])
+                eng.set(SCS_W, W)
+                eng.mstep()
+                out[variant] = (eng.get(SCS_P), eng.get(SCS_LPS), eng.stats()["S"].copy())
+        P_o, lPs_o = O.mstep(g["ref"], g["alt"], W, g["k_alt"])
+        for variant in (0, 2):
+            assert_close(out[variant][0], P_o, RTOL, "%s P variant %d" % (name, variant))
+            assert_close(out[variant][1], lPs_o, RTOL, "%s lPs variant %d" % (name, variant))
+        assert np.allclose(out[0][2], out[2][2], rtol=1e-12, atol=1e-30)
+
+
 def test_pattern_counts(E):
     g = load_golden("k3_ragged")
     U = ((g["ref"] != 0).astype(np.int8) + (g["alt"] != 0).astype(np.int8)).tocsr()
@@ -269,7 +300,7 @@ def test_full_size_properties(E):
 
 
 @pytest.mark.parametrize("K", [1, 3, 7, 8, 11, 12, 16, 17, 24, 32])
-@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("variant", [0, 1, 2])
 def test_state_count_sweep(K, variant, E):
     """Every compiled table width (KP = 2..32: row groups of 1, 2, 4, 8 and 16 lanes) against the oracle, incl. K = 17 of
     BASELINE config 4; the pool is sized so that the E-step operand spans several shared-memory tiles (2V*KP*8 > 208 KB)."""
