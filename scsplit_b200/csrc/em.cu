@@ -156,12 +156,17 @@ static int run_m(scs_ctx* ctx, const int32_t* done, int track, int check_conv) {
             }
             k_mstep_sparse<KPc><<<grid, SPARSE_THREADS, smem, ctx->stream>>>(ctx->M.nrows, N, em.K, ctx->M.lptr, ctx->M.lcode, ctx->M.hptr,
                                                                            ctx->M.hcode, ctx->M.hcnt, em.hq, em.h_stride, em.W, em.stats,
-                                                                           em.stats_stride, gate, em.stats_stride, gate_thr, done);
+                                                                           em.stats_stride, em.sparse_only ? nullptr : gate, em.stats_stride,
+                                                                           gate_thr, done);
         });
         ctx->launches++;
         SCS_TRY(timing_end(ctx, 2, ea, eb));
     }
-    SCS_TRY(launch_spmm(ctx, 1, em.KP, em.R, em.W, N * em.KP, em.stats, em.stats_stride, done, gate, em.stats_stride, gate_thr));
+    // (the sparse kernel is correct for ANY number of unsaturated cells, only slower; once a poll has seen every restart
+    // saturated the tiled pair is not launched at all until a later poll says otherwise)
+    if (!(sparse && em.sparse_only))
+        SCS_TRY(launch_spmm(ctx, 1, em.KP, em.R, em.W, N * em.KP, em.stats, em.stats_stride, done, gate, em.stats_stride, gate_thr));
+    else if (ctx->timing) ctx->t_cnt[1] += 1;   // keep the per-M-step average well defined
     if (ctx->world > 1) SCS_TRY(comm_allreduce_f64(ctx, em.stats, (int64_t)em.R * em.stats_stride));
     dim3 grid((unsigned)((V * em.KP + 255) / 256), (unsigned)em.R);
     k_finalize<<<grid, 256, 0, ctx->stream>>>(V, em.K, em.KP, em.stats, em.stats_stride, ctx->kalt, em.P, em.T, done);
@@ -262,18 +267,27 @@ int scs_em_iterate(scs_ctx* ctx, int n_iter, int check_conv) {
     EmState& em = ctx->em;
     const int32_t* done = check_conv ? em.done : nullptr;
     std::vector<int32_t> h_done((size_t)em.R);
-    const int POLL = 8;   // iterations between host polls of the device-side convergence flags
+    std::vector<double> h_dense((size_t)em.R);
+    const int POLL = 8;   // iterations between host polls of the device-side convergence flags and saturation counts
+    const double* d_dense = em.stats + 2 * ctx->V * em.KP + em.KP + 1;
+    const double dense_thr = (double)std::max<int64_t>(4, ctx->N / 128);
     if (!ctx->ev_iter[0]) { SCS_CUDA(cudaEventCreate(&ctx->ev_iter[0])); SCS_CUDA(cudaEventCreate(&ctx->ev_iter[1])); }
     SCS_CUDA(cudaEventRecord(ctx->ev_iter[0], ctx->stream));
     for (int i = 0; i < n_iter; ++i) {
         SCS_TRY(run_e(ctx, done));
         SCS_TRY(run_m(ctx, done, 1, check_conv));
-        if (check_conv && ((i + 1) % POLL == 0 || i + 1 == n_iter)) {
+        if ((i + 1) % POLL == 0 || (check_conv && i + 1 == n_iter)) {
             SCS_CUDA(cudaMemcpyAsync(h_done.data(), em.done, (size_t)em.R * 4, cudaMemcpyDeviceToHost, ctx->stream));
+            SCS_CUDA(cudaMemcpy2DAsync(h_dense.data(), 8, d_dense, (size_t)em.stats_stride * 8, 8, (size_t)em.R, cudaMemcpyDeviceToHost,
+                                       ctx->stream));
             SCS_CUDA(cudaStreamSynchronize(ctx->stream));
-            bool all = true;
-            for (int32_t d : h_done) all = all && d;
-            if (all) break;
+            bool all = true, saturated = true;
+            for (int r = 0; r < em.R; ++r) {
+                all = all && h_done[r];
+                if (!(check_conv && h_done[r])) saturated = saturated && (h_dense[r] <= dense_thr);
+            }
+            em.sparse_only = saturated ? 1 : 0;
+            if (check_conv && all) break;
         }
     }
     SCS_CUDA(cudaEventRecord(ctx->ev_iter[1], ctx->stream));

@@ -62,7 +62,7 @@ k_mstep_sparse(int64_t nrows, int64_t N, int K, const int64_t* __restrict__ lptr
     extern __shared__ __align__(128) unsigned char smem[];
     const int r = blockIdx.y;
     if (done && done[r]) return;
-    if (gate[(int64_t)r * gate_stride] > gate_thr) return;      // too many unsaturated cells: the tiled SpMM runs instead
+    if (gate && gate[(int64_t)r * gate_stride] > gate_thr) return;   // too many unsaturated cells: the tiled SpMM runs instead
     constexpr size_t ACC_BYTES = (size_t)SPARSE_THREADS * KP * 8;
     unsigned char* s_tab = smem + ACC_BYTES;
     uint64_t* bar = reinterpret_cast<uint64_t*>(s_tab + ((((size_t)h_stride * 4) + 127) & ~(size_t)127));
