@@ -22,6 +22,8 @@ CASES = {
     "cli_c1": dict(V=2000, N=500, samples=2, dfrac=0.0, lam=0.15, pseed=1001, n=2, d="0", e=3, seed=2001),
     "cli_k4": dict(V=1200, N=300, samples=3, dfrac=0.06, lam=0.2, pseed=31, n=3, d="0.1", e=3, seed=2002),
     "cli_k4_nod": dict(V=1200, N=300, samples=3, dfrac=0.06, lam=0.2, pseed=31, n=3, d=None, e=2, seed=2003),
+    # autodetect (-n 0): sweep K = 2..s, elbow on the LL curve (scSplit:550-558, incl. the elbow quirk of 493-501)
+    "cli_auto": dict(V=1200, N=300, samples=3, dfrac=0.0, lam=0.2, pseed=32, n=0, d="0", e=2, seed=2004, s=4),
 }
 
 
@@ -35,6 +37,8 @@ def main():
             argv = ["run", "-r", rp, "-a", ap, "-n", str(c["n"]), "-o", tmp, "-e", str(c["e"])]
             if c["d"] is not None:
                 argv += ["-d", c["d"]]
+            if "s" in c:
+                argv += ["-s", str(c["s"])]
             np.random.seed(c["seed"])
             with warnings.catch_warnings():
                 warnings.simplefilter("ignore")

@@ -341,6 +341,9 @@ def core_batched(base_calls_mtx, num, output, ems, device=0, chunk=64):
             m.lP_c_m = float(ll[r])
             m.convergence = int(iterations < 300)
             _log(output, 'Model Log-Likelihood = ' + str(m.lP_c_m) + '\n')
+            if i == ems - 1:
+                # the reference returns the LAST model object and later reads ITS lP_c_s (autodetect, scSplit:555 with 488)
+                m.lP_c_s = pd.DataFrame(eng.get(SCS_L, r), index=m.barcodes, columns=range(num))
             if m.lP_c_m > max_likelihood:
                 max_likelihood = m.lP_c_m
                 hist = eng.get(4, r)[:iterations]
