@@ -18,7 +18,7 @@ import numpy as np
 def _positions_to_drop(rng, n):
     """scSplit:113-114: sorted unique int(beta(1,10) * n) positions, int(0.1*n + 0.5) draws."""
     draws = rng.beta(1, 10, int(0.1 * n + 0.5)) * n
-    return np.sort(np.unique(list(map(int, draws)))).astype(np.int64)
+    return np.unique(draws.astype(np.int64))      # int() truncation of non-negative floats; np.unique returns sorted values
 
 
 def trim_subset(count_fn, V, N, K, rng=np.random):
@@ -47,8 +47,8 @@ def trim_subset(count_fn, V, N, K, rng=np.random):
         keep_c[:] = 0
         keep_c[icols] = 1
         row_cnt, col_cnt = count_fn(keep_r, keep_c)
-        mrows = min(col_cnt[icols])                     # scSplit:124 (named mrows, is the min COLUMN fill)
-        mcols = min(row_cnt[irows])                     # scSplit:125
+        mrows = col_cnt[icols].min()                    # scSplit:124 (named mrows, is the min COLUMN fill)
+        mcols = row_cnt[irows].min()                    # scSplit:125
     return irows, icols, nrows, ncols
 
 
