@@ -234,6 +234,7 @@ def run_cuda_arm(args):
         raise SystemExit("bench.py needs a CUDA device: scsplit_b200 has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")          # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     def barrier():

@@ -127,7 +127,7 @@ static int run_e(scs_ctx* ctx, const int32_t* done) {
     const int64_t V = ctx->V, N = ctx->N;
     SCS_TRY(launch_spmm(ctx, 0, em.KP, em.R, em.T, 2 * V * em.KP, em.L, N * em.KP, done));
     dim3 grid((unsigned)em.nblk, (unsigned)em.R);
-    SCS_DISPATCH_KP(em.KP, (k_bayes<KPc><<<grid, CELL_BLOCK, 0, ctx->stream>>>(N, em.K, em.L, em.W, em.lps, em.partial, em.nblk, em.hq,
+    SCS_DISPATCH_KP(em.KP, (k_bayes<KPc><<<grid, 1024, 0, ctx->stream>>>(N, em.K, em.L, em.W, em.lps, em.partial, em.nblk, em.hq,
                                                                               em.h_stride, done)));
     k_reduce_stats<<<em.R, 256, 0, ctx->stream>>>(em.KP, em.KP + 2, em.partial, em.nblk, em.stats, em.stats_stride, 2 * V * em.KP, 1, done);
     ctx->launches += 2;
@@ -202,7 +202,7 @@ int scs_em_begin(scs_ctx* ctx, int R, int K, const double* P0, int max_iter) {
     em.R = R; em.K = K; em.KP = round_even(K); em.max_iter = max_iter;
     const int KP = em.KP;
     em.stats_stride = 2 * V * KP + KP + 2;
-    em.nblk = (int)((N + CELL_BLOCK - 1) / CELL_BLOCK);
+    em.nblk = (int)((N + bayes_cells_per_block(KP) - 1) / bayes_cells_per_block(KP));
     SCS_TRY(dev_alloc(ctx, &em.T, (int64_t)R * 2 * V * KP));
     SCS_TRY(dev_alloc(ctx, &em.P, (int64_t)R * V * KP));
     SCS_TRY(dev_alloc(ctx, &em.L, (int64_t)R * N * KP));
@@ -252,7 +252,7 @@ int scs_mstep(scs_ctx* ctx) {
     EmState& em = ctx->em;
     // column mass of whatever W currently holds (it may have been injected with scs_em_set)
     dim3 grid((unsigned)em.nblk, (unsigned)em.R);
-    SCS_DISPATCH_KP(em.KP, (k_colsum_partial<KPc><<<grid, CELL_BLOCK, 0, ctx->stream>>>(ctx->N, em.K, em.W, em.partial, em.nblk, em.hq,
+    SCS_DISPATCH_KP(em.KP, (k_colsum_partial<KPc><<<grid, 1024, 0, ctx->stream>>>(ctx->N, em.K, em.W, em.partial, em.nblk, em.hq,
                                                                                        em.h_stride)));
     k_reduce_stats<<<em.R, 256, 0, ctx->stream>>>(em.KP, em.KP + 2, em.partial, em.nblk, em.stats, em.stats_stride, 2 * ctx->V * em.KP, 0, nullptr);
     ctx->launches += 2;

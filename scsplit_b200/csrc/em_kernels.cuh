@@ -86,13 +86,14 @@ __global__ void __launch_bounds__(256) k_spmm_rows(int64_t nrows, const int64_t*
 // Fixed-order block reduction of NV values per thread (256 threads): shuffle tree inside each warp, then the
 // 8 warp results are added in warp order.  Same bits for the same inputs, every run.
 // ---------------------------------------------------------------------------------------------------------
-template <int NV>
-__device__ __forceinline__ void block_reduce_store(double (&v)[NV], double* smem /*[8][NV]*/, double* out /*[NV]*/) {
+template <int NV, int MINO = 1>
+__device__ __forceinline__ void block_reduce_store(double (&v)[NV], double* smem /*[warps][NV]*/, double* out /*[NV]*/) {
+    // MINO > 1: only lanes that are multiples of MINO carry values (the others hold zeros), so the tree stops early
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
 #pragma unroll
-        for (int o = 16; o; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+        for (int o = 16; o >= MINO; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
     }
     if (lane == 0) {
 #pragma unroll
@@ -135,57 +136,57 @@ __device__ __forceinline__ uint32_t sparsify_row(const double (&w)[KP], int K) {
 
 // W[c,i] = 1 / sum_j 2^(((L_j + s_j) - L_i) - s_i)   (scSplit:181-185, j ascending, left-to-right)
 // ll_c   = log2( sum_k 2^((L_k - max_k L) + s_k) ) + max_k L   with pandas skipna  (scSplit:188)
-// partial[r][blk][0..KP) = sum over the block's cells of W[c,k] (NaN skipped, scSplit:198), [KP] = sum of ll_c
+// partial[r][blk][0..KP) = sum over the block's cells of W[c,k] (NaN skipped, scSplit:198), [KP] = sum of ll_c,
+// [KP+1] = number of cells whose posterior row does not pack into a sparse word.
+//
+// One cell is handled by a group of BAYES_GL lanes (lane i = state i), so the K^2 exp2 of a cell run K-wide and a 20k-cell
+// pool still gives every SM sub-partition several warps; sums over states are taken in the reference's order by shuffling.
 template <int KP>
-__global__ void __launch_bounds__(CELL_BLOCK) k_bayes(int64_t N, int K, const double* __restrict__ L, double* __restrict__ W,
+struct BayesCfg {
+    static constexpr int GL = KP <= 16 ? 16 : 32;     // lanes per cell
+    static constexpr int THREADS = 1024;
+    static constexpr int CPB = THREADS / GL;          // cells per block
+};
+inline int bayes_cells_per_block(int KP) { return KP <= 16 ? 64 : 32; }
+
+template <int KP>
+__global__ void __launch_bounds__(1024) k_bayes(int64_t N, int K, const double* __restrict__ L, double* __restrict__ W,
                                                const double* __restrict__ lps, double* __restrict__ partial, int nblk,
                                                uint32_t* __restrict__ hq, int64_t h_stride, const int32_t* __restrict__ done) {
+    using C = BayesCfg<KP>;
     const int r = blockIdx.y;
     if (done && done[r]) return;
-    __shared__ double s_lps[KP];
-    __shared__ double s_red[8 * (KP + 2)];
-    if (threadIdx.x < KP) s_lps[threadIdx.x] = lps[(int64_t)r * KP + threadIdx.x];
-    __syncthreads();
-    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ double s_red[32 * (KP + 2)];
+    const int i = threadIdx.x & (C::GL - 1);
+    const int64_t c = (int64_t)blockIdx.x * C::CPB + threadIdx.x / C::GL;
+    const bool live = c < N && i < K;
+    const double Li = live ? L[((int64_t)r * N + c) * KP + i] : 0.0;
+    const double si = i < K ? lps[(int64_t)r * KP + i] : 0.0;
+    const double ti = Li + si;                                   // L_i + s_i
+    double denom = 0.0;
+    for (int j = 0; j < K; ++j) {
+        const double tj = __shfl_sync(0xffffffffu, ti, j, C::GL);
+        denom += exp2((tj - Li) - si);
+    }
+    const double wi = live ? 1.0 / denom : 0.0;
+    if (c < N && i < KP) W[((int64_t)r * N + c) * KP + i] = wi;
+    // total log-likelihood term (skipna max, skipna sum), states taken in ascending order
+    double m = __shfl_sync(0xffffffffu, Li, 0, C::GL);
+    for (int k = 1; k < K; ++k) m = fmax(m, __shfl_sync(0xffffffffu, Li, k, C::GL));   // fmax ignores NaN operands
+    const double xi = exp2((Li - m) + si);
+    double sum = 0.0;
+    for (int k = 0; k < K; ++k) {
+        const double xk = __shfl_sync(0xffffffffu, xi, k, C::GL);
+        if (xk == xk) sum += xk;
+    }
+    double w[KP];
+#pragma unroll
+    for (int k = 0; k < KP; ++k) w[k] = __shfl_sync(0xffffffffu, wi, k, C::GL);
     double v[KP + 2];
 #pragma unroll
     for (int k = 0; k <= KP + 1; ++k) v[k] = 0.0;
-    if (c < N) {
-        const double* l = L + ((int64_t)r * N + c) * KP;
-        double Lr[KP], t[KP];
-#pragma unroll
-        for (int j = 0; j < KP / 2; ++j) { double2 x = *reinterpret_cast<const double2*>(l + 2 * j); Lr[2 * j] = x.x; Lr[2 * j + 1] = x.y; }
-#pragma unroll
-        for (int k = 0; k < KP; ++k) t[k] = Lr[k] + s_lps[k];     // L_j + s_j
-        double w[KP];
-#pragma unroll
-        for (int i = 0; i < KP; ++i) {
-            double denom = 0.0;
-            if (i < K) {
-#pragma unroll
-                for (int j = 0; j < KP; ++j)
-                    if (j < K) denom += exp2((t[j] - Lr[i]) - s_lps[i]);
-                w[i] = 1.0 / denom;
-            } else {
-                w[i] = 0.0;
-            }
-        }
-        double* wout = W + ((int64_t)r * N + c) * KP;
-#pragma unroll
-        for (int j = 0; j < KP / 2; ++j) *reinterpret_cast<double2*>(wout + 2 * j) = make_double2(w[2 * j], w[2 * j + 1]);
-        // total log-likelihood term (skipna max, skipna sum)
-        double m = Lr[0];
-#pragma unroll
-        for (int k = 1; k < KP; ++k)
-            if (k < K) m = fmax(m, Lr[k]);          // fmax ignores NaN operands; NaN only if every L is NaN
-        double s = 0.0;
-#pragma unroll
-        for (int k = 0; k < KP; ++k)
-            if (k < K) {
-                double x = exp2((Lr[k] - m) + s_lps[k]);
-                if (x == x) s += x;
-            }
-        double ll = log2(s) + m;
+    if (c < N && i == 0) {
+        const double ll = log2(sum) + m;
 #pragma unroll
         for (int k = 0; k < KP; ++k) v[k] = (w[k] == w[k]) ? w[k] : 0.0;
         v[KP] = (ll == ll) ? ll : 0.0;
@@ -193,30 +194,34 @@ __global__ void __launch_bounds__(CELL_BLOCK) k_bayes(int64_t N, int K, const do
         hq[(int64_t)r * h_stride + c] = q;
         v[KP + 1] = q == SPARSE_DENSE ? 1.0 : 0.0;       // number of cells that need the dense M-step path
     }
-    block_reduce_store<KP + 2>(v, s_red, partial + ((int64_t)r * nblk + blockIdx.x) * (KP + 2));
+    block_reduce_store<KP + 2, C::GL>(v, s_red, partial + ((int64_t)r * nblk + blockIdx.x) * (KP + 2));
 }
 
-// column mass and (state, weight) form of an arbitrary W (step-level M-step entry): same block mapping and order as k_bayes
+// column mass and packed form of an arbitrary W (step-level M-step entry): same block mapping and order as k_bayes
 template <int KP>
-__global__ void __launch_bounds__(CELL_BLOCK) k_colsum_partial(int64_t N, int K, const double* __restrict__ W, double* __restrict__ partial,
+__global__ void __launch_bounds__(1024) k_colsum_partial(int64_t N, int K, const double* __restrict__ W, double* __restrict__ partial,
                                                         int nblk, uint32_t* __restrict__ hq, int64_t h_stride) {
+    using C = BayesCfg<KP>;
     const int r = blockIdx.y;
-    __shared__ double s_red[8 * (KP + 2)];
-    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ double s_red[32 * (KP + 2)];
+    const int i = threadIdx.x & (C::GL - 1);
+    const int64_t c = (int64_t)blockIdx.x * C::CPB + threadIdx.x / C::GL;
+    const double wi = (c < N && i < K) ? W[((int64_t)r * N + c) * KP + i] : 0.0;
+    double w[KP];
+#pragma unroll
+    for (int k = 0; k < KP; ++k) w[k] = __shfl_sync(0xffffffffu, wi, k, C::GL);
     double v[KP + 2];
 #pragma unroll
     for (int k = 0; k <= KP + 1; ++k) v[k] = 0.0;
-    if (c < N) {
-        const double* wp = W + ((int64_t)r * N + c) * KP;
-        double w[KP];
+    if (c < N && i == 0) {
 #pragma unroll
-        for (int k = 0; k < KP; ++k) { w[k] = wp[k]; v[k] = (w[k] == w[k]) ? w[k] : 0.0; }
+        for (int k = 0; k < KP; ++k) v[k] = (w[k] == w[k]) ? w[k] : 0.0;
         const uint32_t q = sparsify_row<KP>(w, K);
         hq[(int64_t)r * h_stride + c] = q;
         v[KP + 1] = q == SPARSE_DENSE ? 1.0 : 0.0;
     }
     // [KP] (LL) is left untouched by the caller's reduce (with_ll = 0)
-    block_reduce_store<KP + 2>(v, s_red, partial + ((int64_t)r * nblk + blockIdx.x) * (KP + 2));
+    block_reduce_store<KP + 2, C::GL>(v, s_red, partial + ((int64_t)r * nblk + blockIdx.x) * (KP + 2));
 }
 
 // partial[r][blk][NV] -> tail[r][0..NV): column mass [0,KP), LL [KP] (if with_ll), dense-path cell count [KP+1] (if NV = KP+2);
