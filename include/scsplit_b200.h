@@ -138,7 +138,8 @@ int scs_launch_count(scs_ctx* ctx, int64_t* out);
  * out[2]=#E launches timed, out[3]=#M launches timed.  Timing is enabled by scs_set_timing(ctx,1). */
 int scs_set_timing(scs_ctx* ctx, int enable);
 int scs_kernel_times(scs_ctx* ctx, double out[4], int reset);
-/* select kernel variant: 0 = auto, 1 = v1 (warp-per-row, L2 gathers), 2 = v2 (tiled shared-memory gathers) */
+/* select kernel variant: 0 = auto (tiled shared-memory SpMM; sparse M-step once posteriors saturate), 1 = v1 (warp per row,
+ * gathers from L1/L2; for A/B tests), 2 = tiled SpMM for both half-steps (sparse M-step off) */
 int scs_set_variant(scs_ctx* ctx, int variant);
 
 #if defined(__GNUC__)

@@ -1,19 +1,22 @@
 // EM kernels of the scSplit hot path (sm_100a).  See DESIGN.md for the roofline of each.
 //
-//   k_spmm_rows     Y[row,:] = sum_{count-1 entries} X[g(code),:] + sum_{count>1 entries} cnt * X[g(code),:]
-//                   E-step:  rows = cells,        X = log table T[2V][KP],  Y = L[N][KP]      (scSplit:175-178)
-//                   M-step:  rows = 2V pseudo-rows, X = W[N][KP],           Y = S[2V][KP]     (scSplit:196)
-//   k_bayes         W, per-cell LL, fixed-order block partials of column mass and LL           (scSplit:181-188)
-//   k_reduce_stats  block partials -> colsum[K], LL                                            (scSplit:188,198)
-//   k_finalize      S, k_alt -> P, log2 P, log2(1-P)                                            (scSplit:196, 176-177)
-//   k_update_prior  colsum -> lP_s; LL history; bitwise stop rule                               (scSplit:198, 156-161)
+//   k_spmm_rows      v1 SpMM (warp per row, gathers from global); the production SpMM is k_spmm_tiled (spmm_tiled.cuh)
+//                    Y[row,:] = sum_{count-1 entries} X[g(code),:] + sum_{count>1 entries} cnt * X[g(code),:]
+//                    E-step:  rows = cells,          X = log table T[2V][KP],  Y = L[N][KP]     (scSplit:175-178)
+//                    M-step:  rows = 2V pseudo-rows, X = W[N][KP],             Y = S[2V][KP]    (scSplit:196)
+//   k_bayes          W, per-cell LL, packed sparse posterior word, fixed-order block partials    (scSplit:181-188)
+//   k_colsum_partial the same partials for an injected W (step-level M-step entry)
+//   k_reduce_stats   block partials -> colsum[K], LL, dense-cell count                           (scSplit:188,198)
+//   k_finalize       S, k_alt -> P, log2 P, log2(1-P)                                             (scSplit:196, 176-177)
+//   k_update_prior   colsum -> lP_s; LL history; bitwise stop rule                                (scSplit:198, 156-161)
+//   (k_mstep_sparse, the M-step for saturated posteriors, lives in mstep_sparse.cuh)
 #pragma once
 #include "common.cuh"
 
 namespace scs {
 
-// threads per block of the per-cell kernels (k_bayes, k_colsum_partial, k_masked_colsum): small blocks so that even
-// 20k cells give >2 CTAs per SM; the block count fixes the order of the two-level column-mass / LL reduction
+// threads per block of the thread-per-cell kernel k_masked_colsum (post.cu): small blocks so that even 20k cells give >2
+// CTAs per SM; the block count fixes the order of its two-level reduction
 constexpr int CELL_BLOCK = 64;
 
 __device__ __forceinline__ double2 ldg2(const double* p) { return __ldg(reinterpret_cast<const double2*>(p)); }
