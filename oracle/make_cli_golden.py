@@ -20,7 +20,7 @@ from scsplit_b200 import synth  # noqa: E402
 
 CASES = {
     "cli_c1": dict(V=2000, N=500, samples=2, dfrac=0.0, lam=0.15, pseed=1001, n=2, d="0", e=3, seed=2001),
-    "cli_k4": dict(V=1200, N=300, samples=3, dfrac=0.06, lam=0.2, pseed=31, n=3, d="0.1", e=3, seed=2002),
+    "cli_k4": dict(V=1200, N=300, samples=3, dfrac=0.06, lam=0.2, pseed=31, n=3, d="0.1", e=3, seed=2002, genotype=True),
     "cli_k4_nod": dict(V=1200, N=300, samples=3, dfrac=0.06, lam=0.2, pseed=31, n=3, d=None, e=2, seed=2003),
     # autodetect (-n 0): sweep K = 2..s, elbow on the LL curve (scSplit:550-558, incl. the elbow quirk of 493-501)
     "cli_auto": dict(V=1200, N=300, samples=3, dfrac=0.0, lam=0.2, pseed=32, n=0, d="0", e=2, seed=2004, s=4),
@@ -56,6 +56,14 @@ def main():
                        result_header=np.array([head]), psc=psc.values, psc_index=np.array(list(map(str, psc.index.tolist())), dtype=str), psc_columns=np.array(list(map(str, psc.columns.tolist())), dtype=str),
                        pa=pa.values.astype(np.float64), pa_index=np.array(list(map(str, pa.index.tolist())), dtype=str), pa_columns=np.array(list(map(str, pa.columns.tolist())), dtype=str),
                        dist_variants=np.array(sorted(dv)), log=np.array([log]))
+            if c.get("genotype"):
+                with warnings.catch_warnings():
+                    warnings.simplefilter("ignore")
+                    ref_loader.run_reference_cli(["genotype", "-r", rp, "-a", ap, "-p", os.path.join(tmp, "scSplit_P_s_c.csv"), "-o", tmp])
+                with open(os.path.join(tmp, "scSplit.vcf")) as f:
+                    out["vcf"] = np.array([f.read()])
+                with open(os.path.join(tmp, "scSplit_P_s_c.csv")) as f:
+                    out["psc_csv"] = np.array([f.read()])
             np.savez_compressed(os.path.join(ROOT, "tests", "golden", name + ".npz"), **out)
             print(name, res["Cluster"].value_counts().to_dict(), len(dv), "variants")
         finally:

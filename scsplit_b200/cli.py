@@ -1,7 +1,7 @@
 """`scSplit run` drop-in: same flags, same input CSVs, same five output files and log lines (scSplit:467-600).
 
-Only the `run` sub-command is in scope; `count` (BAM pile-up, pysam) and `genotype` are not part
-of the EM hot path and are reported as such.
+`run` is the hot path; `genotype` (section 8f rank 3, a direct consumer of scSplit_P_s_c.csv) reuses the
+hard-sum kernel; `count` (BAM pile-up, pysam) is upstream of the path and is reported as out of scope.
 """
 import argparse
 import datetime
@@ -144,16 +144,93 @@ def run(argv):
     return model
 
 
+# GRCh37 contig table of the VCF header the reference writes (scSplit:679-692); kept verbatim for byte-compatible output
+_VCF_CONTIGS = [("1", 249250621), ("10", 135534747), ("11", 135006516), ("12", 133851895), ("13", 115169878), ("14", 107349540),
+                ("15", 102531392), ("16", 90354753), ("17", 81195210), ("18", 78077248), ("19", 59128983), ("2", 243199373),
+                ("20", 63025520), ("21", 48129895), ("22", 51304566), ("3", 198022430), ("4", 191154276), ("5", 180915260),
+                ("6", 171115067), ("7", 159138663), ("8", 146364022), ("9", 141213431), ("MT", 16569), ("X", 155270560),
+                ("Y", 59373566)]
+
+
+def _vcf_header():
+    lines = ['##fileformat=VCFv4.2', '##fileDate=' + str(datetime.datetime.today()).split(' ')[0], '##source=scSplit']
+    lines += ['##contig=<ID=%s,length=%d>' % c for c in _VCF_CONTIGS]
+    lines += ['##FILTER=<ID=PASS,Description="All filters passed">',
+              '##INFO=<ID=AN,Number=1,Type=Integer,Description="Total Allele Count">',
+              '##INFO=<ID=AC,Number=A,Type=Integer,Description="Alternate Allele Count">',
+              '##INFO=<ID=AF,Number=A,Type=Float,Description="Estimated Alternate Allele Frequency">',
+              '##FORMAT=<ID=GL,Number=3,Type=Float,Description="Genotype Likelihood for RR/RA/AA">']
+    return '\n'.join(lines) + '\n'
+
+
+def genotype(argv):
+    """`scSplit genotype` (scSplit:603-696): per-cluster genotype likelihoods from the hard (P(s|c) >= 0.9) allele sums.
+
+    The sums alt.dot(A), (alt+ref).dot(A) (scSplit:637-639) are the integer cluster sums of `scs_cluster_counts`; the
+    binomial pmf at p in {err, 0.5, 1-err}, the GP/GL rounding and the VCF text follow the reference on the host.
+    """
+    import csv
+    from scipy.stats import binom
+    from .engine import Engine
+    parser = argparse.ArgumentParser(prog='scSplit genotype', description='Generate sample genotypes in VCF format')
+    parser.add_argument('-r', '--ref', required=True, help='REF count CSV input')
+    parser.add_argument('-a', '--alt', required=True, help='ALT count CSV input')
+    parser.add_argument('-p', '--psc', required=True, help='generated P(S|C)')
+    parser.add_argument('-o', '--out', required=True, help='Output directory')
+    parser.add_argument('--device', type=int, default=0, help='CUDA device ordinal (scsplit_b200 extension)')
+    args = parser.parse_args(argv)
+    if not os.path.exists(args.out):
+        raise ValueError('Specified output directory does not exist')
+    ref_s, all_POS, _ = read_count_csv(args.ref)
+    alt_s, _, _ = read_count_csv(args.alt)
+    P_s_c = pd.read_csv(args.psc, header=0, index_col=0)
+    num = len(P_s_c.columns)
+    hit = (P_s_c.values >= 0.9)
+    if (hit.sum(axis=1) > 1).any():
+        raise ValueError('a barcode has P(s|c) >= 0.9 for two clusters')
+    labels = np.where(hit.any(axis=1), hit.argmax(axis=1), -1).astype(np.int32)
+    with Engine(ref_s, alt_s, device=args.device) as eng:
+        n_ref, n_alt, _ = eng.cluster_counts(labels, num)
+    k = pd.DataFrame(n_alt.astype(np.float64))
+    n = pd.DataFrame((n_alt + n_ref).astype(np.float64))
+    err = 0.01
+    ids = all_POS.tolist()
+
+    def log_pmf(p):
+        return pd.DataFrame(binom.pmf(k, n, [p] * num), index=ids, columns=range(num)).apply(np.log10)
+
+    lp_rr, lp_ra, lp_aa = log_pmf(err), log_pmf(0.5), log_pmf(1 - err)
+    gl_rr, gl_ra, gl_aa = 10 ** lp_rr.astype(float), 10 ** lp_ra.astype(float), 10 ** lp_aa.astype(float)
+    nom = gl_rr + gl_ra + gl_aa
+    text = lambda frame: round(frame, 3).astype(str)
+    gp = [text(gl_rr / nom), text(gl_ra / nom), text(gl_aa / nom)]
+    lg = [text(lp_rr.astype(float)), text(lp_ra.astype(float)), text(lp_aa.astype(float))]
+    cols = {'#CHROM': [i.split(':')[0] for i in ids], 'POS': [i.split(':')[1] for i in ids], 'ID': ids}
+    for name in ('REF', 'ALT', 'QUAL', 'FILTER', 'INFO'):
+        cols[name] = '.'
+    cols['FORMAT'] = 'GP:GL'
+    vcf_content = pd.DataFrame(cols, index=ids)
+    for c in range(num):
+        vcf_content[c] = gp[0][c] + ',' + gp[1][c] + ',' + gp[2][c] + ':' + lg[0][c] + ',' + lg[1][c] + ',' + lg[2][c]
+    with open(os.path.join(args.out, r'scSplit.vcf'), 'w+') as f:
+        f.write(_vcf_header())
+        vcf_content.to_csv(f, index=False, sep='\t', quoting=csv.QUOTE_NONE, escapechar='"')
+    return vcf_content
+
+
 def main(argv=None):
     argv = sys.argv[1:] if argv is None else list(argv)
     if not argv or argv[0] in ('-h', '--help'):
-        print('usage: scSplit <command> [<args>]\n\nCommands:\n   run       Demultiplex the scRNA-Seq using REF/ALT count matrices (B200 CUDA path)')
+        print('usage: scSplit <command> [<args>]\n\nCommands:\n   run       Demultiplex the scRNA-Seq using REF/ALT count matrices (B200 CUDA path)\n   genotype  Generate sample genotypes in VCF format')
         return 0
     if argv[0] == 'run':
         run(argv[1:])
         return 0
-    if argv[0] in ('count', 'genotype'):
-        raise SystemExit('scsplit_b200 accelerates `scSplit run` only; `%s` is outside the EM hot path (use the reference)' % argv[0])
+    if argv[0] == 'genotype':
+        genotype(argv[1:])
+        return 0
+    if argv[0] == 'count':
+        raise SystemExit('scsplit_b200 accelerates `scSplit run` (and `genotype`); `count` (BAM pile-up) is outside the EM hot path')
     raise SystemExit('unknown command %r' % argv[0])
 
 
