@@ -3,7 +3,7 @@
 // When nearly every posterior row packs into one 32-bit word (state, 1 - weight; see sparsify_row in em_kernels.cuh) the
 // M-step sums S[g, k] = sum_{entries of pseudo-row g} W[cell, k] need 4 bytes of posterior per entry instead of a KP*8-byte
 // row.  The packed words of ALL cells are staged in shared memory with TMA bulk copies (4 bytes x N), a group of 8 lanes
-// walks one pseudo-row of the SNV-major stream (4 rows per warp), and every lane owns K fp64 accumulators in shared
+// walks one pseudo-row of the SNV-major stream (2 rows per warp), and every lane owns K fp64 accumulators in shared
 // memory laid out [state][lane] -- the bank is the lane, so the data-dependent read-modify-write is conflict-free.  A
 // fixed xor-shuffle tree over the 8 lanes finishes a row.  Cells that are not saturated are gathered as full rows from
 // global memory.  The kernel runs only when the dense-path cell count published by k_reduce_stats is below the gate
@@ -15,7 +15,8 @@
 namespace scs {
 
 constexpr int SPARSE_THREADS = 1024;
-constexpr int SPARSE_GS = 8;                       // lanes per pseudo-row
+constexpr int SPARSE_GS = 16;                      // lanes per pseudo-row (>= KP/2: the row's column pairs are stored by lanes 0..KP/2-1)
+static_assert(SPARSE_GS * 2 >= SCS_MAX_K, "a row group must cover all column pairs");
 
 inline size_t sparse_smem_bytes(int64_t h_stride, int KP) {
     const size_t acc = (size_t)SPARSE_THREADS * KP * 8;                  // [warp][state][lane] fp64
@@ -86,7 +87,7 @@ k_mstep_sparse(int64_t nrows, int64_t N, int K, const int64_t* __restrict__ lptr
     S += (int64_t)r * s_stride;
     const int li = lane & (SPARSE_GS - 1), g = lane / SPARSE_GS;
     constexpr int GPW = 32 / SPARSE_GS;
-    // 4 consecutive pseudo-rows per warp and step (consecutive rows are the same allele: similar lengths)
+    // GPW consecutive pseudo-rows per warp and step (consecutive rows are the same allele: similar lengths)
     for (int64_t row0 = ((int64_t)blockIdx.x * nwarps + warp) * GPW; row0 < nrows; row0 += (int64_t)gridDim.x * nwarps * GPW) {
         const int64_t row = row0 + g;
         const bool act = row < nrows;
@@ -118,7 +119,7 @@ k_mstep_sparse(int64_t nrows, int64_t N, int K, const int64_t* __restrict__ lptr
             sparse_add<KP>(acc_base, K, lds_u32(tab + (uint32_t)c0 * 4u), c0, W, (double)__ldg(hcnt + h));
         }
         __syncwarp();
-        // fixed tree over the 8 lanes of the row group, state by state; slots are reset on the way
+        // fixed tree over the lanes of the row group, state by state; slots are reset on the way
         double tot[KP];
 #pragma unroll
         for (int k = 0; k < KP; ++k) {

@@ -220,6 +220,32 @@ def test_sparse_mstep_matches_dense(E):
         assert np.allclose(out[0][2], out[2][2], rtol=1e-12, atol=1e-30)
 
 
+@pytest.mark.parametrize("K", [2, 8, 9, 16, 17, 24, 32])
+def test_sparse_mstep_state_counts(K, E):
+    """Saturated posteriors for every row-group width of the sparse M-step kernel (incl. K > 16: all column pairs stored)."""
+    from oracle import em_oracle as O
+    from scsplit_b200 import synth
+    from scsplit_b200._lib import SCS_P, SCS_W
+    V, N = 1500, 500
+    pool = synth.make_pool(V, N, 3, 0.0, 0.2, seed=300 + K)
+    rng = np.random.default_rng(K)
+    W = np.full((N, K), 1e-200)
+    W[np.arange(N), rng.integers(0, K, N)] = 1.0 + (rng.random(N) - 0.5) * 2e-13
+    W[rng.choice(N, 3, replace=False)] = rng.dirichlet(np.ones(K), 3)          # a few dense rows
+    res = {}
+    for variant in (0, 2):
+        with E(pool.ref, pool.alt) as eng:
+            eng.set_variant(variant)
+            eng.em_begin(np.full((V, K), 0.5))
+            eng.set(SCS_W, W)
+            eng.mstep()
+            res[variant] = (eng.get(SCS_P), eng.stats()["S"].copy())
+    P_o, _ = O.mstep(pool.ref, pool.alt, W, O.kalt(pool.ref, pool.alt))
+    assert_close(res[0][0], P_o, RTOL, "sparse P K=%d" % K)
+    assert_close(res[2][0], P_o, RTOL, "dense P K=%d" % K)
+    assert np.allclose(res[0][1], res[2][1], rtol=1e-12, atol=1e-30)
+
+
 def test_pattern_counts(E):
     g = load_golden("k3_ragged")
     U = ((g["ref"] != 0).astype(np.int8) + (g["alt"] != 0).astype(np.int8)).tocsr()
