@@ -144,6 +144,15 @@ __device__ __forceinline__ uint32_t sparsify_row(const double (&w)[KP], int K) {
 //
 // One cell is handled by a group of BAYES_GL lanes (lane i = state i), so the K^2 exp2 of a cell run K-wide and a 20k-cell
 // pool still gives every SM sub-partition several warps; sums over states are taken in the reference's order by shuffling.
+// 2^x for the Bayes ratios.  Saturated posteriors make almost every exponent either hugely negative or hugely positive;
+// exp2 returns exactly 0 below -1075 and exactly +inf from 1024 on, so those lanes skip the (long) double-precision exp2
+// sequence without changing a bit of the result.  NaN exponents fall through to exp2 and stay NaN.
+__device__ __forceinline__ double exp2_sat(double x) {
+    if (x < -1100.0) return 0.0;
+    if (x > 1100.0) return __longlong_as_double(0x7ff0000000000000LL);
+    return exp2(x);
+}
+
 template <int KP>
 struct BayesCfg {
     static constexpr int GL = KP <= 16 ? 16 : 32;     // lanes per cell
@@ -169,14 +178,14 @@ __global__ void __launch_bounds__(1024) k_bayes(int64_t N, int K, const double* 
     double denom = 0.0;
     for (int j = 0; j < K; ++j) {
         const double tj = __shfl_sync(0xffffffffu, ti, j, C::GL);
-        denom += exp2((tj - Li) - si);
+        denom += exp2_sat((tj - Li) - si);
     }
     const double wi = live ? 1.0 / denom : 0.0;
     if (c < N && i < KP) W[((int64_t)r * N + c) * KP + i] = wi;
     // total log-likelihood term (skipna max, skipna sum), states taken in ascending order
     double m = __shfl_sync(0xffffffffu, Li, 0, C::GL);
     for (int k = 1; k < K; ++k) m = fmax(m, __shfl_sync(0xffffffffu, Li, k, C::GL));   // fmax ignores NaN operands
-    const double xi = exp2((Li - m) + si);
+    const double xi = exp2_sat((Li - m) + si);
     double sum = 0.0;
     for (int k = 0; k < K; ++k) {
         const double xk = __shfl_sync(0xffffffffu, xi, k, C::GL);
