@@ -202,18 +202,19 @@ __device__ __forceinline__ int64_t row_lower_bound(const uint32_t* __restrict__ 
 
 // one thread per unit u = tile * nrows + row: entries of `row` inside `tile`, padded to a multiple of `pad`
 __global__ void k_tile_counts(int64_t nrows, int ntiles, int TR, int pad, const int64_t* __restrict__ lptr,
-                              const uint32_t* __restrict__ lcode, int64_t* __restrict__ cnt) {
+                              const uint32_t* __restrict__ lcode, int64_t* __restrict__ cnt, int32_t* __restrict__ ulo) {
     const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (u >= nrows * ntiles) return;
     const int64_t t = u / nrows, row = u - t * nrows;
     const int64_t b = lptr[row], e = lptr[row + 1];
     const int64_t lo = row_lower_bound(lcode, b, e, t * TR), hi = row_lower_bound(lcode, b, e, (t + 1) * (int64_t)TR);
     cnt[u] = ((hi - lo) + pad - 1) / pad * pad;
+    ulo[u] = (int32_t)(lo - b);     // where the unit's entries start inside the row (a row holds < 2^31 entries)
 }
 
 // one warp per row: scatter its entries to their units as 16-bit in-tile offsets; pad slots point at the zero row
 __global__ void k_tile_scatter(int64_t nrows, int ntiles, int TR, const int64_t* __restrict__ lptr, const uint32_t* __restrict__ lcode,
-                               const int64_t* __restrict__ tptr, uint16_t* __restrict__ tcode) {
+                               const int64_t* __restrict__ tptr, const int32_t* __restrict__ ulo, uint16_t* __restrict__ tcode) {
     const int lane = threadIdx.x & 31;
     const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= nrows) return;
@@ -221,13 +222,13 @@ __global__ void k_tile_scatter(int64_t nrows, int ntiles, int TR, const int64_t*
     for (int64_t i = b + lane; i < e; i += 32) {
         const int64_t g = (int64_t)(lcode[i] >> 1);
         const int64_t t = g / TR;
-        const int64_t lo = row_lower_bound(lcode, b, e, t * TR);
-        tcode[tptr[t * nrows + row] + (i - lo)] = (uint16_t)(g - t * TR);
+        const int64_t u = t * nrows + row;
+        tcode[tptr[u] + (i - b - ulo[u])] = (uint16_t)(g - t * TR);
     }
     for (int64_t t = lane; t < ntiles; t += 32) {   // pad slots: from the unit's true count up to its padded length
-        const int64_t lo = row_lower_bound(lcode, b, e, t * TR), hi = row_lower_bound(lcode, b, e, (t + 1) * (int64_t)TR);
         const int64_t u = t * nrows + row, base = tptr[u], plen = tptr[u + 1] - base;
-        for (int64_t k = hi - lo; k < plen; ++k) tcode[base + k] = (uint16_t)TR;
+        const int64_t cnt = (t + 1 < ntiles ? (int64_t)ulo[u + nrows] : e - b) - ulo[u];
+        for (int64_t k = cnt; k < plen; ++k) tcode[base + k] = (uint16_t)TR;
     }
 }
 
@@ -280,7 +281,9 @@ int build_tiled(scs_ctx* ctx, const Stream& s, TiledStream& t, int KP, int TR, i
     cudaStream_t st = ctx->stream;
     SCS_TRY(dev_alloc(ctx, &t.tptr, t.nunits + 1));
     SCS_CUDA(cudaMemsetAsync(t.tptr, 0, sizeof(int64_t), st));
-    k_tile_counts<<<(unsigned)((t.nunits + 255) / 256), 256, 0, st>>>(s.nrows, t.ntiles, TR, pad, s.lptr, s.lcode, t.tptr + 1);
+    int32_t* d_ulo = nullptr;
+    SCS_CUDA(cudaMallocAsync((void**)&d_ulo, (size_t)t.nunits * 4, st));
+    k_tile_counts<<<(unsigned)((t.nunits + 255) / 256), 256, 0, st>>>(s.nrows, t.ntiles, TR, pad, s.lptr, s.lcode, t.tptr + 1, d_ulo);
     ctx->launches++;
     size_t tb = 0;
     SCS_CUDA(cub::DeviceScan::InclusiveSum(nullptr, tb, t.tptr + 1, t.tptr + 1, t.nunits, st));
@@ -294,7 +297,8 @@ int build_tiled(scs_ctx* ctx, const Stream& s, TiledStream& t, int KP, int TR, i
     SCS_CUDA(e); SCS_CUDA(e2); SCS_CUDA(e3);
     ctx->launches += 2;
     SCS_TRY(dev_alloc(ctx, &t.tcode, total + 2));
-    k_tile_scatter<<<(unsigned)((s.nrows + 7) / 8), 256, 0, st>>>(s.nrows, t.ntiles, TR, s.lptr, s.lcode, t.tptr, t.tcode);
+    k_tile_scatter<<<(unsigned)((s.nrows + 7) / 8), 256, 0, st>>>(s.nrows, t.ntiles, TR, s.lptr, s.lcode, t.tptr, d_ulo, t.tcode);
+    cudaFreeAsync(d_ulo, st);
     ctx->launches++;
     // ---- static work plan: CTA ranges (device), tile segments (host, <= ncta + ntiles of them), group cuts (device)
     t.ncta = ncta;

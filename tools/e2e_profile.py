@@ -13,7 +13,7 @@ pa = csr_matrix((pin(alt.data.astype(np.int16)), pin(alt.indices.astype(np.int32
 eng = Engine(pr, pa, canonicalize=False)
 P0 = eng.seed_af(bench.random_seed_labels(pool.ref.shape[1], K, 0), K); eng.close()
 P0p, outW, outP = pin(P0), pin(np.empty((ref.shape[1], K))), pin(np.empty((ref.shape[0], K)))
-for rep in range(4):
+for rep in range(10):
     t=[time.perf_counter()]
     eng = Engine(pr, pa, canonicalize=False); t.append(time.perf_counter())
     eng.em_begin(P0p); t.append(time.perf_counter())
