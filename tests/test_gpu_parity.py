@@ -398,3 +398,53 @@ def test_config3_full_size_properties(E):
         n_ref, n_alt, _ = eng.cluster_counts(labels, K)
         assert np.array_equal(n_ref.sum(axis=1), np.asarray(pool.ref.sum(axis=1)).ravel())
         assert np.array_equal(n_alt.sum(axis=1), np.asarray(pool.alt.sum(axis=1)).ravel())
+
+
+def test_skewed_coverage_against_oracle(E):
+    """Non-Poisson input: SNV coverage and cell depth spread over two orders of magnitude, counts up to the hundreds, some
+    SNVs with int32-sized totals -- the work plan (equal-cost CTA ranges / group cuts) and the count>1 path must hold."""
+    from oracle import em_oracle as O
+    from scipy.sparse import csr_matrix
+    from scsplit_b200._lib import SCS_L, SCS_LPS, SCS_P, SCS_W
+    rng = np.random.default_rng(11)
+    V, N, K = 6000, 1500, 6
+    snv_rate = np.exp(rng.normal(-3.5, 1.4, V))[:, None]            # log-normal coverage per SNV
+    cell_depth = np.exp(rng.normal(0.0, 0.9, N))[None, :]            # and per cell
+    lam = np.minimum(snv_rate * cell_depth, 40.0)
+    depth = rng.poisson(lam)
+    depth[rng.choice(V, 5, replace=False)[:, None], rng.choice(N, 40, replace=False)[None, :]] += 300   # a few huge counts
+    geno = rng.choice([0.01, 0.5, 0.99], size=(V, 4), p=[0.5, 0.3, 0.2])
+    p = geno[:, rng.integers(0, 4, N)]
+    a = rng.binomial(depth, p)
+    ref, alt = csr_matrix((depth - a).astype(np.int32)), csr_matrix(a.astype(np.int32))
+    lab = np.full(N, -1, dtype=np.int32)
+    lab[rng.choice(N, 3 * K, replace=False)] = np.arange(3 * K) % K
+    for variant in (0, 1):
+        with E(ref, alt) as eng:
+            eng.set_variant(variant)
+            info = eng.layout_info()
+            assert info["heavy"] > 0 and info["light"] > 0
+            k_alt = eng.kalt()
+            assert np.array_equal(k_alt, O.kalt(ref, alt))
+            P0 = eng.seed_af(lab, K)
+            assert np.array_equal(P0, O.seed_af(ref, alt, k_alt, lab, K))
+            eng.em_begin(P0)
+            P, lPs = P0, np.array([np.log2(1 / K)] * K)
+            for t in range(3):
+                eng.set(SCS_P, P)
+                eng.set(SCS_LPS, lPs)
+                eng.estep()
+                L_o, W_o, LL_o = O.estep(ref, alt, P, lPs)
+                assert_close(eng.get(SCS_L), L_o, RTOL, "L skewed")
+                assert_close(eng.stats()["ll"], LL_o, RTOL, "LL skewed")
+                eng.set(SCS_W, W_o)
+                eng.mstep()
+                P_o, lPs_o = O.mstep(ref, alt, W_o, k_alt)
+                assert_close(eng.get(SCS_P), P_o, RTOL, "P skewed")
+                assert_close(eng.get(SCS_LPS), lPs_o, RTOL, "lPs skewed")
+                P, lPs = P_o, lPs_o
+            eng.em_begin(P0)
+            eng.em_run()
+            want = O.run_em(ref, alt, P0, k_alt)
+            with np.errstate(invalid="ignore"):
+                assert np.array_equal(eng.get(SCS_W) >= 0.99, want["W"] >= 0.99)
