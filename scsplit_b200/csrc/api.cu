@@ -67,8 +67,8 @@ int scs_create(scs_ctx** out, int device, int64_t V, int64_t N, const int64_t* r
     ctx->device = device;
     ctx->V = V;
     ctx->N = N;
-    cudaDeviceProp prop;
-    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
+    int sms = 0;   // (cudaGetDeviceProperties costs milliseconds; one attribute query does not)
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess) ctx->sm_count = sms;
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
         uint64_t keep = ~0ull;   // keep freed blocks cached: contexts are created once per restart batch in `scSplit run`

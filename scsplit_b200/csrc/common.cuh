@@ -158,6 +158,9 @@ int build_tiled(scs_ctx* ctx, const Stream& s, TiledStream& t, int KP, int TR, i
 int launch_spmm(scs_ctx* ctx, int kind /*0=E,1=M*/, int KP, int R, const double* X, int64_t x_stride, double* Y,
                 int64_t y_stride, const int32_t* done, const double* gate = nullptr, int64_t gate_stride = 0, double gate_thr = 0.0);
 int em_free(scs_ctx* ctx);
+// host [rows][K] <-> device [rows][KP] through a staging buffer and a (un)pitch kernel (strided 2-D copies of small rows are slow)
+int upload_pitched(scs_ctx* ctx, double* dst_dev, const double* host, int64_t rows, int K, int KP);
+int download_pitched(scs_ctx* ctx, double* host, const double* src_dev, int64_t rows, int K, int KP);
 
 // comm.cu
 int comm_allreduce_f64(scs_ctx* ctx, double* buf_dev, int64_t count);

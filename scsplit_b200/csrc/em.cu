@@ -111,6 +111,47 @@ int em_free(scs_ctx* ctx) {
     return 0;
 }
 
+// dst[row][KP] <- src[row][K] (pad columns zero): small rows make a strided cudaMemcpy2D slow, a kernel does not care
+__global__ void k_repitch(int64_t rows, int K, int KP, const double* __restrict__ src, double* __restrict__ dst) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * KP) return;
+    const int64_t row = i / KP;
+    const int k = (int)(i - row * KP);
+    dst[i] = k < K ? src[row * K + k] : 0.0;
+}
+
+// host [rows][K] -> device [rows][KP], stream-ordered (the staging buffer returns to the pool when the copy is done)
+int upload_pitched(scs_ctx* ctx, double* dst, const double* host, int64_t rows, int K, int KP) {
+    double* tmp = nullptr;
+    SCS_CUDA(cudaMallocAsync((void**)&tmp, (size_t)rows * K * 8, ctx->stream));
+    SCS_CUDA(cudaMemcpyAsync(tmp, host, (size_t)rows * K * 8, cudaMemcpyHostToDevice, ctx->stream));
+    k_repitch<<<(unsigned)((rows * KP + 255) / 256), 256, 0, ctx->stream>>>(rows, K, KP, tmp, dst);
+    ctx->launches++;
+    SCS_CUDA(cudaFreeAsync(tmp, ctx->stream));
+    SCS_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// dst[row][K] <- src[row][KP]
+__global__ void k_unpitch(int64_t rows, int K, int KP, const double* __restrict__ src, double* __restrict__ dst) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * K) return;
+    const int64_t row = i / K;
+    dst[i] = src[row * KP + (i - row * K)];
+}
+
+// device [rows][KP] -> host [rows][K], stream-ordered
+int download_pitched(scs_ctx* ctx, double* host, const double* src, int64_t rows, int K, int KP) {
+    double* tmp = nullptr;
+    SCS_CUDA(cudaMallocAsync((void**)&tmp, (size_t)rows * K * 8, ctx->stream));
+    k_unpitch<<<(unsigned)((rows * K + 255) / 256), 256, 0, ctx->stream>>>(rows, K, KP, src, tmp);
+    ctx->launches++;
+    SCS_CUDA(cudaMemcpyAsync(host, tmp, (size_t)rows * K * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    SCS_CUDA(cudaFreeAsync(tmp, ctx->stream));
+    SCS_CUDA(cudaGetLastError());
+    return 0;
+}
+
 static int tables_from_P(scs_ctx* ctx, int r0, int nr) {
     EmState& em = ctx->em;
     dim3 grid((unsigned)((ctx->V * em.KP + 255) / 256), (unsigned)nr);
@@ -218,14 +259,13 @@ int scs_em_begin(scs_ctx* ctx, int R, int K, const double* P0, int max_iter) {
     SCS_TRY(dev_alloc(ctx, &em.iters, R));
     SCS_TRY(dev_alloc(ctx, &em.done, R));
     cudaStream_t st = ctx->stream;
-    SCS_CUDA(cudaMemsetAsync(em.P, 0, (size_t)R * V * KP * 8, st));
     SCS_CUDA(cudaMemsetAsync(em.W, 0, (size_t)R * N * KP * 8, st));
     SCS_CUDA(cudaMemsetAsync(em.L, 0, (size_t)R * N * KP * 8, st));
     SCS_CUDA(cudaMemsetAsync(em.stats, 0, (size_t)R * em.stats_stride * 8, st));
     SCS_CUDA(cudaMemsetAsync(em.hist, 0, (size_t)R * max_iter * 8, st));
     SCS_CUDA(cudaMemsetAsync(em.iters, 0, (size_t)R * 4, st));
     SCS_CUDA(cudaMemsetAsync(em.done, 0, (size_t)R * 4, st));
-    SCS_CUDA(cudaMemcpy2DAsync(em.P, (size_t)KP * 8, P0, (size_t)K * 8, (size_t)K * 8, (size_t)R * V, cudaMemcpyHostToDevice, st));
+    SCS_TRY(upload_pitched(ctx, em.P, P0, (int64_t)R * V, K, KP));
     // lP_s = [log2(1/K)] * K (scSplit:91); sum_log_likelihood = [1, 2] (scSplit:155) -> previous LL = 2
     std::vector<double> h_lps((size_t)R * KP, 0.0), h_prev((size_t)R, 2.0);
     const double l0 = log2(1.0 / (double)K);
@@ -335,9 +375,9 @@ int scs_em_get(scs_ctx* ctx, int restart, int what, double* out) {
     const int K = em.K, KP = em.KP;
     SCS_CUDA(cudaStreamSynchronize(ctx->stream));
     switch (what) {
-        case SCS_P: SCS_CUDA(cudaMemcpy2DAsync(out, (size_t)K * 8, em.P + (int64_t)restart * V * KP, (size_t)KP * 8, (size_t)K * 8, (size_t)V, cudaMemcpyDeviceToHost, ctx->stream)); break;
-        case SCS_W: SCS_CUDA(cudaMemcpy2DAsync(out, (size_t)K * 8, em.W + (int64_t)restart * N * KP, (size_t)KP * 8, (size_t)K * 8, (size_t)N, cudaMemcpyDeviceToHost, ctx->stream)); break;
-        case SCS_L: SCS_CUDA(cudaMemcpy2DAsync(out, (size_t)K * 8, em.L + (int64_t)restart * N * KP, (size_t)KP * 8, (size_t)K * 8, (size_t)N, cudaMemcpyDeviceToHost, ctx->stream)); break;
+        case SCS_P: SCS_TRY(download_pitched(ctx, out, em.P + (int64_t)restart * V * KP, V, K, KP)); break;
+        case SCS_W: SCS_TRY(download_pitched(ctx, out, em.W + (int64_t)restart * N * KP, N, K, KP)); break;
+        case SCS_L: SCS_TRY(download_pitched(ctx, out, em.L + (int64_t)restart * N * KP, N, K, KP)); break;
         case SCS_LPS: SCS_CUDA(cudaMemcpyAsync(out, em.lps + (int64_t)restart * KP, (size_t)K * 8, cudaMemcpyDeviceToHost, ctx->stream)); break;
         case SCS_LLHIST: SCS_CUDA(cudaMemcpyAsync(out, em.hist + (int64_t)restart * em.max_iter, (size_t)em.max_iter * 8, cudaMemcpyDeviceToHost, ctx->stream)); break;
         case SCS_STATS: SCS_CUDA(cudaMemcpyAsync(out, em.stats + (int64_t)restart * em.stats_stride, (size_t)em.stats_stride * 8, cudaMemcpyDeviceToHost, ctx->stream)); break;
@@ -358,11 +398,11 @@ int scs_em_set(scs_ctx* ctx, int restart, int what, const double* in) {
     SCS_CUDA(cudaStreamSynchronize(ctx->stream));
     switch (what) {
         case SCS_P:
-            SCS_CUDA(cudaMemcpy2DAsync(em.P + (int64_t)restart * V * KP, (size_t)KP * 8, in, (size_t)K * 8, (size_t)K * 8, (size_t)V, cudaMemcpyHostToDevice, ctx->stream));
+            SCS_TRY(upload_pitched(ctx, em.P + (int64_t)restart * V * KP, in, V, K, KP));
             SCS_TRY(tables_from_P(ctx, restart, 1));
             break;
-        case SCS_W: SCS_CUDA(cudaMemcpy2DAsync(em.W + (int64_t)restart * N * KP, (size_t)KP * 8, in, (size_t)K * 8, (size_t)K * 8, (size_t)N, cudaMemcpyHostToDevice, ctx->stream)); break;
-        case SCS_L: SCS_CUDA(cudaMemcpy2DAsync(em.L + (int64_t)restart * N * KP, (size_t)KP * 8, in, (size_t)K * 8, (size_t)K * 8, (size_t)N, cudaMemcpyHostToDevice, ctx->stream)); break;
+        case SCS_W: SCS_TRY(upload_pitched(ctx, em.W + (int64_t)restart * N * KP, in, N, K, KP)); break;
+        case SCS_L: SCS_TRY(upload_pitched(ctx, em.L + (int64_t)restart * N * KP, in, N, K, KP)); break;
         case SCS_LPS: SCS_CUDA(cudaMemcpyAsync(em.lps + (int64_t)restart * KP, in, (size_t)K * 8, cudaMemcpyHostToDevice, ctx->stream)); break;
         default: SCS_CHECK(false, "array id %d cannot be set", what);
     }

@@ -8,6 +8,8 @@
 #include <cub/cub.cuh>
 
 #include <algorithm>
+#include <chrono>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -347,6 +349,21 @@ int build_tiled(scs_ctx* ctx, const Stream& s, TiledStream& t, int KP, int TR, i
     return 0;
 }
 
+// SCS_TRACE=1: host-side phase times of the layout build on stderr (each phase ends with a stream synchronise)
+struct PhaseTrace {
+    bool on;
+    cudaStream_t st;
+    std::chrono::steady_clock::time_point t0;
+    explicit PhaseTrace(cudaStream_t s) : on(std::getenv("SCS_TRACE") != nullptr), st(s), t0(std::chrono::steady_clock::now()) {}
+    void mark(const char* what) {
+        if (!on) return;
+        cudaStreamSynchronize(st);
+        auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[scs trace] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
+
 int build_layout(scs_ctx* ctx, const int64_t* ref_indptr, const int32_t* ref_indices, const void* ref_data,
                  const int64_t* alt_indptr, const int32_t* alt_indices, const void* alt_data, int data_bytes) {
     const int64_t V = ctx->V, N = ctx->N;
@@ -377,6 +394,8 @@ int build_layout(scs_ctx* ctx, const int64_t* ref_indptr, const int32_t* ref_ind
     if (nA) SCS_CUDA(cudaMemcpyAsync(a_val, alt_data, (size_t)nA * data_bytes, cudaMemcpyHostToDevice, st));
     if (nR) SCS_CUDA(cudaMemcpyAsync(r_val, ref_data, (size_t)nR * data_bytes, cudaMemcpyHostToDevice, st));
 
+    PhaseTrace trace(st);
+    trace.mark("alloc + H2D");
     int* err = nullptr;
     unsigned long long* ndup = nullptr;
     SCS_CUDA(cudaMallocAsync((void**)&err, sizeof(int), ctx->stream));
@@ -396,10 +415,12 @@ int build_layout(scs_ctx* ctx, const int64_t* ref_indptr, const int32_t* ref_ind
     unsigned gridPR = (unsigned)((2 * V + WPB - 1) / WPB);
     k_count_rows<<<gridPR, WPB * 32, 0, st>>>(V, a_ptr, a_val, r_ptr, r_val, data_bytes, cntL, cntH, rowsum, err);
     ctx->launches++;
+    trace.mark("count_rows");
     SCS_TRY(dev_alloc(ctx, &M.lptr, 2 * V + 1));
     SCS_TRY(dev_alloc(ctx, &M.hptr, 2 * V + 1));
     SCS_TRY(inclusive_scan_into_ptr(ctx, cntL, M.lptr, 2 * V));
     SCS_TRY(inclusive_scan_into_ptr(ctx, cntH, M.hptr, 2 * V));
+    trace.mark("scans");
     int herr = 0;
     SCS_CUDA(cudaMemcpy(&herr, err, sizeof(int), cudaMemcpyDeviceToHost));
     SCS_CHECK(herr == 0, "count matrices must hold strictly positive counts that fit int32 (explicit zeros are not allowed)");
@@ -424,6 +445,7 @@ int build_layout(scs_ctx* ctx, const int64_t* ref_indptr, const int32_t* ref_ind
                                           M.lcode, M.hcode, M.hcnt, lkey, lval, hkey, hval, ndup, err);
     ctx->launches++;
 
+    trace.mark("allocs + fill_M");
     // ---- cell-major stream: stable sort of the SNV-major order by cell
     Stream& E = ctx->E;
     E.nrows = N;
@@ -437,6 +459,7 @@ int build_layout(scs_ctx* ctx, const int64_t* ref_indptr, const int32_t* ref_ind
     SCS_TRY(dev_alloc(ctx, &E.hcnt, E.n_heavy));
     SCS_TRY(stable_sort_by_cell<uint32_t>(ctx, lkey, lkey_s, lval, E.lcode, M.n_light, N));
     SCS_TRY(stable_sort_by_cell<uint64_t>(ctx, hkey, hkey_s, hval, hval_s, M.n_heavy, N));
+    trace.mark("allocs + sorts");
     k_ptr_from_sorted<<<(unsigned)((M.n_light + 256) / 256), 256, 0, st>>>(lkey_s, M.n_light, N, E.lptr);
     k_ptr_from_sorted<<<(unsigned)((M.n_heavy + 256) / 256), 256, 0, st>>>(hkey_s, M.n_heavy, N, E.hptr);
     if (M.n_heavy) k_split_heavy<<<(unsigned)((M.n_heavy + 255) / 256), 256, 0, st>>>(hval_s, M.n_heavy, E.hcode, E.hcnt);
@@ -455,6 +478,7 @@ int build_layout(scs_ctx* ctx, const int64_t* ref_indptr, const int32_t* ref_ind
     SCS_CUDA(cudaMemcpyAsync(&herr, err, sizeof(int), cudaMemcpyDeviceToHost, st));
     SCS_CUDA(cudaStreamSynchronize(st));
     SCS_CUDA(cudaGetLastError());
+    trace.mark("ptrs, sums, kalt");
     cudaFreeAsync(a_ptr, ctx->stream); cudaFreeAsync(r_ptr, ctx->stream); cudaFreeAsync(a_idx, ctx->stream); cudaFreeAsync(r_idx, ctx->stream); cudaFreeAsync(a_val, ctx->stream); cudaFreeAsync(r_val, ctx->stream);
     cudaFreeAsync(cntL, ctx->stream); cudaFreeAsync(cntH, ctx->stream); cudaFreeAsync(rowsum, ctx->stream); cudaFreeAsync(err, ctx->stream); cudaFreeAsync(ndup, ctx->stream);
     cudaFreeAsync(lkey, ctx->stream); cudaFreeAsync(lval, ctx->stream); cudaFreeAsync(lkey_s, ctx->stream); cudaFreeAsync(hkey, ctx->stream); cudaFreeAsync(hkey_s, ctx->stream); cudaFreeAsync(hval, ctx->stream); cudaFreeAsync(hval_s, ctx->stream);

@@ -204,7 +204,7 @@ int scs_seed_af(scs_ctx* ctx, int R, int K, const int32_t* labels, double* P0_ou
     dim3 grid((unsigned)((V * KP + 255) / 256), (unsigned)R);
     k_finalize<<<grid, 256, 0, st>>>(V, K, KP, d_S, stride, ctx->kalt, d_P, nullptr, nullptr);
     ctx->launches++;
-    SCS_CUDA(cudaMemcpy2DAsync(P0_out, (size_t)K * 8, d_P, (size_t)KP * 8, (size_t)K * 8, (size_t)R * V, cudaMemcpyDeviceToHost, st));
+    SCS_TRY(download_pitched(ctx, P0_out, d_P, (int64_t)R * V, K, KP));
     SCS_CUDA(cudaStreamSynchronize(st));
     SCS_CUDA(cudaGetLastError());
     return 0;
@@ -256,8 +256,7 @@ int scs_doublet_scores(scs_ctx* ctx, int K, const double* P, const uint8_t* mask
     SCS_TRY(s.get(&d_part, (int64_t)nblk * (KP + 1)));
     SCS_TRY(s.get(&d_out, KP + 2));
     SCS_TRY(s.get(&d_mask, N));
-    SCS_CUDA(cudaMemsetAsync(d_P, 0, (size_t)V * KP * 8, st));
-    SCS_CUDA(cudaMemcpy2DAsync(d_P, (size_t)KP * 8, P, (size_t)K * 8, (size_t)K * 8, (size_t)V, cudaMemcpyHostToDevice, st));
+    SCS_TRY(upload_pitched(ctx, d_P, P, V, K, KP));
     SCS_CUDA(cudaMemcpyAsync(d_mask, mask, (size_t)N, cudaMemcpyHostToDevice, st));
     dim3 grid((unsigned)((V * KP + 255) / 256), 1);
     k_tables_from_P<<<grid, 256, 0, st>>>(V, K, KP, d_P, d_T);
