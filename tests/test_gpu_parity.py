@@ -448,3 +448,32 @@ def test_skewed_coverage_against_oracle(E):
             want = O.run_em(ref, alt, P0, k_alt)
             with np.errstate(invalid="ignore"):
                 assert np.array_equal(eng.get(SCS_W) >= 0.99, want["W"] >= 0.99)
+
+
+@pytest.mark.parametrize("V,N,K", [(1, 1, 1), (3, 2, 2), (5, 40, 3), (40, 5, 4), (2, 300, 2)])
+def test_tiny_shapes(V, N, K, E):
+    """Degenerate sizes: single SNV / single cell / fewer cells than a warp, K = 1; everything against the oracle."""
+    from oracle import em_oracle as O
+    from scipy.sparse import csr_matrix
+    from scsplit_b200._lib import SCS_L, SCS_P, SCS_W
+    rng = np.random.default_rng(V * 1000 + N)
+    depth = rng.poisson(1.2, size=(V, N))
+    a = rng.binomial(depth, 0.4)
+    ref, alt = csr_matrix((depth - a).astype(np.int16)), csr_matrix(a.astype(np.int16))
+    lab = (np.arange(N) % (K + 1) - 1).astype(np.int32)            # includes -1 (unused) cells
+    with E(ref, alt) as eng:
+        k_alt = eng.kalt()
+        assert np.array_equal(k_alt, O.kalt(ref, alt))
+        P0 = eng.seed_af(lab, K)
+        assert np.array_equal(P0, O.seed_af(ref, alt, k_alt, lab, K))
+        eng.em_begin(P0)
+        eng.em_iterate(4, check_conv=False)
+        want = O.run_em(ref, alt, P0, k_alt, fixed_iters=4)
+        assert_close(eng.get(SCS_L), want["L"], RTOL, "L tiny")
+        assert_close(eng.get(SCS_W), want["W"], 1e-7, "W tiny")
+        assert_close(eng.get(SCS_P), want["P"], RTOL, "P tiny")
+        assert_close(eng.em_status()[2][0], want["LL"], RTOL, "LL tiny")
+        rc, cc = eng.pattern_counts()
+        U = ((ref != 0).astype(np.int8) + (alt != 0).astype(np.int8))
+        assert np.array_equal(rc, np.asarray((U != 0).sum(axis=1)).ravel())
+        assert np.array_equal(cc, np.asarray((U != 0).sum(axis=0)).ravel())
