@@ -8,7 +8,8 @@ import os
 from ctypes import POINTER, c_char_p, c_double, c_int, c_int8, c_int32, c_int64, c_uint8, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libscsplit_b200.so")
+# SCSPLIT_B200_LIB points the loader at another build of the same ABI (kernel experiments); the default is the in-tree library
+LIB_PATH = os.environ.get("SCSPLIT_B200_LIB") or os.path.join(HERE, "libscsplit_b200.so")
 
 SCS_P, SCS_W, SCS_L, SCS_LPS, SCS_LLHIST, SCS_STATS = range(6)
 SCS_MAX_K = 32

@@ -298,7 +298,7 @@ int build_tiled(scs_ctx* ctx, const Stream& s, TiledStream& t, int KP, int TR, i
     cudaFreeAsync(tmp, ctx->stream);
     SCS_CUDA(e); SCS_CUDA(e2); SCS_CUDA(e3);
     ctx->launches += 2;
-    SCS_TRY(dev_alloc(ctx, &t.tcode, total + 2));
+    SCS_TRY(dev_alloc(ctx, &t.tcode, total + 64));   // slack: the kernel prefetches one batch past a group's run
     k_tile_scatter<<<(unsigned)((s.nrows + 7) / 8), 256, 0, st>>>(s.nrows, t.ntiles, TR, s.lptr, s.lcode, t.tptr, d_ulo, t.tcode);
     cudaFreeAsync(d_ulo, st);
     ctx->launches++;

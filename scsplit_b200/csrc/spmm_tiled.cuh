@@ -140,11 +140,15 @@ k_spmm_tiled(int64_t nrows, int TR, int64_t xrows, const int64_t* __restrict__ t
         double2 c0 = make_double2(0.0, 0.0), c1 = make_double2(0.0, 0.0);   // current unit (even / odd entries)
         double2 n0 = make_double2(0.0, 0.0), n1 = make_double2(0.0, 0.0);   // next unit
         // all GPW groups of the warp iterate together; a group that has finished feeds zero rows until the others end
+        // this lane's index word (two entries) of the NEXT batch is always in flight: the stream of a group is contiguous,
+        // so the next batch starts at `lim` whatever the unit bounds turn out to be (the stream buffer has slack at its end)
+        uint32_t word = act ? __ldg(reinterpret_cast<const uint32_t*>(tcode + e) + li) : zero_pair;
         while (__any_sync(0xffffffffu, u < uend)) {
             const int64_t lim = min(e + BE, b2);          // never past the end of unit u+1
             const int nvalid = (u < uend) ? (int)(lim - e) : 0;
             const int ncur = (int)min((int64_t)nvalid, max((int64_t)0, b1 - e));   // entries of this batch that belong to unit u
-            const uint32_t mine = (2 * li < nvalid) ? __ldg(reinterpret_cast<const uint32_t*>(tcode + e) + li) : zero_pair;
+            const uint32_t mine = (2 * li < nvalid) ? word : zero_pair;
+            if (u < uend) word = __ldg(reinterpret_cast<const uint32_t*>(tcode + lim) + li);
             constexpr int UW = C::GS < 4 ? C::GS : 4;
 #pragma unroll
             for (int j0 = 0; j0 < C::GS; j0 += UW) {
