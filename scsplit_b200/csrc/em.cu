@@ -105,10 +105,15 @@ int launch_spmm_tiled(scs_ctx* ctx, int kind, int KP, int R, const double* X, in
 int em_free(scs_ctx* ctx) {
     EmState& em = ctx->em;
     dev_free(ctx, em.T); dev_free(ctx, em.P); dev_free(ctx, em.L); dev_free(ctx, em.W); dev_free(ctx, em.stats); dev_free(ctx, em.lps);
-    dev_free(ctx, em.hq);
+    dev_free(ctx, em.hq); dev_free(ctx, em.sched);
     dev_free(ctx, em.partial); dev_free(ctx, em.hist); dev_free(ctx, em.ll_prev); dev_free(ctx, em.iters); dev_free(ctx, em.done);
     em = EmState();
     return 0;
+}
+
+static __global__ void k_fill_u32(uint32_t* __restrict__ p, int64_t n, uint32_t v) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
 }
 
 // dst[row][KP] <- src[row][K] (pad columns zero): small rows make a strided cudaMemcpy2D slow, a kernel does not care
@@ -198,7 +203,7 @@ static int run_m(scs_ctx* ctx, const int32_t* done, int track, int check_conv) {
             k_mstep_sparse<KPc><<<grid, SPARSE_THREADS, smem, ctx->stream>>>(ctx->M.nrows, N, em.K, ctx->M.lptr, ctx->M.lcode, ctx->M.hptr,
                                                                            ctx->M.hcode, ctx->M.hcnt, em.hq, em.h_stride, em.W, em.stats,
                                                                            em.stats_stride, em.sparse_only ? nullptr : gate, em.stats_stride,
-                                                                           gate_thr, done);
+                                                                           gate_thr, done, em.sched);
         });
         ctx->launches++;
         SCS_TRY(timing_end(ctx, 2, ea, eb));
@@ -253,7 +258,10 @@ int scs_em_begin(scs_ctx* ctx, int R, int K, const double* P0, int max_iter) {
     SCS_TRY(dev_alloc(ctx, &em.partial, (int64_t)R * em.nblk * (KP + 2)));
     em.h_stride = (N + 3) / 4 * 4;
     SCS_TRY(dev_alloc(ctx, &em.hq, (int64_t)R * em.h_stride));
-    SCS_CUDA(cudaMemsetAsync(em.hq, 255, (size_t)R * em.h_stride * 4, ctx->stream));
+    k_fill_u32<<<(unsigned)((R * em.h_stride + 255) / 256), 256, 0, ctx->stream>>>(em.hq, R * em.h_stride, SPARSE_DENSE);
+    ctx->launches++;
+    SCS_TRY(dev_alloc(ctx, &em.sched, 2 * R));
+    SCS_CUDA(cudaMemsetAsync(em.sched, 0, (size_t)R * 8, ctx->stream));
     SCS_TRY(dev_alloc(ctx, &em.hist, (int64_t)R * max_iter));
     SCS_TRY(dev_alloc(ctx, &em.ll_prev, R));
     SCS_TRY(dev_alloc(ctx, &em.iters, R));

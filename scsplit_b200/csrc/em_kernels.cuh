@@ -117,7 +117,11 @@ __device__ __forceinline__ void block_reduce_store(double (&v)[NV], double* smem
 // the M-step, where the sums only ever enter (S + k_alt) and (S + 1) with k_alt >= 1e-10: 2^31 such terms stay under half
 // an ulp.  Rows that do not fit the format (soft, NaN) are marked SPARSE_DENSE and take the dense path.
 constexpr double SPARSE_TINY = 1e-40;
-constexpr uint32_t SPARSE_DENSE = 0xffffffffu;
+// Both special words decode to "state s, 1 - weight = 1.0f", i.e. weight 0: the sparse M-step can run them through its
+// branch-free accumulate (adds 0.0) and only has to notice SPARSE_DENSE.  A packed row never looks like either
+// (its 1 - weight lies in [-0.5, 0.5]).
+constexpr uint32_t SPARSE_DENSE = 0x3f800000u;       // unsaturated row: take the full posterior row
+constexpr uint32_t SPARSE_NOP = 0x3f800001u;         // no entry (a lane past the end of a pseudo-row)
 template <int KP>
 __device__ __forceinline__ uint32_t sparsify_row(const double (&w)[KP], int K) {
     int im = 0;

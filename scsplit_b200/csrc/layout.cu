@@ -427,7 +427,7 @@ int build_layout(scs_ctx* ctx, const int64_t* ref_indptr, const int32_t* ref_ind
     SCS_CUDA(cudaMemcpy(&M.n_light, M.lptr + 2 * V, sizeof(int64_t), cudaMemcpyDeviceToHost));
     SCS_CUDA(cudaMemcpy(&M.n_heavy, M.hptr + 2 * V, sizeof(int64_t), cudaMemcpyDeviceToHost));
     SCS_CHECK(M.n_light + M.n_heavy == nA + nR, "internal: light+heavy != nnz");
-    SCS_TRY(dev_alloc(ctx, &M.lcode, M.n_light));
+    SCS_TRY(dev_alloc(ctx, &M.lcode, M.n_light + 4));   // + slack: the sparse M-step reads whole 16-byte vectors
     SCS_TRY(dev_alloc(ctx, &M.hcode, M.n_heavy));
     SCS_TRY(dev_alloc(ctx, &M.hcnt, M.n_heavy));
 

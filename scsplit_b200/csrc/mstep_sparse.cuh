@@ -18,10 +18,11 @@ constexpr int SPARSE_THREADS = 1024;
 constexpr int SPARSE_GS = 16;                      // lanes per pseudo-row (>= KP/2: the row's column pairs are stored by lanes 0..KP/2-1)
 static_assert(SPARSE_GS * 2 >= SCS_MAX_K, "a row group must cover all column pairs");
 
+// packed words of all cells + one SPARSE_NOP word, rounded to the 128-byte alignment of the mbarrier behind it
+__host__ __device__ inline size_t sparse_tab_bytes(int64_t h_stride) { return (((size_t)h_stride * 4 + 4) + 127) & ~(size_t)127; }
 inline size_t sparse_smem_bytes(int64_t h_stride, int KP) {
     const size_t acc = (size_t)SPARSE_THREADS * KP * 8;                  // [warp][state][lane] fp64
-    const size_t tab = (((size_t)h_stride * 4) + 127) & ~(size_t)127;
-    return acc + tab + 16;
+    return acc + sparse_tab_bytes(h_stride) + 16;
 }
 inline bool sparse_fits(int64_t N, int KP) { return sparse_smem_bytes((N + 3) / 4 * 4, KP) <= (size_t)TILE_BYTES + 1024; }
 
@@ -37,36 +38,69 @@ __device__ __forceinline__ double lds_f64(uint32_t addr) {
 }
 __device__ __forceinline__ void sts_f64(uint32_t addr, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory"); }
 
-// acc_base: shared address of this lane's slot for state 0; slots of consecutive states are 256 bytes apart
-template <int KP>
-__device__ __forceinline__ void sparse_add(uint32_t acc_base, int K, uint32_t q, int64_t cell, const double* __restrict__ W, double cnt) {
-    if (q != SPARSE_DENSE) {
-        const double w = 1.0 - (double)__uint_as_float(q & ~31u);        // the exact posterior weight
-        const uint32_t a = acc_base + (q & 31u) * 256u;
-        sts_f64(a, lds_f64(a) + cnt * w);
-    } else {                                                             // unsaturated cell: full row from global memory
-        const double* wr = W + cell * KP;
-        for (int k = 0; k < K; ++k) {
-            const uint32_t a = acc_base + (uint32_t)k * 256u;
-            sts_f64(a, lds_f64(a) + cnt * __ldg(wr + k));
+// Reduce-scatter butterfly over the SPARSE_GS lanes of a row group: every round a lane hands one half of its values to
+// its partner and adds the partner's copy of the half it keeps, so the 4 rounds move CNT, CNT/2, CNT/4, ... values instead
+// of CNT each (22 instead of 80 shuffles for K = 9).  On return out[0..nval) are finished sums of states base, base+1, ...
+// (odd halvings pad with zeros, nval counts the real ones); the tree (hence the rounding) of every state is fixed.
+template <int CNT, int O>
+struct GroupReduce {
+    static constexpr int HALF = (CNT + 1) / 2;
+    static constexpr int LEFT = GroupReduce<HALF, O / 2>::LEFT;
+    __device__ __forceinline__ static void run(double (&v)[CNT], double (&out)[LEFT], int li, int& base, int& nval) {
+        const bool hi = (li & O) != 0;
+        double w[HALF];
+#pragma unroll
+        for (int i = 0; i < HALF; ++i) {
+            const double lo_v = v[i], hi_v = (i + HALF < CNT) ? v[i + HALF] : 0.0;
+            const double keep = hi ? hi_v : lo_v, send = hi ? lo_v : hi_v;
+            w[i] = keep + __shfl_xor_sync(0xffffffffu, send, O);
         }
+        base += hi ? HALF : 0;
+        nval = hi ? max(nval - HALF, 0) : min(nval, HALF);
+        GroupReduce<HALF, O / 2>::run(w, out, li, base, nval);
+    }
+};
+template <int CNT>
+struct GroupReduce<CNT, 0> {
+    static constexpr int LEFT = CNT;
+    __device__ __forceinline__ static void run(double (&v)[CNT], double (&out)[CNT], int, int&, int&) {
+#pragma unroll
+        for (int i = 0; i < CNT; ++i) out[i] = v[i];
+    }
+};
+
+// acc_base: shared address of this lane's slot for state 0; slots of consecutive states are 256 bytes apart
+__device__ __forceinline__ void sparse_rmw(uint32_t acc_base, uint32_t q, double cnt) {
+    const double w = 1.0 - (double)__uint_as_float(q & ~31u);            // the exact posterior weight
+    const uint32_t a = acc_base + (q & 31u) * 256u;
+    sts_f64(a, lds_f64(a) + cnt * w);
+}
+template <int KP>
+__device__ __forceinline__ void dense_add(uint32_t acc_base, int K, int64_t cell, const double* __restrict__ W, double cnt) {
+    const double* wr = W + cell * KP;                                    // unsaturated cell: full row from global memory
+    for (int k = 0; k < K; ++k) {
+        const uint32_t a = acc_base + (uint32_t)k * 256u;
+        sts_f64(a, lds_f64(a) + cnt * __ldg(wr + k));
     }
 }
 
+// grid = (CTAs, R).  Row pairs are handed out through sched[r][0] (an integer ticket counter), longest rows first, so the
+// SMs finish together whatever the row-length profile is; the last CTA to leave resets the tickets for the next launch.
+// Which warp sums a row never changes the order inside the row, so the result is the same bits on every run.
 template <int KP>
 __global__ void __launch_bounds__(SPARSE_THREADS, 1)
 k_mstep_sparse(int64_t nrows, int64_t N, int K, const int64_t* __restrict__ lptr, const uint32_t* __restrict__ lcode,
                const int64_t* __restrict__ hptr, const uint32_t* __restrict__ hcode, const int32_t* __restrict__ hcnt,
                const uint32_t* __restrict__ hq, int64_t h_stride, const double* __restrict__ W, double* __restrict__ S,
                int64_t s_stride, const double* __restrict__ gate, int64_t gate_stride, double gate_thr,
-               const int32_t* __restrict__ done) {
+               const int32_t* __restrict__ done, int32_t* __restrict__ sched) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int r = blockIdx.y;
     if (done && done[r]) return;
     if (gate && gate[(int64_t)r * gate_stride] > gate_thr) return;   // too many unsaturated cells: the tiled SpMM runs instead
     constexpr size_t ACC_BYTES = (size_t)SPARSE_THREADS * KP * 8;
     unsigned char* s_tab = smem + ACC_BYTES;
-    uint64_t* bar = reinterpret_cast<uint64_t*>(s_tab + ((((size_t)h_stride * 4) + 127) & ~(size_t)127));
+    uint64_t* bar = reinterpret_cast<uint64_t*>(s_tab + sparse_tab_bytes(h_stride));
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     if (tid == 0) {
         mbar_init(bar, 1);
@@ -75,65 +109,144 @@ k_mstep_sparse(int64_t nrows, int64_t N, int K, const int64_t* __restrict__ lptr
         mbar_expect_tx(bar, bytes);
         const char* src = reinterpret_cast<const char*>(hq + (int64_t)r * h_stride);
         for (uint32_t off = 0; off < bytes; off += 32768u) bulk_g2s(s_tab + off, src + off, min(32768u, bytes - off), bar);
+        // word h_stride of the table (past the copied part): where the codes of lanes beyond a row's end point
+        reinterpret_cast<uint32_t*>(s_tab)[h_stride] = SPARSE_NOP;
     }
     // this lane's accumulator slots: [warp][state][lane], zeroed once; every row leaves them zero again
-    const uint32_t acc_base = smem_u32(smem) + (uint32_t)warp * (KP * 256u) + (uint32_t)lane * 8u;
+    uint32_t acc_base = smem_u32(smem) + (uint32_t)warp * (KP * 256u) + (uint32_t)lane * 8u;
+    uint32_t tab = smem_u32(s_tab);
+    asm volatile("" : "+r"(acc_base), "+r"(tab));                    // keep both in registers (no re-derivation per entry)
 #pragma unroll
     for (int k = 0; k < KP; ++k) sts_f64(acc_base + k * 256u, 0.0);
     __syncthreads();
     mbar_wait(bar, 0);
-    const uint32_t tab = smem_u32(s_tab);
     W += (int64_t)r * N * KP;
     S += (int64_t)r * s_stride;
+    sched += 2 * r;
     const int li = lane & (SPARSE_GS - 1), g = lane / SPARSE_GS;
     constexpr int GPW = 32 / SPARSE_GS;
-    // GPW consecutive pseudo-rows per warp and step (consecutive rows are the same allele: similar lengths)
-    for (int64_t row0 = ((int64_t)blockIdx.x * nwarps + warp) * GPW; row0 < nrows; row0 += (int64_t)gridDim.x * nwarps * GPW) {
-        const int64_t row = row0 + g;
-        const bool act = row < nrows;
-        const int64_t lb = act ? lptr[row] : 0, le = act ? lptr[row + 1] : 0;
-        // UNR entries per lane per step; the codes of the NEXT step are fetched before this step's accumulator updates,
-        // so the global-load latency overlaps the shared-memory read-modify-writes
-        constexpr int UNR = 4;
-        uint32_t cur[UNR], nxt[UNR];
-        int64_t e = lb + li;
-#pragma unroll
-        for (int j = 0; j < UNR; ++j) cur[j] = (e + j * SPARSE_GS < le) ? __ldg(lcode + e + j * SPARSE_GS) : SPARSE_DENSE;
-        while (e < le) {
-            const int64_t en = e + UNR * SPARSE_GS;
-#pragma unroll
-            for (int j = 0; j < UNR; ++j) nxt[j] = (en + j * SPARSE_GS < le) ? __ldg(lcode + en + j * SPARSE_GS) : SPARSE_DENSE;
-            uint32_t q[UNR];
-#pragma unroll
-            for (int j = 0; j < UNR; ++j) q[j] = (cur[j] != SPARSE_DENSE) ? lds_u32(tab + (cur[j] >> 1) * 4u) : 0u;
-#pragma unroll
-            for (int j = 0; j < UNR; ++j)
-                if (cur[j] != SPARSE_DENSE) sparse_add<KP>(acc_base, K, q[j], (int64_t)(cur[j] >> 1), W, 1.0);
-#pragma unroll
-            for (int j = 0; j < UNR; ++j) cur[j] = nxt[j];
-            e = en;
+    constexpr int UV = 2;
+    const int npairs = (int)((nrows + GPW - 1) / GPW);
+    const uint32_t nop_code = (uint32_t)h_stride << 1;               // code whose table word is SPARSE_NOP
+    // A row (pair) is a short job (a few hundred entries), so the chain ticket -> row bounds -> first codes is software-
+    // pipelined across rows: the ticket is drawn two rows ahead, the bounds are loaded one row ahead, and the first code
+    // vectors of the next row are requested before the current row's reduction tree runs.
+    struct RowJob {
+        int64_t row;      // pseudo-row of this lane's group (>= nrows: none)
+        int64_t lb;       // first entry
+        int n;            // entries
+    };
+    auto draw = [&]() -> int { return lane == 0 ? atomicAdd(sched, 1) : 0; };           // raw: only lane 0 holds the ticket
+    auto job_of = [&](int ticket) -> RowJob {
+        // GPW consecutive pseudo-rows per warp (consecutive rows are the same allele: similar lengths); the ref rows
+        // (second half, longer) go first
+        RowJob j;
+        j.row = ticket < npairs ? (int64_t)(npairs - 1 - ticket) * GPW + g : nrows;
+        const bool act = j.row < nrows;
+        j.lb = act ? __ldg(lptr + j.row) : 0;
+        j.n = act ? (int)(__ldg(lptr + j.row + 1) - j.lb) : 0;
+        return j;
+    };
+    // The codes are read as 16-byte vectors from the aligned address below the row start (`a` elements early), UV vectors
+    // per lane per step, and the vectors of the NEXT step are fetched before this step's accumulator updates.  The step
+    // itself is branch-free: elements outside the row and unsaturated cells both add 0.0 (SPARSE_NOP / SPARSE_DENSE decode
+    // to weight 0); unsaturated cells are only flagged there and added from their full rows afterwards.
+    auto load_vec = [&](const RowJob& j, int v) -> uint4 {             // raw: may hold elements outside the row
+        const int a = (int)(j.lb & 3), m = a + j.n;
+        uint4 c = make_uint4(nop_code, nop_code, nop_code, nop_code);
+        if (4 * v < m) c = __ldg(reinterpret_cast<const uint4*>(lcode + (j.lb - a)) + v);
+        return c;
+    };
+    // blank the elements of vector v outside [a, m): applied when the vector is USED, so that nothing waits on the load
+    auto trim_vec = [&](uint4& c, int v, int a, int m) {
+        const int k0 = 4 * v;
+        if (k0 < a || k0 + 4 > m) {                                    // first / last vector of the row
+            if (k0 < a || k0 >= m) c.x = nop_code;
+            if (k0 + 1 < a || k0 + 1 >= m) c.y = nop_code;
+            if (k0 + 2 < a || k0 + 2 >= m) c.z = nop_code;
+            if (k0 + 3 < a || k0 + 3 >= m) c.w = nop_code;
         }
-        const int64_t hb = act ? hptr[row] : 0, he = act ? hptr[row + 1] : 0;
+    };
+    int t_cur = __shfl_sync(0xffffffffu, draw(), 0);
+    int t_nxt = __shfl_sync(0xffffffffu, draw(), 0);
+    RowJob job = job_of(t_cur);
+    uint4 cur[UV], nxt[UV];
+#pragma unroll
+    for (int j = 0; j < UV; ++j) cur[j] = load_vec(job, li + j * SPARSE_GS);
+    while (t_cur < npairs) {
+        const int raw_after = draw();                       // ticket of the row after next (in flight during this row)
+        const RowJob job_nxt = job_of(t_nxt);               // bounds of the next row (in flight during this row)
+        const int a = (int)(job.lb & 3), m = a + job.n, nv = (m + 3) >> 2;
+        bool any_dense = false;
+        for (int v = li; v < nv; v += UV * SPARSE_GS) {
+#pragma unroll
+            for (int j = 0; j < UV; ++j) nxt[j] = load_vec(job, v + (UV + j) * SPARSE_GS);
+            uint32_t q[4 * UV];
+#pragma unroll
+            for (int j = 0; j < UV; ++j) trim_vec(cur[j], v + j * SPARSE_GS, a, m);
+#pragma unroll
+            for (int j = 0; j < UV; ++j) {
+                q[4 * j + 0] = lds_u32(tab + ((cur[j].x & ~1u) << 1));
+                q[4 * j + 1] = lds_u32(tab + ((cur[j].y & ~1u) << 1));
+                q[4 * j + 2] = lds_u32(tab + ((cur[j].z & ~1u) << 1));
+                q[4 * j + 3] = lds_u32(tab + ((cur[j].w & ~1u) << 1));
+            }
+#pragma unroll
+            for (int j = 0; j < 4 * UV; ++j) {
+                any_dense |= (q[j] == SPARSE_DENSE);
+                sparse_rmw(acc_base, q[j], 1.0);
+            }
+#pragma unroll
+            for (int j = 0; j < UV; ++j) cur[j] = nxt[j];
+        }
+        // first codes of the next row: requested now, used after this row's tail work
+#pragma unroll
+        for (int j = 0; j < UV; ++j) cur[j] = load_vec(job_nxt, li + j * SPARSE_GS);
+        const uint32_t* code = lcode + job.lb;
+        if (any_dense) {                                               // rare: walk this lane's own elements again
+            for (int v = li; v < nv; v += SPARSE_GS)
+                for (int k = max(4 * v, a); k < min(4 * v + 4, m); ++k) {
+                    const uint32_t c = __ldg(code + (k - a)) >> 1;
+                    if (lds_u32(tab + c * 4u) == SPARSE_DENSE) dense_add<KP>(acc_base, K, (int64_t)c, W, 1.0);
+                }
+        }
+        const bool act = job.row < nrows;
+        const int64_t hb = act ? hptr[job.row] : 0, he = act ? hptr[job.row + 1] : 0;
         for (int64_t h = hb + li; h < he; h += SPARSE_GS) {
-            const int64_t c0 = (int64_t)(__ldg(hcode + h) >> 1);
-            sparse_add<KP>(acc_base, K, lds_u32(tab + (uint32_t)c0 * 4u), c0, W, (double)__ldg(hcnt + h));
+            const uint32_t c = __ldg(hcode + h) >> 1;
+            const uint32_t q = lds_u32(tab + c * 4u);
+            const double cnt = (double)__ldg(hcnt + h);
+            if (q != SPARSE_DENSE) sparse_rmw(acc_base, q, cnt);
+            else dense_add<KP>(acc_base, K, (int64_t)c, W, cnt);
         }
         __syncwarp();
-        // fixed tree over the lanes of the row group, state by state; slots are reset on the way
-        double tot[KP];
+        // fixed reduce-scatter tree over the lanes of the row group; slots are reset on the way
+        {
+            using GR = GroupReduce<KP, SPARSE_GS / 2>;
+            double v[KP], out[GR::LEFT];
 #pragma unroll
-        for (int k = 0; k < KP; ++k) {
-            double v = lds_f64(acc_base + k * 256u);
-            sts_f64(acc_base + k * 256u, 0.0);
+            for (int k = 0; k < KP; ++k) {
+                v[k] = lds_f64(acc_base + k * 256u);
+                sts_f64(acc_base + k * 256u, 0.0);
+            }
+            int base = 0, nval = KP;
+            GR::run(v, out, li, base, nval);
+            if (act) {
+                double* y = S + job.row * KP;
 #pragma unroll
-            for (int o = SPARSE_GS / 2; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            tot[k] = v;
+                for (int i = 0; i < GR::LEFT; ++i)
+                    if (i < nval) y[base + i] = out[i];
+            }
         }
-        if (act) {
-            double* y = S + row * KP;
-#pragma unroll
-            for (int j = 0; j < KP / 2; ++j)
-                if (li == j) *reinterpret_cast<double2*>(y + 2 * j) = make_double2(tot[2 * j], tot[2 * j + 1]);
+        job = job_nxt;
+        t_cur = t_nxt;
+        t_nxt = __shfl_sync(0xffffffffu, raw_after, 0);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        if (atomicAdd(sched + 1, 1) == (int)gridDim.x - 1) {         // every CTA has drawn its last ticket: reset for the next launch
+            sched[0] = 0;
+            sched[1] = 0;
         }
     }
 }
