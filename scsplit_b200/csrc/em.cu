@@ -215,10 +215,13 @@ static int run_m(scs_ctx* ctx, const int32_t* done, int track, int check_conv) {
     else if (ctx->timing) ctx->t_cnt[1] += 1;   // keep the per-M-step average well defined
     if (ctx->world > 1) SCS_TRY(comm_allreduce_f64(ctx, em.stats, (int64_t)em.R * em.stats_stride));
     dim3 grid((unsigned)((V * em.KP + 255) / 256), (unsigned)em.R);
-    k_finalize<<<grid, 256, 0, ctx->stream>>>(V, em.K, em.KP, em.stats, em.stats_stride, ctx->kalt, em.P, em.T, done);
-    k_update_prior<<<em.R, 32, 0, ctx->stream>>>(em.K, em.KP, em.stats, em.stats_stride, 2 * V * em.KP, em.lps, em.hist,
-                                                 em.max_iter, em.ll_prev, em.iters, em.done, track, check_conv);
-    ctx->launches += 2;
+    PriorArgs prior;
+    prior.tail_off = 2 * V * em.KP;
+    prior.lps = em.lps; prior.hist = em.hist; prior.max_iter = em.max_iter; prior.ll_prev = em.ll_prev;
+    prior.iters = em.iters; prior.done = em.done; prior.count = em.sched + 2 * em.R;
+    prior.track = track; prior.check_conv = check_conv;
+    k_finalize<<<grid, 256, 0, ctx->stream>>>(V, em.K, em.KP, em.stats, em.stats_stride, ctx->kalt, em.P, em.T, done, prior);
+    ctx->launches += 1;
     SCS_CUDA(cudaGetLastError());
     return 0;
 }
@@ -248,7 +251,19 @@ int scs_em_begin(scs_ctx* ctx, int R, int K, const double* P0, int max_iter) {
     em.R = R; em.K = K; em.KP = round_even(K); em.max_iter = max_iter;
     const int KP = em.KP;
     em.stats_stride = 2 * V * KP + KP + 2;
-    em.nblk = (int)((N + bayes_cells_per_block(KP) - 1) / bayes_cells_per_block(KP));
+    {   // Bayes blocks per restart: every block gets the same number of cells, so pick a count that fills whole waves of
+        // one block per SM (R * nblk close to a multiple of the SM count), never more blocks than 64-cell chunks
+        const int64_t nchunks = (N + bayes_cells_per_block(KP) - 1) / bayes_cells_per_block(KP);
+        const int sms = ctx->sm_count > 0 ? ctx->sm_count : 148;
+        int64_t best = std::min<int64_t>(nchunks, std::max<int64_t>(1, sms / R));
+        for (int waves = 1; waves <= 8 && best < nchunks; ++waves) {
+            const int64_t b = std::min<int64_t>(nchunks, (int64_t)waves * sms / R);
+            if (b < 1) continue;
+            best = b;
+            if ((double)(b * R) >= 0.9 * waves * sms) break;
+        }
+        em.nblk = (int)best;
+    }
     SCS_TRY(dev_alloc(ctx, &em.T, (int64_t)R * 2 * V * KP));
     SCS_TRY(dev_alloc(ctx, &em.P, (int64_t)R * V * KP));
     SCS_TRY(dev_alloc(ctx, &em.L, (int64_t)R * N * KP));
@@ -260,8 +275,8 @@ int scs_em_begin(scs_ctx* ctx, int R, int K, const double* P0, int max_iter) {
     SCS_TRY(dev_alloc(ctx, &em.hq, (int64_t)R * em.h_stride));
     k_fill_u32<<<(unsigned)((R * em.h_stride + 255) / 256), 256, 0, ctx->stream>>>(em.hq, R * em.h_stride, SPARSE_DENSE);
     ctx->launches++;
-    SCS_TRY(dev_alloc(ctx, &em.sched, 2 * R));
-    SCS_CUDA(cudaMemsetAsync(em.sched, 0, (size_t)R * 8, ctx->stream));
+    SCS_TRY(dev_alloc(ctx, &em.sched, 3 * R));           // [R][2] sparse M-step tickets, then [R] k_finalize block counts
+    SCS_CUDA(cudaMemsetAsync(em.sched, 0, (size_t)R * 12, ctx->stream));
     SCS_TRY(dev_alloc(ctx, &em.hist, (int64_t)R * max_iter));
     SCS_TRY(dev_alloc(ctx, &em.ll_prev, R));
     SCS_TRY(dev_alloc(ctx, &em.iters, R));

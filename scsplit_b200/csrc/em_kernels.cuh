@@ -8,7 +8,7 @@
 //   k_colsum_partial the same partials for an injected W (step-level M-step entry)
 //   k_reduce_stats   block partials -> colsum[K], LL, dense-cell count                           (scSplit:188,198)
 //   k_finalize       S, k_alt -> P, log2 P, log2(1-P)                                             (scSplit:196, 176-177)
-//   k_update_prior   colsum -> lP_s; LL history; bitwise stop rule                                (scSplit:198, 156-161)
+//   update_prior     colsum -> lP_s; LL history; bitwise stop rule (last block of k_finalize)      (scSplit:198, 156-161)
 //   (k_mstep_sparse, the M-step for saturated posteriors, lives in mstep_sparse.cuh)
 #pragma once
 #include "common.cuh"
@@ -151,9 +151,15 @@ __device__ __forceinline__ uint32_t sparsify_row(const double (&w)[KP], int K) {
 // 2^x for the Bayes ratios.  Saturated posteriors make almost every exponent either hugely negative or hugely positive;
 // exp2 returns exactly 0 below -1075 and exactly +inf from 1024 on, so those lanes skip the (long) double-precision exp2
 // sequence without changing a bit of the result.  NaN exponents fall through to exp2 and stay NaN.
+// The winning state's own term has an exponent of rounding-noise size (|x| ~ 1e-13): there 2^x = 1 + y + y^2/2 with
+// y = x ln 2 is exact to well below half an ulp (the next term is < 2e-20 for |x| < 2^-20).
 __device__ __forceinline__ double exp2_sat(double x) {
     if (x < -1100.0) return 0.0;
     if (x > 1100.0) return __longlong_as_double(0x7ff0000000000000LL);
+    if (fabs(x) < 9.5367431640625e-07) {
+        const double y = x * 0.6931471805599453094;
+        return fma(y, fma(y, 0.5, 1.0), 1.0);
+    }
     return exp2(x);
 }
 
@@ -165,6 +171,10 @@ struct BayesCfg {
 };
 inline int bayes_cells_per_block(int KP) { return KP <= 16 ? 64 : 32; }
 
+// Block b of nblk owns the contiguous cells [N*b/nblk, N*(b+1)/nblk) and walks them CPB at a time (whole warps without
+// cells skip the pass), so every block does the same work whatever N is and the grid can be sized to the SM count.
+__device__ __forceinline__ int64_t bayes_cell_lo(int64_t N, int b, int nblk) { return N * b / nblk; }
+
 template <int KP>
 __global__ void __launch_bounds__(1024) k_bayes(int64_t N, int K, const double* __restrict__ L, double* __restrict__ W,
                                                const double* __restrict__ lps, double* __restrict__ partial, int nblk,
@@ -174,41 +184,44 @@ __global__ void __launch_bounds__(1024) k_bayes(int64_t N, int K, const double* 
     if (done && done[r]) return;
     __shared__ double s_red[32 * (KP + 2)];
     const int i = threadIdx.x & (C::GL - 1);
-    const int64_t c = (int64_t)blockIdx.x * C::CPB + threadIdx.x / C::GL;
-    const bool live = c < N && i < K;
-    const double Li = live ? L[((int64_t)r * N + c) * KP + i] : 0.0;
     const double si = i < K ? lps[(int64_t)r * KP + i] : 0.0;
-    const double ti = Li + si;                                   // L_i + s_i
-    double denom = 0.0;
-    for (int j = 0; j < K; ++j) {
-        const double tj = __shfl_sync(0xffffffffu, ti, j, C::GL);
-        denom += exp2_sat((tj - Li) - si);
-    }
-    const double wi = live ? 1.0 / denom : 0.0;
-    if (c < N && i < KP) W[((int64_t)r * N + c) * KP + i] = wi;
-    // total log-likelihood term (skipna max, skipna sum), states taken in ascending order
-    double m = __shfl_sync(0xffffffffu, Li, 0, C::GL);
-    for (int k = 1; k < K; ++k) m = fmax(m, __shfl_sync(0xffffffffu, Li, k, C::GL));   // fmax ignores NaN operands
-    const double xi = exp2_sat((Li - m) + si);
-    double sum = 0.0;
-    for (int k = 0; k < K; ++k) {
-        const double xk = __shfl_sync(0xffffffffu, xi, k, C::GL);
-        if (xk == xk) sum += xk;
-    }
-    double w[KP];
-#pragma unroll
-    for (int k = 0; k < KP; ++k) w[k] = __shfl_sync(0xffffffffu, wi, k, C::GL);
+    const int64_t c_lo = bayes_cell_lo(N, blockIdx.x, nblk), c_hi = bayes_cell_lo(N, blockIdx.x + 1, nblk);
     double v[KP + 2];
 #pragma unroll
     for (int k = 0; k <= KP + 1; ++k) v[k] = 0.0;
-    if (c < N && i == 0) {
-        const double ll = log2(sum) + m;
+    for (int64_t c0 = c_lo + (threadIdx.x >> 5) * (32 / C::GL); c0 < c_hi; c0 += C::CPB) {   // warp-uniform
+        const int64_t c = c0 + (threadIdx.x & 31) / C::GL;
+        const bool live = c < c_hi && i < K;
+        const double Li = live ? L[((int64_t)r * N + c) * KP + i] : 0.0;
+        const double ti = Li + si;                                   // L_i + s_i
+        double denom = 0.0;
+        for (int j = 0; j < K; ++j) {
+            const double tj = __shfl_sync(0xffffffffu, ti, j, C::GL);
+            denom += exp2_sat((tj - Li) - si);
+        }
+        const double wi = live ? 1.0 / denom : 0.0;
+        if (c < c_hi && i < KP) W[((int64_t)r * N + c) * KP + i] = wi;
+        // total log-likelihood term (skipna max, skipna sum), states taken in ascending order
+        double m = __shfl_sync(0xffffffffu, Li, 0, C::GL);
+        for (int k = 1; k < K; ++k) m = fmax(m, __shfl_sync(0xffffffffu, Li, k, C::GL));   // fmax ignores NaN operands
+        const double xi = exp2_sat((Li - m) + si);
+        double sum = 0.0;
+        for (int k = 0; k < K; ++k) {
+            const double xk = __shfl_sync(0xffffffffu, xi, k, C::GL);
+            if (xk == xk) sum += xk;
+        }
+        double w[KP];
 #pragma unroll
-        for (int k = 0; k < KP; ++k) v[k] = (w[k] == w[k]) ? w[k] : 0.0;
-        v[KP] = (ll == ll) ? ll : 0.0;
-        const uint32_t q = sparsify_row<KP>(w, K);
-        hq[(int64_t)r * h_stride + c] = q;
-        v[KP + 1] = q == SPARSE_DENSE ? 1.0 : 0.0;       // number of cells that need the dense M-step path
+        for (int k = 0; k < KP; ++k) w[k] = __shfl_sync(0xffffffffu, wi, k, C::GL);
+        if (c < c_hi && i == 0) {
+            const double ll = log2(sum) + m;
+#pragma unroll
+            for (int k = 0; k < KP; ++k) v[k] += (w[k] == w[k]) ? w[k] : 0.0;
+            v[KP] += (ll == ll) ? ll : 0.0;
+            const uint32_t q = sparsify_row<KP>(w, K);
+            hq[(int64_t)r * h_stride + c] = q;
+            v[KP + 1] += q == SPARSE_DENSE ? 1.0 : 0.0;      // number of cells that need the dense M-step path
+        }
     }
     block_reduce_store<KP + 2, C::GL>(v, s_red, partial + ((int64_t)r * nblk + blockIdx.x) * (KP + 2));
 }
@@ -221,20 +234,23 @@ __global__ void __launch_bounds__(1024) k_colsum_partial(int64_t N, int K, const
     const int r = blockIdx.y;
     __shared__ double s_red[32 * (KP + 2)];
     const int i = threadIdx.x & (C::GL - 1);
-    const int64_t c = (int64_t)blockIdx.x * C::CPB + threadIdx.x / C::GL;
-    const double wi = (c < N && i < K) ? W[((int64_t)r * N + c) * KP + i] : 0.0;
-    double w[KP];
-#pragma unroll
-    for (int k = 0; k < KP; ++k) w[k] = __shfl_sync(0xffffffffu, wi, k, C::GL);
+    const int64_t c_lo = bayes_cell_lo(N, blockIdx.x, nblk), c_hi = bayes_cell_lo(N, blockIdx.x + 1, nblk);
     double v[KP + 2];
 #pragma unroll
     for (int k = 0; k <= KP + 1; ++k) v[k] = 0.0;
-    if (c < N && i == 0) {
+    for (int64_t c0 = c_lo + (threadIdx.x >> 5) * (32 / C::GL); c0 < c_hi; c0 += C::CPB) {   // warp-uniform
+        const int64_t c = c0 + (threadIdx.x & 31) / C::GL;
+        const double wi = (c < c_hi && i < K) ? W[((int64_t)r * N + c) * KP + i] : 0.0;
+        double w[KP];
 #pragma unroll
-        for (int k = 0; k < KP; ++k) v[k] = (w[k] == w[k]) ? w[k] : 0.0;
-        const uint32_t q = sparsify_row<KP>(w, K);
-        hq[(int64_t)r * h_stride + c] = q;
-        v[KP + 1] = q == SPARSE_DENSE ? 1.0 : 0.0;
+        for (int k = 0; k < KP; ++k) w[k] = __shfl_sync(0xffffffffu, wi, k, C::GL);
+        if (c < c_hi && i == 0) {
+#pragma unroll
+            for (int k = 0; k < KP; ++k) v[k] += (w[k] == w[k]) ? w[k] : 0.0;
+            const uint32_t q = sparsify_row<KP>(w, K);
+            hq[(int64_t)r * h_stride + c] = q;
+            v[KP + 1] += q == SPARSE_DENSE ? 1.0 : 0.0;
+        }
     }
     // [KP] (LL) is left untouched by the caller's reduce (with_ll = 0)
     block_reduce_store<KP + 2, C::GL>(v, s_red, partial + ((int64_t)r * nblk + blockIdx.x) * (KP + 2));
@@ -257,48 +273,6 @@ static __global__ void __launch_bounds__(256) k_reduce_stats(int KP, int NV, con
     }
 }
 
-// P = (altW + k_alt) / ((altW + refW) + 1);  T[v] = log2 P, T[V+v] = log2(1 - P)   (scSplit:196, 176-177)
-static __global__ void __launch_bounds__(256) k_finalize(int64_t V, int K, int KP, const double* __restrict__ stats, int64_t stats_stride,
-                                                  const double* __restrict__ kalt, double* __restrict__ P, double* __restrict__ T,
-                                                  const int32_t* __restrict__ done) {
-    const int r = blockIdx.y;
-    if (done && done[r]) return;
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= V * KP) return;
-    const int64_t v = i / KP;
-    const int k = (int)(i - v * KP);
-    const double* S = stats + (int64_t)r * stats_stride;
-    double p = 0.0, lp = 0.0, lq = 0.0;
-    if (k < K) {
-        const double a = S[v * KP + k], rf = S[(V + v) * KP + k];
-        p = (a + kalt[v]) / ((a + rf) + 1.0);
-        lp = log2(p);
-        lq = log2(1.0 - p);
-    }
-    P[((int64_t)r * V + v) * KP + k] = p;
-    if (T) {
-        T[((int64_t)r * 2 * V + v) * KP + k] = lp;
-        T[((int64_t)r * 2 * V + V + v) * KP + k] = lq;
-    }
-}
-
-// log tables from a given P (EM start, scs_em_set(SCS_P), post-EM scores)
-static __global__ void __launch_bounds__(256) k_tables_from_P(int64_t V, int K, int KP, const double* __restrict__ P, double* __restrict__ T) {
-    const int r = blockIdx.y;
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= V * KP) return;
-    const int64_t v = i / KP;
-    const int k = (int)(i - v * KP);
-    double lp = 0.0, lq = 0.0;
-    if (k < K) {
-        const double p = P[((int64_t)r * V + v) * KP + k];
-        lp = log2(p);
-        lq = log2(1.0 - p);
-    }
-    T[((int64_t)r * 2 * V + v) * KP + k] = lp;
-    T[((int64_t)r * 2 * V + V + v) * KP + k] = lq;
-}
-
 // numpy's pairwise add.reduce for n < 128 contiguous doubles (what pandas Series.sum() runs for K values)
 __device__ __forceinline__ double numpy_sum_small(const double* a, int n) {
     if (n < 8) {
@@ -317,25 +291,93 @@ __device__ __forceinline__ double numpy_sum_small(const double* a, int n) {
     return res;
 }
 
+// What one thread does per restart once the statistics tail is final.
+struct PriorArgs {
+    int64_t tail_off;     // offset of [colsum KP | LL | dense count] inside a restart's statistics
+    double* lps;          // [R][KP]
+    double* hist;         // [R][max_iter]
+    int max_iter;
+    double* ll_prev;      // [R]
+    int32_t* iters;       // [R]
+    int32_t* done;        // [R]
+    int32_t* count;       // [R] blocks of k_finalize that have finished (self-resetting)
+    int track, check_conv;
+};
+
 // lP_s = log2(colsum) - log2(sum colsum)  (scSplit:198); LL history and the bitwise stop rule (scSplit:156-162)
-static __global__ void k_update_prior(int K, int KP, const double* __restrict__ stats, int64_t stats_stride, int64_t tail_off,
-                               double* __restrict__ lps, double* __restrict__ hist, int max_iter, double* __restrict__ ll_prev,
-                               int32_t* __restrict__ iters, int32_t* __restrict__ done, int track, int check_conv) {
-    const int r = blockIdx.x;
-    if (track && check_conv && done[r]) return;
-    if (threadIdx.x != 0) return;
-    const double* tail = stats + (int64_t)r * stats_stride + tail_off;
+__device__ __forceinline__ void update_prior(int r, int K, int KP, const double* __restrict__ stats, int64_t stats_stride, const PriorArgs& a) {
+    if (a.track && a.check_conv && a.done[r]) return;
+    const double* tail = stats + (int64_t)r * stats_stride + a.tail_off;
     const double tot = numpy_sum_small(tail, K);
     const double ltot = log2(tot);
-    for (int k = 0; k < K; ++k) lps[(int64_t)r * KP + k] = log2(tail[k]) - ltot;
-    if (track) {
+    for (int k = 0; k < K; ++k) a.lps[(int64_t)r * KP + k] = log2(tail[k]) - ltot;
+    if (a.track) {
         const double ll = tail[KP];
-        const int it = iters[r];
-        if (it < max_iter) hist[(int64_t)r * max_iter + it] = ll;
-        iters[r] = it + 1;
-        if (check_conv && (ll == ll_prev[r] || it + 1 >= max_iter)) done[r] = 1;
-        ll_prev[r] = ll;
+        const int it = a.iters[r];
+        if (it < a.max_iter) a.hist[(int64_t)r * a.max_iter + it] = ll;
+        a.iters[r] = it + 1;
+        if (a.check_conv && (ll == a.ll_prev[r] || it + 1 >= a.max_iter)) a.done[r] = 1;
+        a.ll_prev[r] = ll;
     }
+}
+
+// P = (altW + k_alt) / ((altW + refW) + 1);  T[v] = log2 P, T[V+v] = log2(1 - P)   (scSplit:196, 176-177)
+__device__ __forceinline__ void finalize_rows(int64_t V, int K, int KP, const double* __restrict__ stats, int64_t stats_stride,
+                                              const double* __restrict__ kalt, double* __restrict__ P, double* __restrict__ T, int r) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= V * KP) return;   // (the caller's block still takes part in the block count)
+    const int64_t v = i / KP;
+    const int k = (int)(i - v * KP);
+    const double* S = stats + (int64_t)r * stats_stride;
+    double p = 0.0, lp = 0.0, lq = 0.0;
+    if (k < K) {
+        const double a = S[v * KP + k], rf = S[(V + v) * KP + k];
+        p = (a + kalt[v]) / ((a + rf) + 1.0);
+        lp = log2(p);
+        lq = log2(1.0 - p);
+    }
+    P[((int64_t)r * V + v) * KP + k] = p;
+    if (T) {
+        T[((int64_t)r * 2 * V + v) * KP + k] = lp;
+        T[((int64_t)r * 2 * V + V + v) * KP + k] = lq;
+    }
+}
+
+// With `prior` (the EM loop) the LAST block of a restart to finish also runs update_prior (block counter in prior->count,
+// left at zero again): by then every block has read the stop flag, so a restart that stops NOW still gets this
+// iteration's P (scSplit:155-162: E, M, then the test); `done` skips the restarts that had stopped before this iteration.
+static __global__ void __launch_bounds__(256) k_finalize(int64_t V, int K, int KP, const double* __restrict__ stats, int64_t stats_stride,
+                                                  const double* __restrict__ kalt, double* __restrict__ P, double* __restrict__ T,
+                                                  const int32_t* __restrict__ done, const PriorArgs prior) {
+    const int r = blockIdx.y;
+    if (done && done[r]) return;
+    finalize_rows(V, K, KP, stats, stats_stride, kalt, P, T, r);
+    if (prior.lps) {
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0 && atomicAdd(prior.count + r, 1) == (int)gridDim.x - 1) {
+            prior.count[r] = 0;
+            update_prior(r, K, KP, stats, stats_stride, prior);
+        }
+    }
+}
+
+
+// log tables from a given P (EM start, scs_em_set(SCS_P), post-EM scores)
+static __global__ void __launch_bounds__(256) k_tables_from_P(int64_t V, int K, int KP, const double* __restrict__ P, double* __restrict__ T) {
+    const int r = blockIdx.y;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= V * KP) return;
+    const int64_t v = i / KP;
+    const int k = (int)(i - v * KP);
+    double lp = 0.0, lq = 0.0;
+    if (k < K) {
+        const double p = P[((int64_t)r * V + v) * KP + k];
+        lp = log2(p);
+        lq = log2(1.0 - p);
+    }
+    T[((int64_t)r * 2 * V + v) * KP + k] = lp;
+    T[((int64_t)r * 2 * V + V + v) * KP + k] = lq;
 }
 
 }  // namespace scs

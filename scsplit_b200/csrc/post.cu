@@ -202,7 +202,7 @@ int scs_seed_af(scs_ctx* ctx, int R, int K, const int32_t* labels, double* P0_ou
     SCS_TRY(launch_spmm(ctx, 1, KP, R, d_W, N * KP, d_S, stride, nullptr));
     if (ctx->world > 1) SCS_TRY(comm_allreduce_f64(ctx, d_S, (int64_t)R * stride));
     dim3 grid((unsigned)((V * KP + 255) / 256), (unsigned)R);
-    k_finalize<<<grid, 256, 0, st>>>(V, K, KP, d_S, stride, ctx->kalt, d_P, nullptr, nullptr);
+    k_finalize<<<grid, 256, 0, st>>>(V, K, KP, d_S, stride, ctx->kalt, d_P, nullptr, nullptr, PriorArgs{});
     ctx->launches++;
     SCS_TRY(download_pitched(ctx, P0_out, d_P, (int64_t)R * V, K, KP));
     SCS_CUDA(cudaStreamSynchronize(st));

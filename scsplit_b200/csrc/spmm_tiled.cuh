@@ -199,8 +199,20 @@ __global__ void __launch_bounds__(256) k_spmm_combine(int64_t nrows, int ntiles,
     part += (int64_t)r * part_stride;
     X += (int64_t)r * x_stride;
     double2 acc = make_double2(0.0, 0.0);
-    for (int t = 0; t < ntiles; ++t) {
-        const double2 p = *reinterpret_cast<const double2*>(part + ((int64_t)t * nrows + row) * KP + 2 * j);
+    // the partials of a row are ntiles strided 16-byte loads: eight are requested before the (ordered) adds, which is what
+    // keeps enough bytes in flight at ~700 threads per SM
+    const double* prow = part + row * KP + 2 * j;
+    const int64_t tstride = nrows * KP;
+    int t = 0;
+    for (; t + 8 <= ntiles; t += 8) {
+        double2 p[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) p[u] = *reinterpret_cast<const double2*>(prow + (int64_t)(t + u) * tstride);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { acc.x += p[u].x; acc.y += p[u].y; }
+    }
+    for (; t < ntiles; ++t) {
+        const double2 p = *reinterpret_cast<const double2*>(prow + (int64_t)t * tstride);
         acc.x += p.x;
         acc.y += p.y;
     }
