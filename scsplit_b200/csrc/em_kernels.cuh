@@ -141,6 +141,51 @@ __device__ __forceinline__ uint32_t sparsify_row(const double (&w)[KP], int K) {
     return ok ? (bits | (uint32_t)im) : SPARSE_DENSE;
 }
 
+// The same packing decided by the GL lanes of a cell together (lane i holds W[c,i]): the row is sparse iff exactly one
+// live lane holds a weight in [0.5, 1.5], every other live lane is below SPARSE_TINY (NaN is neither) and the winner's
+// 1 - weight fits the float format.  Every lane of the group returns the word.
+template <int GL>
+__device__ __forceinline__ uint32_t sparsify_group(double wi, int i, int K) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t gmask = (GL == 32 ? 0xffffffffu : ((1u << GL) - 1u) << (lane & ~(GL - 1)));
+    const uint32_t live = (K >= 32 ? 0xffffffffu : ((1u << K) - 1u) << (lane & ~(GL - 1))) & gmask;
+    const bool big = wi >= 0.5 && wi <= 1.5;
+    const uint32_t bigm = __ballot_sync(0xffffffffu, big && i < K) & gmask;
+    const uint32_t tinym = __ballot_sync(0xffffffffu, wi < SPARSE_TINY && i < K) & gmask;
+    const double eps = 1.0 - wi;                      // exact for the winner (Sterbenz)
+    const float ef = (float)eps;
+    const uint32_t bits = __float_as_uint(ef);
+    const bool fits = ((double)ef == eps) && ((bits & 31u) == 0u);
+    const int win = __ffs(bigm) - 1;                  // warp lane of the winner (if any)
+    const uint32_t word = __shfl_sync(0xffffffffu, fits ? (bits | (uint32_t)i) : SPARSE_DENSE, win < 0 ? 0 : win);
+    const bool ok = __popc(bigm) == 1 && ((bigm | tinym) == live);
+    return ok ? word : SPARSE_DENSE;
+}
+
+// Block statistics of k_bayes / k_colsum_partial: lane i of every cell group has accumulated column i's mass in `mass`, lane
+// 0 of the group the LL terms and the dense-row count.  Fixed order: the two groups of a warp (GL = 16), then the warps.
+template <int KP, int GL>
+__device__ __forceinline__ void block_stats_store(double mass, double ll, double dense, double* smem /*[warps][KP+2]*/,
+                                                  double* out /*[KP+2]*/) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, i = lane & (GL - 1);
+    if (GL == 16) {
+        mass += __shfl_xor_sync(0xffffffffu, mass, 16);
+        ll += __shfl_xor_sync(0xffffffffu, ll, 16);
+        dense += __shfl_xor_sync(0xffffffffu, dense, 16);
+    }
+    if (lane < GL && i < KP) smem[warp * (KP + 2) + i] = mass;
+    if (lane == 0) {
+        smem[warp * (KP + 2) + KP] = ll;
+        smem[warp * (KP + 2) + KP + 1] = dense;
+    }
+    __syncthreads();
+    if (threadIdx.x < KP + 2) {
+        double s = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += smem[w * (KP + 2) + threadIdx.x];
+        out[threadIdx.x] = s;
+    }
+}
+
 // W[c,i] = 1 / sum_j 2^(((L_j + s_j) - L_i) - s_i)   (scSplit:181-185, j ascending, left-to-right)
 // ll_c   = log2( sum_k 2^((L_k - max_k L) + s_k) ) + max_k L   with pandas skipna  (scSplit:188)
 // partial[r][blk][0..KP) = sum over the block's cells of W[c,k] (NaN skipped, scSplit:198), [KP] = sum of ll_c,
@@ -148,19 +193,29 @@ __device__ __forceinline__ uint32_t sparsify_row(const double (&w)[KP], int K) {
 //
 // One cell is handled by a group of BAYES_GL lanes (lane i = state i), so the K^2 exp2 of a cell run K-wide and a 20k-cell
 // pool still gives every SM sub-partition several warps; sums over states are taken in the reference's order by shuffling.
-// 2^x for the Bayes ratios.  Saturated posteriors make almost every exponent either hugely negative or hugely positive;
-// exp2 returns exactly 0 below -1075 and exactly +inf from 1024 on, so those lanes skip the (long) double-precision exp2
-// sequence without changing a bit of the result.  NaN exponents fall through to exp2 and stay NaN.
-// The winning state's own term has an exponent of rounding-noise size (|x| ~ 1e-13): there 2^x = 1 + y + y^2/2 with
-// y = x ln 2 is exact to well below half an ulp (the next term is < 2e-20 for |x| < 2^-20).
-__device__ __forceinline__ double exp2_sat(double x) {
-    if (x < -1100.0) return 0.0;
-    if (x > 1100.0) return __longlong_as_double(0x7ff0000000000000LL);
-    if (fabs(x) < 9.5367431640625e-07) {
-        const double y = x * 0.6931471805599453094;
-        return fma(y, fma(y, 0.5, 1.0), 1.0);
-    }
-    return exp2(x);
+// 2^x for the Bayes ratios, branch-free.  x = n + f with n = rint(x), |f| <= 1/2; 2^f by the degree-13 Taylor series in
+// f ln 2 (remainder < 4.2e-18, below a quarter ulp; Horner rounding keeps the result within ~1 ulp, as CUDA's own exp2
+// is); 2^n is applied as two exact power-of-two factors so that results in the denormal range are rounded once and
+// exponents from 1024 on overflow to +inf.  The argument is clamped to +-1100 first, where the result is exactly 0 or
+// +inf anyway (saturated posteriors put almost every exponent out there); NaN stays NaN.  The coefficients sit in the
+// constant bank so the fused multiply-adds read them as operands.
+__constant__ double EXP2_C[14] = {1.0,
+                                  0x1.62e42fefa39efp-1,  0x1.ebfbdff82c58fp-3,  0x1.c6b08d704a0c0p-5,  0x1.3b2ab6fba4e77p-7,
+                                  0x1.5d87fe78a6731p-10, 0x1.430912f86c787p-13, 0x1.ffcbfc588b0c7p-17, 0x1.62c0223a5c824p-20,
+                                  0x1.b5253d395e7c4p-24, 0x1.e4cf5158b8ecap-28, 0x1.e8cac7351bb25p-32, 0x1.c3bd650fc2986p-36,
+                                  0x1.816193166d0f9p-40};
+__device__ __forceinline__ double exp2_bf(double x) {
+    const double xc = fmin(fmax(x, -1100.0), 1100.0);
+    const double MAGIC = 6755399441055744.0;             // 1.5 * 2^52: the add rounds xc to an integer in the low word
+    const double t = xc + MAGIC;
+    const int n = __double2loint(t);
+    const double f = xc - (t - MAGIC);
+    double p = EXP2_C[13];
+#pragma unroll
+    for (int k = 12; k >= 0; --k) p = fma(p, f, EXP2_C[k]);
+    const int n1 = n >> 1, n2 = n - n1;
+    const double r = (p * __hiloint2double((n1 + 1023) << 20, 0)) * __hiloint2double((n2 + 1023) << 20, 0);
+    return x != x ? x : r;
 }
 
 template <int KP>
@@ -186,44 +241,39 @@ __global__ void __launch_bounds__(1024) k_bayes(int64_t N, int K, const double* 
     const int i = threadIdx.x & (C::GL - 1);
     const double si = i < K ? lps[(int64_t)r * KP + i] : 0.0;
     const int64_t c_lo = bayes_cell_lo(N, blockIdx.x, nblk), c_hi = bayes_cell_lo(N, blockIdx.x + 1, nblk);
-    double v[KP + 2];
-#pragma unroll
-    for (int k = 0; k <= KP + 1; ++k) v[k] = 0.0;
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+    double mass = 0.0, llsum = 0.0, dense = 0.0;
     for (int64_t c0 = c_lo + (threadIdx.x >> 5) * (32 / C::GL); c0 < c_hi; c0 += C::CPB) {   // warp-uniform
         const int64_t c = c0 + (threadIdx.x & 31) / C::GL;
-        const bool live = c < c_hi && i < K;
+        const bool cell = c < c_hi, live = cell && i < K;
         const double Li = live ? L[((int64_t)r * N + c) * KP + i] : 0.0;
         const double ti = Li + si;                                   // L_i + s_i
         double denom = 0.0;
-        for (int j = 0; j < K; ++j) {
+        for (int j = 0; j < K; ++j) {                                // j ascending, left to right, as the reference adds
             const double tj = __shfl_sync(0xffffffffu, ti, j, C::GL);
-            denom += exp2_sat((tj - Li) - si);
+            denom += exp2_bf((tj - Li) - si);
         }
         const double wi = live ? 1.0 / denom : 0.0;
-        if (c < c_hi && i < KP) W[((int64_t)r * N + c) * KP + i] = wi;
-        // total log-likelihood term (skipna max, skipna sum), states taken in ascending order
-        double m = __shfl_sync(0xffffffffu, Li, 0, C::GL);
-        for (int k = 1; k < K; ++k) m = fmax(m, __shfl_sync(0xffffffffu, Li, k, C::GL));   // fmax ignores NaN operands
-        const double xi = exp2_sat((Li - m) + si);
-        double sum = 0.0;
-        for (int k = 0; k < K; ++k) {
-            const double xk = __shfl_sync(0xffffffffu, xi, k, C::GL);
-            if (xk == xk) sum += xk;
-        }
-        double w[KP];
+        if (cell && i < KP) W[((int64_t)r * N + c) * KP + i] = wi;
+        // total log-likelihood term: skipna max and skipna sum over the states.  Lanes beyond K carry NaN into the max
+        // (fmax drops NaN operands, and an all-NaN row stays NaN) and 0 into the sum; both run as xor trees.
+        double m = live ? Li : qnan;
 #pragma unroll
-        for (int k = 0; k < KP; ++k) w[k] = __shfl_sync(0xffffffffu, wi, k, C::GL);
-        if (c < c_hi && i == 0) {
+        for (int o = C::GL / 2; o; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+        const double xi = exp2_bf((Li - m) + si);
+        double sum = (live && xi == xi) ? xi : 0.0;
+#pragma unroll
+        for (int o = C::GL / 2; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        const uint32_t q = sparsify_group<C::GL>(wi, i, K);
+        if (live && wi == wi) mass += wi;                            // column mass, NaN skipped (scSplit:198)
+        if (cell && i == 0) {
             const double ll = log2(sum) + m;
-#pragma unroll
-            for (int k = 0; k < KP; ++k) v[k] += (w[k] == w[k]) ? w[k] : 0.0;
-            v[KP] += (ll == ll) ? ll : 0.0;
-            const uint32_t q = sparsify_row<KP>(w, K);
+            if (ll == ll) llsum += ll;
             hq[(int64_t)r * h_stride + c] = q;
-            v[KP + 1] += q == SPARSE_DENSE ? 1.0 : 0.0;      // number of cells that need the dense M-step path
+            dense += q == SPARSE_DENSE ? 1.0 : 0.0;                  // number of cells that need the dense M-step path
         }
     }
-    block_reduce_store<KP + 2, C::GL>(v, s_red, partial + ((int64_t)r * nblk + blockIdx.x) * (KP + 2));
+    block_stats_store<KP, C::GL>(mass, llsum, dense, s_red, partial + ((int64_t)r * nblk + blockIdx.x) * (KP + 2));
 }
 
 // column mass and packed form of an arbitrary W (step-level M-step entry): same block mapping and order as k_bayes
@@ -235,25 +285,20 @@ __global__ void __launch_bounds__(1024) k_colsum_partial(int64_t N, int K, const
     __shared__ double s_red[32 * (KP + 2)];
     const int i = threadIdx.x & (C::GL - 1);
     const int64_t c_lo = bayes_cell_lo(N, blockIdx.x, nblk), c_hi = bayes_cell_lo(N, blockIdx.x + 1, nblk);
-    double v[KP + 2];
-#pragma unroll
-    for (int k = 0; k <= KP + 1; ++k) v[k] = 0.0;
+    double mass = 0.0, dense = 0.0;
     for (int64_t c0 = c_lo + (threadIdx.x >> 5) * (32 / C::GL); c0 < c_hi; c0 += C::CPB) {   // warp-uniform
         const int64_t c = c0 + (threadIdx.x & 31) / C::GL;
-        const double wi = (c < c_hi && i < K) ? W[((int64_t)r * N + c) * KP + i] : 0.0;
-        double w[KP];
-#pragma unroll
-        for (int k = 0; k < KP; ++k) w[k] = __shfl_sync(0xffffffffu, wi, k, C::GL);
-        if (c < c_hi && i == 0) {
-#pragma unroll
-            for (int k = 0; k < KP; ++k) v[k] += (w[k] == w[k]) ? w[k] : 0.0;
-            const uint32_t q = sparsify_row<KP>(w, K);
+        const bool cell = c < c_hi, live = cell && i < K;
+        const double wi = live ? W[((int64_t)r * N + c) * KP + i] : 0.0;
+        const uint32_t q = sparsify_group<C::GL>(wi, i, K);
+        if (live && wi == wi) mass += wi;
+        if (cell && i == 0) {
             hq[(int64_t)r * h_stride + c] = q;
-            v[KP + 1] += q == SPARSE_DENSE ? 1.0 : 0.0;
+            dense += q == SPARSE_DENSE ? 1.0 : 0.0;
         }
     }
     // [KP] (LL) is left untouched by the caller's reduce (with_ll = 0)
-    block_reduce_store<KP + 2, C::GL>(v, s_red, partial + ((int64_t)r * nblk + blockIdx.x) * (KP + 2));
+    block_stats_store<KP, C::GL>(mass, 0.0, dense, s_red, partial + ((int64_t)r * nblk + blockIdx.x) * (KP + 2));
 }
 
 // partial[r][blk][NV] -> tail[r][0..NV): column mass [0,KP), LL [KP] (if with_ll), dense-path cell count [KP+1] (if NV = KP+2);

@@ -101,7 +101,7 @@ k_mstep_sparse(int64_t nrows, int64_t N, int K, const int64_t* __restrict__ lptr
     constexpr size_t ACC_BYTES = (size_t)SPARSE_THREADS * KP * 8;
     unsigned char* s_tab = smem + ACC_BYTES;
     uint64_t* bar = reinterpret_cast<uint64_t*>(s_tab + sparse_tab_bytes(h_stride));
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) {
         mbar_init(bar, 1);
         fence_proxy_async();
