@@ -141,6 +141,9 @@ int scs_kernel_times(scs_ctx* ctx, double out[4], int reset);
 /* select kernel variant: 0 = auto (tiled shared-memory SpMM; sparse M-step once posteriors saturate), 1 = v1 (warp per row,
  * gathers from L1/L2; for A/B tests), 2 = tiled SpMM for both half-steps (sparse M-step off) */
 int scs_set_variant(scs_ctx* ctx, int variant);
+/* self-test of the device 2^x used by the Bayes step (scSplit:184, 188 evaluate `2 ** x` in numpy): y[i] = 2^x[i] for n host
+ * doubles, computed on the context's device with the kernel's own routine */
+int scs_selftest_exp2(scs_ctx* ctx, const double* x, double* y, int64_t n);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

@@ -50,6 +50,7 @@ SIGNATURES = {
     "scs_set_timing": (c_int, [c_void_p, c_int]),
     "scs_kernel_times": (c_int, [c_void_p, POINTER(c_double), c_int]),
     "scs_set_variant": (c_int, [c_void_p, c_int]),
+    "scs_selftest_exp2": (c_int, [c_void_p, c_void_p, c_void_p, c_int64]),
 }
 
 _lib = None

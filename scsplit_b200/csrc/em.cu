@@ -111,6 +111,11 @@ int em_free(scs_ctx* ctx) {
     return 0;
 }
 
+static __global__ void k_selftest_exp2(const double* __restrict__ x, double* __restrict__ y, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] = exp2_bf(x[i]);
+}
+
 static __global__ void k_fill_u32(uint32_t* __restrict__ p, int64_t n, uint32_t v) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;
@@ -231,6 +236,24 @@ static int run_m(scs_ctx* ctx, const int32_t* done, int track, int check_conv) {
 using namespace scs;
 
 extern "C" {
+
+int scs_selftest_exp2(scs_ctx* ctx, const double* x, double* y, int64_t n) {
+    SCS_CHECK(ctx, "null context");
+    SCS_CHECK(x && y && n >= 0, "bad arguments");
+    if (n == 0) return 0;
+    SCS_CUDA(cudaSetDevice(ctx->device));
+    double *dx = nullptr, *dy = nullptr;
+    SCS_TRY(dev_alloc(ctx, &dx, n));
+    SCS_TRY(dev_alloc(ctx, &dy, n));
+    SCS_CUDA(cudaMemcpyAsync(dx, x, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    k_selftest_exp2<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(dx, dy, n);
+    ctx->launches++;
+    SCS_CUDA(cudaMemcpyAsync(y, dy, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    SCS_CUDA(cudaStreamSynchronize(ctx->stream));
+    dev_free(ctx, dx);
+    dev_free(ctx, dy);
+    return 0;
+}
 
 int scs_em_end(scs_ctx* ctx) {
     SCS_CHECK(ctx, "null context");

@@ -229,3 +229,10 @@ class Engine:
 
     def set_variant(self, v):
         check(self.lib.scs_set_variant(self.h, int(v)))
+
+    def selftest_exp2(self, x):
+        """2**x through the Bayes kernel's own device routine (diagnostic; tests compare it with numpy's)."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        y = np.empty_like(x)
+        check(self.lib.scs_selftest_exp2(self.h, x.ctypes.data, y.ctypes.data, x.size))
+        return y

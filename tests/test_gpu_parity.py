@@ -477,3 +477,28 @@ def test_tiny_shapes(V, N, K, E):
         U = ((ref != 0).astype(np.int8) + (alt != 0).astype(np.int8))
         assert np.array_equal(rc, np.asarray((U != 0).sum(axis=1)).ravel())
         assert np.array_equal(cc, np.asarray((U != 0).sum(axis=0)).ravel())
+
+
+def test_device_exp2_matches_numpy(E):
+    """The Bayes step's own 2**x (scSplit:184, 188 use numpy's) over the whole exponent range, specials included."""
+    from scipy.sparse import csr_matrix
+    rng = np.random.default_rng(7)
+    x = np.concatenate([
+        rng.uniform(-1080, 1030, 200000), rng.uniform(-2, 2, 100000), rng.normal(0, 1e-13, 50000),
+        rng.uniform(-1075, -1020, 50000),                       # results in the denormal range
+        np.arange(-1080, 1030, dtype=np.float64), np.arange(-1080, 1030) + 0.5,
+        [0.0, -0.0, 1023.9999999999999, 1024.0, 1e300, -1e300, np.inf, -np.inf, np.nan, -1074.0, -1074.5, -1075.0, -1076.0],
+    ])
+    m = csr_matrix(np.ones((2, 2), dtype=np.int16))
+    with E(m, m) as eng:
+        y = eng.selftest_exp2(x)
+    with np.errstate(over="ignore", under="ignore"):
+        want = np.exp2(x)
+    assert np.array_equal(np.isnan(y), np.isnan(want))
+    fin = np.isfinite(want) & ~np.isnan(want)
+    assert np.array_equal(y[~fin & ~np.isnan(want)], want[~fin & ~np.isnan(want)])          # +inf where numpy overflows
+    normal = fin & (want >= 2.0 ** -1022)
+    ulp = np.spacing(want[normal])
+    assert np.max(np.abs(y[normal] - want[normal]) / ulp) <= 2.0
+    sub = fin & (want < 2.0 ** -1022)                                                       # denormals and exact zeros
+    assert np.max(np.abs(y[sub] - want[sub])) <= 2.0 ** -1074
