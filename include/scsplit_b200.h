@@ -135,7 +135,9 @@ int scs_csv_free(scs_csv* csv);
 int scs_launch_count(scs_ctx* ctx, int64_t* out);
 /* average device time in microseconds of the E-step SpMM and M-step SpMM launches recorded with CUDA events
  * on the context's stream since the last reset; pass reset=1 to clear. out[0]=E us, out[1]=M us,
- * out[2]=#E launches timed, out[3]=#M launches timed.  Timing is enabled by scs_set_timing(ctx,1). */
+ * out[2]=#E-steps timed, out[3]=#M-steps timed.  scs_set_timing(ctx, n): n = 0 off, n >= 1 times every n-th E-step and
+ * every n-th M-step of the EM loop (the event records cost ~11 us per timed iteration at config 3, so a loop that is
+ * itself being timed samples, e.g. n = 8); step-level calls outside the loop are always timed while n >= 1. */
 int scs_set_timing(scs_ctx* ctx, int enable);
 int scs_kernel_times(scs_ctx* ctx, double out[4], int reset);
 /* select kernel variant: 0 = auto (tiled shared-memory SpMM; sparse M-step once posteriors saturate), 1 = v1 (warp per row,

@@ -141,7 +141,10 @@ int scs_launch_count(scs_ctx* ctx, int64_t* out) {
 
 int scs_set_timing(scs_ctx* ctx, int enable) {
     SCS_CHECK(ctx, "null context");
+    SCS_CHECK(enable >= 0, "timing period must be >= 0");
     ctx->timing = enable;
+    ctx->phase_seen[0] = ctx->phase_seen[1] = 0;
+    ctx->sample_on = true;
     return 0;
 }
 
@@ -167,10 +170,13 @@ int scs_kernel_times(scs_ctx* ctx, double out[4], int reset) {
     ctx->ev_pending.clear();
     // the M-step figure is the sum of its gated launches (tiled pair + sparse kernel; the inactive one costs ~2 us)
     out[0] = ctx->t_cnt[0] ? ctx->t_sum[0] / (double)ctx->t_cnt[0] : 0.0;
-    out[1] = ctx->t_cnt[1] ? (ctx->t_sum[1] + ctx->t_sum[2]) / (double)ctx->t_cnt[1] : 0.0;
+    out[1] = ctx->m_samples ? (ctx->t_sum[1] + ctx->t_sum[2]) / (double)ctx->m_samples : 0.0;
     out[2] = (double)ctx->t_cnt[0];
-    out[3] = (double)ctx->t_cnt[1];
-    if (reset) { for (int i = 0; i < 3; ++i) { ctx->t_sum[i] = 0.0; ctx->t_cnt[i] = 0; } }
+    out[3] = (double)ctx->m_samples;
+    if (reset) {
+        for (int i = 0; i < 3; ++i) { ctx->t_sum[i] = 0.0; ctx->t_cnt[i] = 0; }
+        ctx->m_samples = 0;
+    }
     return 0;
 }
 

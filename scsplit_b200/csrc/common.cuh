@@ -118,7 +118,10 @@ struct scs_ctx {
     int rank = 0, world = 1;
     // instrumentation
     int64_t launches = 0;
-    int timing = 0;
+    int timing = 0;              // 0 = off, n = time every n-th E-step and every n-th M-step
+    int64_t phase_seen[2] = {0, 0};   // E-steps / M-steps seen since timing was switched on
+    bool sample_on = true;       // whether the launches issued right now belong to a sampled step
+    int64_t m_samples = 0;       // sampled M-steps (an M-step is up to three launches)
     int variant = 0;
     std::vector<cudaEvent_t> ev_pool;
     std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> ev_pending;  // (kind, (start, stop))

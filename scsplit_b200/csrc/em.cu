@@ -31,7 +31,7 @@ namespace scs {
     }
 
 static int timing_begin(scs_ctx* ctx, cudaEvent_t* a, cudaEvent_t* b) {
-    if (!ctx->timing || ctx->ev_pending.size() >= 8192) { *a = *b = nullptr; return 0; }
+    if (!ctx->timing || !ctx->sample_on || ctx->ev_pending.size() >= 8192) { *a = *b = nullptr; return 0; }
     for (cudaEvent_t* e : {a, b}) {
         if (!ctx->ev_pool.empty()) { *e = ctx->ev_pool.back(); ctx->ev_pool.pop_back(); }
         else SCS_CUDA(cudaEventCreate(e));
@@ -39,6 +39,16 @@ static int timing_begin(scs_ctx* ctx, cudaEvent_t* a, cudaEvent_t* b) {
     SCS_CUDA(cudaEventRecord(*a, ctx->stream));
     return 0;
 }
+// E-steps (phase 0) and M-steps (phase 1) are sampled every ctx->timing-th time, so the event records cost the timed loop
+// next to nothing; launches outside the EM loop are always sampled
+struct PhaseSample {
+    scs_ctx* ctx;
+    PhaseSample(scs_ctx* c, int phase) : ctx(c) {
+        if (c->timing) c->sample_on = (c->phase_seen[phase]++ % c->timing) == 0;
+        if (c->timing && c->sample_on && phase == 1) c->m_samples++;
+    }
+    ~PhaseSample() { ctx->sample_on = true; }
+};
 static int timing_end(scs_ctx* ctx, int kind, cudaEvent_t a, cudaEvent_t b) {
     if (!a) return 0;
     SCS_CUDA(cudaEventRecord(b, ctx->stream));
@@ -175,6 +185,7 @@ static int tables_from_P(scs_ctx* ctx, int r0, int nr) {
 // ---- the five launches of one iteration -----------------------------------------------------------------
 static int run_e(scs_ctx* ctx, const int32_t* done) {
     EmState& em = ctx->em;
+    PhaseSample sample(ctx, 0);
     const int64_t V = ctx->V, N = ctx->N;
     SCS_TRY(launch_spmm(ctx, 0, em.KP, em.R, em.T, 2 * V * em.KP, em.L, N * em.KP, done));
     dim3 grid((unsigned)em.nblk, (unsigned)em.R);
@@ -188,6 +199,7 @@ static int run_e(scs_ctx* ctx, const int32_t* done) {
 
 static int run_m(scs_ctx* ctx, const int32_t* done, int track, int check_conv) {
     EmState& em = ctx->em;
+    PhaseSample sample(ctx, 1);
     const int64_t V = ctx->V, N = ctx->N;
     // M-step sums: the sparse kernel when (nearly) all posterior rows are saturated, else the tiled SpMM; both are launched
     // and the dense-path cell count in the statistics tail (written by k_reduce_stats) gates which one does the work
@@ -217,7 +229,6 @@ static int run_m(scs_ctx* ctx, const int32_t* done, int track, int check_conv) {
     // saturated the tiled pair is not launched at all until a later poll says otherwise)
     if (!(sparse && em.sparse_only))
         SCS_TRY(launch_spmm(ctx, 1, em.KP, em.R, em.W, N * em.KP, em.stats, em.stats_stride, done, gate, em.stats_stride, gate_thr));
-    else if (ctx->timing) ctx->t_cnt[1] += 1;   // keep the per-M-step average well defined
     if (ctx->world > 1) SCS_TRY(comm_allreduce_f64(ctx, em.stats, (int64_t)em.R * em.stats_stride));
     dim3 grid((unsigned)((V * em.KP + 255) / 256), (unsigned)em.R);
     PriorArgs prior;

@@ -219,8 +219,9 @@ class Engine:
         check(self.lib.scs_launch_count(self.h, ctypes.byref(n)))
         return n.value
 
-    def set_timing(self, on=True):
-        check(self.lib.scs_set_timing(self.h, 1 if on else 0))
+    def set_timing(self, on=True, every=1):
+        """CUDA-event timing of the E-step SpMM and of the M-step sums, on every `every`-th EM iteration."""
+        check(self.lib.scs_set_timing(self.h, int(every) if on else 0))
 
     def kernel_times(self, reset=False):
         out = (ctypes.c_double * 4)()
