@@ -86,7 +86,7 @@ struct EmState {
     double* partial = nullptr;  // [R][nblk][KP+2] per-block column mass, LL, dense-path cell count (fixed-order reduction)
     uint32_t* hq = nullptr;     // [R][h_stride] packed (state, 1 - weight) of a saturated posterior row, or SPARSE_DENSE
     int64_t h_stride = 0;       // N rounded up to 4 (16-byte multiples for the bulk copy)
-    int32_t* sched = nullptr;   // [R][2] row tickets / finished-CTA count of the sparse M-step, then [R] k_finalize block counts (self-resetting)
+    int32_t* sched = nullptr;   // [R][2] row tickets / finished-CTA count of the sparse M-step, then [R] k_finalize and [R] k_bayes block counts (self-resetting)
     int sparse_only = 0;        // host hint from the last poll: every restart is saturated -> launch only the sparse M-step
     double* hist = nullptr;     // [R][max_iter]
     double* ll_prev = nullptr;  // [R]

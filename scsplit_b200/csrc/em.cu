@@ -190,9 +190,9 @@ static int run_e(scs_ctx* ctx, const int32_t* done) {
     SCS_TRY(launch_spmm(ctx, 0, em.KP, em.R, em.T, 2 * V * em.KP, em.L, N * em.KP, done));
     dim3 grid((unsigned)em.nblk, (unsigned)em.R);
     SCS_DISPATCH_KP(em.KP, (k_bayes<KPc><<<grid, 1024, 0, ctx->stream>>>(N, em.K, em.L, em.W, em.lps, em.partial, em.nblk, em.hq,
-                                                                              em.h_stride, done)));
-    k_reduce_stats<<<em.R, 256, 0, ctx->stream>>>(em.KP, em.KP + 2, em.partial, em.nblk, em.stats, em.stats_stride, 2 * V * em.KP, 1, done);
-    ctx->launches += 2;
+                                                                              em.h_stride, done, em.stats + 2 * V * em.KP,
+                                                                              em.stats_stride, em.sched + 3 * em.R)));
+    ctx->launches += 1;
     SCS_CUDA(cudaGetLastError());
     return 0;
 }
@@ -309,8 +309,8 @@ int scs_em_begin(scs_ctx* ctx, int R, int K, const double* P0, int max_iter) {
     SCS_TRY(dev_alloc(ctx, &em.hq, (int64_t)R * em.h_stride));
     k_fill_u32<<<(unsigned)((R * em.h_stride + 255) / 256), 256, 0, ctx->stream>>>(em.hq, R * em.h_stride, SPARSE_DENSE);
     ctx->launches++;
-    SCS_TRY(dev_alloc(ctx, &em.sched, 3 * R));           // [R][2] sparse M-step tickets, then [R] k_finalize block counts
-    SCS_CUDA(cudaMemsetAsync(em.sched, 0, (size_t)R * 12, ctx->stream));
+    SCS_TRY(dev_alloc(ctx, &em.sched, 4 * R));   // [R][2] sparse M-step tickets, [R] k_finalize and [R] k_bayes block counts
+    SCS_CUDA(cudaMemsetAsync(em.sched, 0, (size_t)R * 16, ctx->stream));
     SCS_TRY(dev_alloc(ctx, &em.hist, (int64_t)R * max_iter));
     SCS_TRY(dev_alloc(ctx, &em.ll_prev, R));
     SCS_TRY(dev_alloc(ctx, &em.iters, R));

@@ -186,6 +186,19 @@ __device__ __forceinline__ void block_stats_store(double mass, double ll, double
     }
 }
 
+// partial[blk][NV] -> tail[0..NV): warp w takes values w, w + nwarps, ...; lanes stride over the blocks, then an xor tree.
+// L2 loads (__ldcg): the partials were written by other blocks of the same launch when this runs inside k_bayes.
+__device__ __forceinline__ void reduce_partials(int KP, int NV, const double* partial, int nblk, double* tail, int with_ll) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    for (int k = warp; k < NV; k += nwarps) {
+        double s = 0.0;
+        for (int b = lane; b < nblk; b += 32) s += __ldcg(partial + (int64_t)b * NV + k);
+#pragma unroll
+        for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0 && (k != KP || with_ll)) tail[k] = s;
+    }
+}
+
 // W[c,i] = 1 / sum_j 2^(((L_j + s_j) - L_i) - s_i)   (scSplit:181-185, j ascending, left-to-right)
 // ll_c   = log2( sum_k 2^((L_k - max_k L) + s_k) ) + max_k L   with pandas skipna  (scSplit:188)
 // partial[r][blk][0..KP) = sum over the block's cells of W[c,k] (NaN skipped, scSplit:198), [KP] = sum of ll_c,
@@ -233,11 +246,14 @@ __device__ __forceinline__ int64_t bayes_cell_lo(int64_t N, int b, int nblk) { r
 template <int KP>
 __global__ void __launch_bounds__(1024) k_bayes(int64_t N, int K, const double* __restrict__ L, double* __restrict__ W,
                                                const double* __restrict__ lps, double* __restrict__ partial, int nblk,
-                                               uint32_t* __restrict__ hq, int64_t h_stride, const int32_t* __restrict__ done) {
+                                               uint32_t* __restrict__ hq, int64_t h_stride, const int32_t* __restrict__ done,
+                                               double* __restrict__ tail /* stats + tail_off */, int64_t stats_stride,
+                                               int32_t* __restrict__ count) {
     using C = BayesCfg<KP>;
     const int r = blockIdx.y;
     if (done && done[r]) return;
     __shared__ double s_red[32 * (KP + 2)];
+    __shared__ int s_last;
     const int i = threadIdx.x & (C::GL - 1);
     const double si = i < K ? lps[(int64_t)r * KP + i] : 0.0;
     const int64_t c_lo = bayes_cell_lo(N, blockIdx.x, nblk), c_hi = bayes_cell_lo(N, blockIdx.x + 1, nblk);
@@ -274,6 +290,16 @@ __global__ void __launch_bounds__(1024) k_bayes(int64_t N, int K, const double* 
         }
     }
     block_stats_store<KP, C::GL>(mass, llsum, dense, s_red, partial + ((int64_t)r * nblk + blockIdx.x) * (KP + 2));
+    // the last block of the restart to get here folds the block partials into the statistics tail (column mass, LL,
+    // dense-row count), in the order k_reduce_stats uses; the block counter is left at zero again
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(count + r, 1) == (int)gridDim.x - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    reduce_partials(KP, KP + 2, partial + (int64_t)r * nblk * (KP + 2), nblk, tail + (int64_t)r * stats_stride, 1);
+    if (threadIdx.x == 0) count[r] = 0;
 }
 
 // column mass and packed form of an arbitrary W (step-level M-step entry): same block mapping and order as k_bayes
@@ -308,14 +334,7 @@ static __global__ void __launch_bounds__(256) k_reduce_stats(int KP, int NV, con
                                                       const int32_t* __restrict__ done) {
     const int r = blockIdx.x;
     if (done && done[r]) return;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int k = warp; k < NV; k += 8) {
-        double s = 0.0;
-        for (int b = lane; b < nblk; b += 32) s += partial[((int64_t)r * nblk + b) * NV + k];
-#pragma unroll
-        for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (lane == 0 && (k != KP || with_ll)) stats[(int64_t)r * stats_stride + tail_off + k] = s;
-    }
+    reduce_partials(KP, NV, partial + (int64_t)r * nblk * NV, nblk, stats + (int64_t)r * stats_stride + tail_off, with_ll);
 }
 
 // numpy's pairwise add.reduce for n < 128 contiguous doubles (what pandas Series.sum() runs for K values)

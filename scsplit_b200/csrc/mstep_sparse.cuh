@@ -154,7 +154,7 @@ k_mstep_sparse(int64_t nrows, int64_t N, int K, const int64_t* __restrict__ lptr
     auto load_vec = [&](const RowJob& j, int v) -> uint4 {             // raw: may hold elements outside the row
         const int a = (int)(j.lb & 3), m = a + j.n;
         uint4 c = make_uint4(nop_code, nop_code, nop_code, nop_code);
-        if (4 * v < m) c = __ldg(reinterpret_cast<const uint4*>(lcode + (j.lb - a)) + v);
+        if (4 * v < m) c = __ldcs(reinterpret_cast<const uint4*>(lcode + (j.lb - a)) + v);
         return c;
     };
     // blank the elements of vector v outside [a, m): applied when the vector is USED, so that nothing waits on the load

@@ -142,13 +142,13 @@ k_spmm_tiled(int64_t nrows, int TR, int64_t xrows, const int64_t* __restrict__ t
         // all GPW groups of the warp iterate together; a group that has finished feeds zero rows until the others end
         // this lane's index word (two entries) of the NEXT batch is always in flight: the stream of a group is contiguous,
         // so the next batch starts at `lim` whatever the unit bounds turn out to be (the stream buffer has slack at its end)
-        uint32_t word = act ? __ldg(reinterpret_cast<const uint32_t*>(tcode + e) + li) : zero_pair;
+        uint32_t word = act ? __ldcs(reinterpret_cast<const uint32_t*>(tcode + e) + li) : zero_pair;
         while (__any_sync(0xffffffffu, u < uend)) {
             const int64_t lim = min(e + BE, b2);          // never past the end of unit u+1
             const int nvalid = (u < uend) ? (int)(lim - e) : 0;
             const int ncur = (int)min((int64_t)nvalid, max((int64_t)0, b1 - e));   // entries of this batch that belong to unit u
             const uint32_t mine = (2 * li < nvalid) ? word : zero_pair;
-            if (u < uend) word = __ldg(reinterpret_cast<const uint32_t*>(tcode + lim) + li);
+            if (u < uend) word = __ldcs(reinterpret_cast<const uint32_t*>(tcode + lim) + li);
             constexpr int UW = C::GS < 4 ? C::GS : 4;
 #pragma unroll
             for (int j0 = 0; j0 < C::GS; j0 += UW) {
@@ -207,12 +207,12 @@ __global__ void __launch_bounds__(256) k_spmm_combine(int64_t nrows, int ntiles,
     for (; t + 8 <= ntiles; t += 8) {
         double2 p[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) p[u] = *reinterpret_cast<const double2*>(prow + (int64_t)(t + u) * tstride);
+        for (int u = 0; u < 8; ++u) p[u] = __ldcs(reinterpret_cast<const double2*>(prow + (int64_t)(t + u) * tstride));
 #pragma unroll
         for (int u = 0; u < 8; ++u) { acc.x += p[u].x; acc.y += p[u].y; }
     }
     for (; t < ntiles; ++t) {
-        const double2 p = *reinterpret_cast<const double2*>(prow + (int64_t)t * tstride);
+        const double2 p = __ldcs(reinterpret_cast<const double2*>(prow + (int64_t)t * tstride));
         acc.x += p.x;
         acc.y += p.y;
     }
