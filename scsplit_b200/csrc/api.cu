@@ -98,6 +98,7 @@ int scs_destroy(scs_ctx* ctx) {
     comm_destroy(ctx);
     free_stream(ctx, ctx->E);
     free_stream(ctx, ctx->M);
+    dev_free(ctx, ctx->m_order);
     free_tiled(ctx, ctx->TE);
     free_tiled(ctx, ctx->TM);
     dev_free(ctx, ctx->part);

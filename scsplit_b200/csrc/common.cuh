@@ -109,6 +109,7 @@ struct scs_ctx {
     scs::TiledStream TE, TM;   // tile-major copies for the current KP
     double* part = nullptr;    // per-(tile,row) partial sums of the tiled SpMM
     int64_t part_doubles = 0;
+    int32_t* m_order = nullptr;  // [2V] pseudo-rows of the M stream by descending length (job order of the sparse M-step; built on first use)
     int64_t* sum_alt = nullptr;  // [V] integer row sums (global after comm_init)
     int64_t* sum_ref = nullptr;  // [V]
     double* kalt = nullptr;      // [V]
@@ -157,6 +158,7 @@ int build_layout(scs_ctx* ctx, const int64_t* ref_indptr, const int32_t* ref_ind
 void free_stream(scs_ctx* ctx, Stream& s);
 void free_tiled(scs_ctx* ctx, TiledStream& t);
 int build_tiled(scs_ctx* ctx, const Stream& s, TiledStream& t, int KP, int TR, int pad, int ncta, int ngroups);
+int build_row_order(scs_ctx* ctx, const Stream& s, int32_t** order);   // rows by descending light-entry count, ties by index
 
 // em.cu
 int launch_spmm(scs_ctx* ctx, int kind /*0=E,1=M*/, int KP, int R, const double* X, int64_t x_stride, double* Y,

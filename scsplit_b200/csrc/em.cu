@@ -209,6 +209,7 @@ static int run_m(scs_ctx* ctx, const int32_t* done, int track, int check_conv) {
     if (sparse) {
         cudaEvent_t ea = nullptr, eb = nullptr;
         SCS_TRY(timing_begin(ctx, &ea, &eb));
+        if (!ctx->m_order) SCS_TRY(build_row_order(ctx, ctx->M, &ctx->m_order));
         const size_t smem = sparse_smem_bytes(em.h_stride, em.KP);
         dim3 grid((unsigned)(ctx->sm_count > 0 ? ctx->sm_count : 148), (unsigned)em.R);
         SCS_DISPATCH_KP(em.KP, {
@@ -217,7 +218,7 @@ static int run_m(scs_ctx* ctx, const int32_t* done, int track, int check_conv) {
                 SCS_CUDA(cudaFuncSetAttribute(k_mstep_sparse<KPc>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_BYTES + 1024));
                 attr_set = true;
             }
-            k_mstep_sparse<KPc><<<grid, SPARSE_THREADS, smem, ctx->stream>>>(ctx->M.nrows, N, em.K, ctx->M.lptr, ctx->M.lcode, ctx->M.hptr,
+            k_mstep_sparse<KPc><<<grid, SPARSE_THREADS, smem, ctx->stream>>>(ctx->M.nrows, N, em.K, ctx->m_order, ctx->M.lptr, ctx->M.lcode, ctx->M.hptr,
                                                                            ctx->M.hcode, ctx->M.hcnt, em.hq, em.h_stride, em.W, em.stats,
                                                                            em.stats_stride, em.sparse_only ? nullptr : gate, em.stats_stride,
                                                                            gate_thr, done, em.sched);

@@ -177,6 +177,37 @@ static int stable_sort_by_cell(scs_ctx* ctx, const uint32_t* kin, uint32_t* kout
     return 0;
 }
 
+// ---- job order of the sparse M-step: pseudo-rows by descending length (stable, so ties keep their index order)
+static __global__ void k_row_len_keys(int64_t nrows, const int64_t* __restrict__ lptr, uint32_t* __restrict__ key, int32_t* __restrict__ val) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nrows) return;
+    key[i] = 0xffffffffu - (uint32_t)min((int64_t)0xffffffffLL, lptr[i + 1] - lptr[i]);
+    val[i] = (int32_t)i;
+}
+
+int build_row_order(scs_ctx* ctx, const Stream& s, int32_t** order) {
+    const int64_t n = s.nrows;
+    uint32_t *kin = nullptr, *kout = nullptr;
+    int32_t *vin = nullptr, *vout = nullptr;
+    SCS_TRY(dev_alloc(ctx, &kin, n));
+    SCS_TRY(dev_alloc(ctx, &kout, n));
+    SCS_TRY(dev_alloc(ctx, &vin, n));
+    SCS_TRY(dev_alloc(ctx, &vout, n));
+    k_row_len_keys<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(n, s.lptr, kin, vin);
+    ctx->launches++;
+    size_t tb = 0;
+    SCS_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, kin, kout, vin, vout, n, 0, 32, ctx->stream));
+    void* tmp = nullptr;
+    SCS_CUDA(cudaMallocAsync(&tmp, tb ? tb : 1, ctx->stream));
+    cudaError_t e = cub::DeviceRadixSort::SortPairs(tmp, tb, kin, kout, vin, vout, n, 0, 32, ctx->stream);
+    cudaFreeAsync(tmp, ctx->stream);
+    dev_free(ctx, kin); dev_free(ctx, kout); dev_free(ctx, vin);
+    SCS_CUDA(e);
+    ctx->launches += 4;
+    *order = vout;
+    return 0;
+}
+
 static int inclusive_scan_into_ptr(scs_ctx* ctx, const int64_t* cnt, int64_t* ptr, int64_t n) {
     SCS_CUDA(cudaMemsetAsync(ptr, 0, sizeof(int64_t), ctx->stream));
     size_t tb = 0;

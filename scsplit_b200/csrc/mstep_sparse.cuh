@@ -89,7 +89,8 @@ __device__ __forceinline__ void dense_add(uint32_t acc_base, int K, int64_t cell
 // Which warp sums a row never changes the order inside the row, so the result is the same bits on every run.
 template <int KP>
 __global__ void __launch_bounds__(SPARSE_THREADS, 1)
-k_mstep_sparse(int64_t nrows, int64_t N, int K, const int64_t* __restrict__ lptr, const uint32_t* __restrict__ lcode,
+k_mstep_sparse(int64_t nrows, int64_t N, int K, const int32_t* __restrict__ order, const int64_t* __restrict__ lptr,
+               const uint32_t* __restrict__ lcode,
                const int64_t* __restrict__ hptr, const uint32_t* __restrict__ hcode, const int32_t* __restrict__ hcnt,
                const uint32_t* __restrict__ hq, int64_t h_stride, const double* __restrict__ W, double* __restrict__ S,
                int64_t s_stride, const double* __restrict__ gate, int64_t gate_stride, double gate_thr,
@@ -125,7 +126,10 @@ k_mstep_sparse(int64_t nrows, int64_t N, int K, const int64_t* __restrict__ lptr
     sched += 2 * r;
     const int li = lane & (SPARSE_GS - 1), g = lane / SPARSE_GS;
     constexpr int GPW = 32 / SPARSE_GS;
-    constexpr int UV = 2;
+#ifndef SCS_SPARSE_UV
+#define SCS_SPARSE_UV 2
+#endif
+    constexpr int UV = SCS_SPARSE_UV;
     const int npairs = (int)((nrows + GPW - 1) / GPW);
     const uint32_t nop_code = (uint32_t)h_stride << 1;               // code whose table word is SPARSE_NOP
     // A row (pair) is a short job (a few hundred entries), so the chain ticket -> row bounds -> first codes is software-
@@ -138,10 +142,11 @@ k_mstep_sparse(int64_t nrows, int64_t N, int K, const int64_t* __restrict__ lptr
     };
     auto draw = [&]() -> int { return lane == 0 ? atomicAdd(sched, 1) : 0; };           // raw: only lane 0 holds the ticket
     auto job_of = [&](int ticket) -> RowJob {
-        // GPW consecutive pseudo-rows per warp (consecutive rows are the same allele: similar lengths); the ref rows
-        // (second half, longer) go first
+        // `order` lists the pseudo-rows by descending length: the GPW rows of a warp are neighbours in that list (equal
+        // lengths, so the groups of a warp finish together) and the longest rows are drawn first
         RowJob j;
-        j.row = ticket < npairs ? (int64_t)(npairs - 1 - ticket) * GPW + g : nrows;
+        const int64_t idx = (int64_t)ticket * GPW + g;
+        j.row = (ticket < npairs && idx < nrows) ? (int64_t)__ldg(order + idx) : nrows;
         const bool act = j.row < nrows;
         j.lb = act ? __ldg(lptr + j.row) : 0;
         j.n = act ? (int)(__ldg(lptr + j.row + 1) - j.lb) : 0;
