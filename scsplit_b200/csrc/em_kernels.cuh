@@ -122,26 +122,7 @@ constexpr double SPARSE_TINY = 1e-40;
 // (its 1 - weight lies in [-0.5, 0.5]).
 constexpr uint32_t SPARSE_DENSE = 0x3f800000u;       // unsaturated row: take the full posterior row
 constexpr uint32_t SPARSE_NOP = 0x3f800001u;         // no entry (a lane past the end of a pseudo-row)
-template <int KP>
-__device__ __forceinline__ uint32_t sparsify_row(const double (&w)[KP], int K) {
-    int im = 0;
-    double wm = w[0];
-#pragma unroll
-    for (int k = 1; k < KP; ++k)
-        if (k < K && w[k] > wm) { wm = w[k]; im = k; }
-    // the reference's own rounding puts the winning posterior at 1 +- O(1e-13), on either side of 1; NaN rows are never sparse
-    bool ok = (wm == wm) && wm >= 0.5 && wm <= 1.5;
-#pragma unroll
-    for (int k = 0; k < KP; ++k)
-        if (k < K && k != im) ok = ok && (w[k] < SPARSE_TINY);
-    const double eps = 1.0 - wm;                      // exact (Sterbenz)
-    const float ef = (float)eps;
-    const uint32_t bits = __float_as_uint(ef);
-    ok = ok && ((double)ef == eps) && ((bits & 31u) == 0u);
-    return ok ? (bits | (uint32_t)im) : SPARSE_DENSE;
-}
-
-// The same packing decided by the GL lanes of a cell together (lane i holds W[c,i]): the row is sparse iff exactly one
+// The packing is decided by the GL lanes of a cell together (lane i holds W[c,i]): the row is sparse iff exactly one
 // live lane holds a weight in [0.5, 1.5], every other live lane is below SPARSE_TINY (NaN is neither) and the winner's
 // 1 - weight fits the float format.  Every lane of the group returns the word.
 template <int GL>

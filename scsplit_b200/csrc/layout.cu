@@ -189,21 +189,24 @@ int build_row_order(scs_ctx* ctx, const Stream& s, int32_t** order) {
     const int64_t n = s.nrows;
     uint32_t *kin = nullptr, *kout = nullptr;
     int32_t *vin = nullptr, *vout = nullptr;
-    SCS_TRY(dev_alloc(ctx, &kin, n));
-    SCS_TRY(dev_alloc(ctx, &kout, n));
-    SCS_TRY(dev_alloc(ctx, &vin, n));
-    SCS_TRY(dev_alloc(ctx, &vout, n));
-    k_row_len_keys<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(n, s.lptr, kin, vin);
-    ctx->launches++;
-    size_t tb = 0;
-    SCS_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, kin, kout, vin, vout, n, 0, 32, ctx->stream));
     void* tmp = nullptr;
-    SCS_CUDA(cudaMallocAsync(&tmp, tb ? tb : 1, ctx->stream));
-    cudaError_t e = cub::DeviceRadixSort::SortPairs(tmp, tb, kin, kout, vin, vout, n, 0, 32, ctx->stream);
-    cudaFreeAsync(tmp, ctx->stream);
+    auto body = [&]() -> int {
+        SCS_TRY(dev_alloc(ctx, &kin, n));
+        SCS_TRY(dev_alloc(ctx, &kout, n));
+        SCS_TRY(dev_alloc(ctx, &vin, n));
+        SCS_TRY(dev_alloc(ctx, &vout, n));
+        k_row_len_keys<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(n, s.lptr, kin, vin);
+        size_t tb = 0;
+        SCS_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, kin, kout, vin, vout, n, 0, 32, ctx->stream));
+        SCS_CUDA(cudaMallocAsync(&tmp, tb ? tb : 1, ctx->stream));
+        SCS_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tb, kin, kout, vin, vout, n, 0, 32, ctx->stream));
+        ctx->launches += 5;
+        return 0;
+    };
+    const int rc = body();
+    if (tmp) cudaFreeAsync(tmp, ctx->stream);
     dev_free(ctx, kin); dev_free(ctx, kout); dev_free(ctx, vin);
-    SCS_CUDA(e);
-    ctx->launches += 4;
+    if (rc) { dev_free(ctx, vout); return rc; }
     *order = vout;
     return 0;
 }

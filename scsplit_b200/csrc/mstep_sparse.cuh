@@ -1,13 +1,14 @@
 // M-step fast path for saturated posteriors (DESIGN.md "sparse M-step").
 //
-// When nearly every posterior row packs into one 32-bit word (state, 1 - weight; see sparsify_row in em_kernels.cuh) the
+// When nearly every posterior row packs into one 32-bit word (state, 1 - weight; see sparsify_group in em_kernels.cuh) the
 // M-step sums S[g, k] = sum_{entries of pseudo-row g} W[cell, k] need 4 bytes of posterior per entry instead of a KP*8-byte
-// row.  The packed words of ALL cells are staged in shared memory with TMA bulk copies (4 bytes x N), a group of 8 lanes
-// walks one pseudo-row of the SNV-major stream (2 rows per warp), and every lane owns K fp64 accumulators in shared
-// memory laid out [state][lane] -- the bank is the lane, so the data-dependent read-modify-write is conflict-free.  A
-// fixed xor-shuffle tree over the 8 lanes finishes a row.  Cells that are not saturated are gathered as full rows from
-// global memory.  The kernel runs only when the dense-path cell count published by k_reduce_stats is below the gate
-// threshold; otherwise the tiled SpMM (gated the other way) does the M-step.  Same bits on every run.
+// row.  The packed words of ALL cells are staged in shared memory with TMA bulk copies (4 bytes x N), a group of 16 lanes
+// walks one pseudo-row of the SNV-major stream (2 rows per warp, 16-byte code vectors), and every lane owns K fp64
+// accumulators in shared memory laid out [state][lane] -- the bank is the lane, so the data-dependent read-modify-write
+// is conflict-free.  A fixed reduce-scatter butterfly over the 16 lanes finishes a row.  Cells that are not saturated are
+// added as full rows from global memory.  Rows are jobs drawn from a ticket counter in descending-length order.  The
+// kernel runs only when the dense-path cell count published by k_bayes is below the gate threshold; otherwise the tiled
+// SpMM (gated the other way) does the M-step.  Same bits on every run.
 #pragma once
 #include "em_kernels.cuh"
 #include "spmm_tiled.cuh"
@@ -15,8 +16,7 @@
 namespace scs {
 
 constexpr int SPARSE_THREADS = 1024;
-constexpr int SPARSE_GS = 16;                      // lanes per pseudo-row (>= KP/2: the row's column pairs are stored by lanes 0..KP/2-1)
-static_assert(SPARSE_GS * 2 >= SCS_MAX_K, "a row group must cover all column pairs");
+constexpr int SPARSE_GS = 16;                      // lanes per pseudo-row
 
 // packed words of all cells + one SPARSE_NOP word, rounded to the 128-byte alignment of the mbarrier behind it
 __host__ __device__ inline size_t sparse_tab_bytes(int64_t h_stride) { return (((size_t)h_stride * 4 + 4) + 127) & ~(size_t)127; }
