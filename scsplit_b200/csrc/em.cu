@@ -203,14 +203,15 @@ static int run_m(scs_ctx* ctx, const int32_t* done, int track, int check_conv) {
     const int64_t V = ctx->V, N = ctx->N;
     // M-step sums: the sparse kernel when (nearly) all posterior rows are saturated, else the tiled SpMM; both are launched
     // and the dense-path cell count in the statistics tail (written by k_reduce_stats) gates which one does the work
-    const bool sparse = ctx->variant == 0 && sparse_fits(N, em.KP);
+    const int sparse_threads = ctx->variant == 0 ? sparse_threads_for(N, em.KP) : 0;
+    const bool sparse = sparse_threads > 0;
     const double* gate = sparse ? em.stats + 2 * V * em.KP + em.KP + 1 : nullptr;
     const double gate_thr = (double)std::max<int64_t>(16, N / 32);
     if (sparse) {
         cudaEvent_t ea = nullptr, eb = nullptr;
         SCS_TRY(timing_begin(ctx, &ea, &eb));
         if (!ctx->m_order) SCS_TRY(build_row_order(ctx, ctx->M, &ctx->m_order));
-        const size_t smem = sparse_smem_bytes(em.h_stride, em.KP);
+        const size_t smem = sparse_smem_bytes(em.h_stride, em.KP, sparse_threads);
         dim3 grid((unsigned)(ctx->sm_count > 0 ? ctx->sm_count : 148), (unsigned)em.R);
         SCS_DISPATCH_KP(em.KP, {
             static bool attr_set = false;
@@ -218,7 +219,7 @@ static int run_m(scs_ctx* ctx, const int32_t* done, int track, int check_conv) {
                 SCS_CUDA(cudaFuncSetAttribute(k_mstep_sparse<KPc>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_BYTES + 1024));
                 attr_set = true;
             }
-            k_mstep_sparse<KPc><<<grid, SPARSE_THREADS, smem, ctx->stream>>>(ctx->M.nrows, N, em.K, ctx->m_order, ctx->M.lptr, ctx->M.lcode, ctx->M.hptr,
+            k_mstep_sparse<KPc><<<grid, sparse_threads, smem, ctx->stream>>>(ctx->M.nrows, N, em.K, ctx->m_order, ctx->M.lptr, ctx->M.lcode, ctx->M.hptr,
                                                                            ctx->M.hcode, ctx->M.hcnt, em.hq, em.h_stride, em.W, em.stats,
                                                                            em.stats_stride, em.sparse_only ? nullptr : gate, em.stats_stride,
                                                                            gate_thr, done, em.sched);

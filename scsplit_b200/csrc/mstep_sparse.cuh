@@ -15,16 +15,22 @@
 
 namespace scs {
 
-constexpr int SPARSE_THREADS = 1024;
+constexpr int SPARSE_THREADS = 1024;                // most threads per CTA; fewer when the accumulators would not fit
 constexpr int SPARSE_GS = 16;                      // lanes per pseudo-row
 
 // packed words of all cells + one SPARSE_NOP word, rounded to the 128-byte alignment of the mbarrier behind it
 __host__ __device__ inline size_t sparse_tab_bytes(int64_t h_stride) { return (((size_t)h_stride * 4 + 4) + 127) & ~(size_t)127; }
-inline size_t sparse_smem_bytes(int64_t h_stride, int KP) {
-    const size_t acc = (size_t)SPARSE_THREADS * KP * 8;                  // [warp][state][lane] fp64
+inline size_t sparse_smem_bytes(int64_t h_stride, int KP, int threads) {
+    const size_t acc = (size_t)threads * KP * 8;                         // [warp][state][lane] fp64
     return acc + sparse_tab_bytes(h_stride) + 16;
 }
-inline bool sparse_fits(int64_t N, int KP) { return sparse_smem_bytes((N + 3) / 4 * 4, KP) <= (size_t)TILE_BYTES + 1024; }
+// threads per CTA of the sparse M-step for N cells and KP columns: as many warps as fit next to the N packed words (every
+// lane owns KP fp64 slots), at least 8 warps; 0 = the pool does not fit and the tiled SpMM keeps the M-step
+inline int sparse_threads_for(int64_t N, int KP) {
+    for (int t = SPARSE_THREADS; t >= 256; t -= 128)
+        if (sparse_smem_bytes((N + 3) / 4 * 4, KP, t) <= (size_t)TILE_BYTES + 1024) return t;
+    return 0;
+}
 
 __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {   // read-only table: free to be scheduled early
     uint32_t v;
@@ -99,7 +105,7 @@ k_mstep_sparse(int64_t nrows, int64_t N, int K, const int32_t* __restrict__ orde
     const int r = blockIdx.y;
     if (done && done[r]) return;
     if (gate && gate[(int64_t)r * gate_stride] > gate_thr) return;   // too many unsaturated cells: the tiled SpMM runs instead
-    constexpr size_t ACC_BYTES = (size_t)SPARSE_THREADS * KP * 8;
+    const size_t ACC_BYTES = (size_t)blockDim.x * KP * 8;
     unsigned char* s_tab = smem + ACC_BYTES;
     uint64_t* bar = reinterpret_cast<uint64_t*>(s_tab + sparse_tab_bytes(h_stride));
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
