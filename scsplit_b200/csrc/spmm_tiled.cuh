@@ -14,11 +14,14 @@ constexpr int TILED_THREADS = 1024;
 // padding granule of a unit in the tile-major stream (entries); 2 keeps the 32-bit words aligned
 inline int unit_pad_for(int /*KP*/) { return 2; }
 
-inline int groups_per_warp_for(int KP) {
+// lanes per row group: the next power of two >= the 16-byte chunks of a table row -- except for 9 chunks (K = 17, the
+// "16 samples + doublets" shape), where 8 lanes read the first 8 chunks (one full 128-byte wavefront) and the ninth chunk
+// of an entry is read by the lane that holds the entry's index ("side" chunk, TileCfg::SIDE)
+constexpr int tiled_group_size(int KP) {
     const int ch = KP / 2;
-    const int gs = ch <= 1 ? 1 : ch <= 2 ? 2 : ch <= 4 ? 4 : ch <= 8 ? 8 : 16;
-    return 32 / gs;
+    return ch <= 1 ? 1 : ch <= 2 ? 2 : ch <= 4 ? 4 : ch <= 9 ? 8 : 16;
 }
+inline int groups_per_warp_for(int KP) { return 32 / tiled_group_size(KP); }
 
 inline int tile_rows_for(int KP, int64_t xrows) {
     int64_t tr = TILE_BYTES / (KP * 8);
@@ -63,8 +66,9 @@ __device__ __forceinline__ double2 lds_f64x2(uint32_t addr) {
 template <int KP>
 struct TileCfg {
     static constexpr int CH = KP / 2;                                                       // 16-byte chunks per table row
-    static constexpr int GS = CH <= 1 ? 1 : CH <= 2 ? 2 : CH <= 4 ? 4 : CH <= 8 ? 8 : 16;  // lanes per row group
+    static constexpr int GS = tiled_group_size(KP);                                         // lanes per row group
     static constexpr int GPW = 32 / GS;                                                     // row groups per warp
+    static constexpr bool SIDE = CH == GS + 1;                                              // one chunk beyond the group
 };
 
 // grid = (CTAs, R).  CTA j runs its segments of the static work plan (TiledStream::seg_ptr / seg_tile / gb).
@@ -139,6 +143,7 @@ k_spmm_tiled(int64_t nrows, int TR, int64_t xrows, const int64_t* __restrict__ t
         int64_t b3 = (u + 3 <= uend) ? __ldg(tptr + u + 3) : eend;
         double2 c0 = make_double2(0.0, 0.0), c1 = make_double2(0.0, 0.0);   // current unit (even / odd entries)
         double2 n0 = make_double2(0.0, 0.0), n1 = make_double2(0.0, 0.0);   // next unit
+        double2 sc = make_double2(0.0, 0.0), sn = make_double2(0.0, 0.0);   // side chunk of this lane's own entries (SIDE)
         // all GPW groups of the warp iterate together; a group that has finished feeds zero rows until the others end
         // this lane's index word (two entries) of the NEXT batch is always in flight: the stream of a group is contiguous,
         // so the next batch starts at `lim` whatever the unit bounds turn out to be (the stream buffer has slack at its end)
@@ -149,7 +154,7 @@ k_spmm_tiled(int64_t nrows, int TR, int64_t xrows, const int64_t* __restrict__ t
             const int ncur = (int)min((int64_t)nvalid, max((int64_t)0, b1 - e));   // entries of this batch that belong to unit u
             const uint32_t mine = (2 * li < nvalid) ? word : zero_pair;
             if (u < uend) word = __ldcs(reinterpret_cast<const uint32_t*>(tcode + lim) + li);
-            constexpr int UW = C::GS < 4 ? C::GS : 4;
+            constexpr int UW = C::GS < 4 ? C::GS : C::SIDE ? 2 : 4;   // (the side variant has fewer registers to spare)
 #pragma unroll
             for (int j0 = 0; j0 < C::GS; j0 += UW) {
                 double2 v[2 * UW];
@@ -166,11 +171,32 @@ k_spmm_tiled(int64_t nrows, int TR, int64_t xrows, const int64_t* __restrict__ t
                     if (p0 + 1 < ncur) { c1.x += v[2 * jj + 1].x; c1.y += v[2 * jj + 1].y; } else { n1.x += v[2 * jj + 1].x; n1.y += v[2 * jj + 1].y; }
                 }
             }
+            if constexpr (C::SIDE) {
+                // chunk GS of the two entries whose indices this lane holds: 8 different rows per quarter-warp (a few
+                // wavefronts per 32 entries instead of one nearly empty wavefront per entry)
+                const uint32_t side_base = smem_u32(smem) + (uint32_t)C::GS * 16u;
+                const double2 s0 = lds_f64x2(side_base + (mine & 0xffffu) * (KP * 8));
+                const double2 s1 = lds_f64x2(side_base + (mine >> 16) * (KP * 8));
+                if (2 * li < ncur) { sc.x += s0.x; sc.y += s0.y; } else { sn.x += s0.x; sn.y += s0.y; }
+                if (2 * li + 1 < ncur) { sc.x += s1.x; sc.y += s1.y; } else { sn.x += s1.x; sn.y += s1.y; }
+            }
             e = (u < uend) ? lim : e;
             // flush every unit the stream has passed (an empty unit is passed immediately and stores zeros)
             while (u < uend && e >= b1) {
                 if (li < C::CH)
                     *reinterpret_cast<double2*>(part + u * KP + 2 * li) = make_double2(c0.x + c1.x, c0.y + c1.y);
+                if constexpr (C::SIDE) {                  // the side chunk's sum is spread over the lanes of the group
+                    const uint32_t gmask = ((1u << C::GS) - 1u) << (g * C::GS);
+                    double2 s = sc;
+#pragma unroll
+                    for (int o = C::GS / 2; o; o >>= 1) {
+                        s.x += __shfl_xor_sync(gmask, s.x, o);
+                        s.y += __shfl_xor_sync(gmask, s.y, o);
+                    }
+                    if (li == 0) *reinterpret_cast<double2*>(part + u * KP + 2 * C::GS) = s;
+                    sc = sn;
+                    sn = make_double2(0.0, 0.0);
+                }
                 c0 = n0; c1 = n1;
                 n0 = make_double2(0.0, 0.0); n1 = make_double2(0.0, 0.0);
                 ++u;
