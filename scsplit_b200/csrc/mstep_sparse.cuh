@@ -188,7 +188,12 @@ k_mstep_sparse(int64_t nrows, int64_t N, int K, const int32_t* __restrict__ orde
         const int raw_after = draw();                       // ticket of the row after next (in flight during this row)
         const RowJob job_nxt = job_of(t_nxt);               // bounds of the next row (in flight during this row)
         const int a = (int)(job.lb & 3), m = a + job.n, nv = (m + 3) >> 2;
-        bool any_dense = false;
+        // unsaturated cells met by this lane: bit (EB * steps_back + j) for element j of a step (EB = 4 * UV bits per step,
+        // newest step in the low bits); `lost` collects what a row longer than 64 / EB steps per lane shifts out
+        constexpr int EB = 4 * UV;
+        uint64_t dmask = 0;
+        uint32_t lost = 0;
+        int steps = 0;
         for (int v = li; v < nv; v += UV * SPARSE_GS) {
 #pragma unroll
             for (int j = 0; j < UV; ++j) nxt[j] = load_vec(job, v + (UV + j) * SPARSE_GS);
@@ -202,11 +207,15 @@ k_mstep_sparse(int64_t nrows, int64_t N, int K, const int32_t* __restrict__ orde
                 q[4 * j + 2] = lds_u32(tab + ((cur[j].z & ~1u) << 1));
                 q[4 * j + 3] = lds_u32(tab + ((cur[j].w & ~1u) << 1));
             }
+            uint32_t m8 = 0;
 #pragma unroll
             for (int j = 0; j < 4 * UV; ++j) {
-                any_dense |= (q[j] == SPARSE_DENSE);
+                m8 |= (q[j] == SPARSE_DENSE) ? (1u << j) : 0u;
                 sparse_rmw(acc_base, q[j], 1.0);
             }
+            lost |= (uint32_t)(dmask >> (64 - EB));
+            dmask = (dmask << EB) | m8;
+            ++steps;
 #pragma unroll
             for (int j = 0; j < UV; ++j) cur[j] = nxt[j];
         }
@@ -214,12 +223,20 @@ k_mstep_sparse(int64_t nrows, int64_t N, int K, const int32_t* __restrict__ orde
 #pragma unroll
         for (int j = 0; j < UV; ++j) cur[j] = load_vec(job_nxt, li + j * SPARSE_GS);
         const uint32_t* code = lcode + job.lb;
-        if (any_dense) {                                               // rare: walk this lane's own elements again
+        if (lost) {                                                    // very long row: walk this lane's own elements again
             for (int v = li; v < nv; v += SPARSE_GS)
                 for (int k = max(4 * v, a); k < min(4 * v + 4, m); ++k) {
                     const uint32_t c = __ldg(code + (k - a)) >> 1;
                     if (lds_u32(tab + c * 4u) == SPARSE_DENSE) dense_add<KP>(acc_base, K, (int64_t)c, W, 1.0);
                 }
+        } else {
+            while (dmask) {                                            // rare: exactly the flagged elements, full rows
+                const int b = __ffsll((long long)dmask) - 1;
+                dmask &= dmask - 1;
+                const int s_idx = steps - 1 - b / EB, j = b % EB;
+                const int k = 4 * (li + (s_idx * UV + (j >> 2)) * SPARSE_GS) + (j & 3);
+                dense_add<KP>(acc_base, K, (int64_t)(__ldg(code + (k - a)) >> 1), W, 1.0);
+            }
         }
         const bool act = job.row < nrows;
         const int64_t hb = act ? hptr[job.row] : 0, he = act ? hptr[job.row + 1] : 0;

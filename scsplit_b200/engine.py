@@ -173,7 +173,8 @@ class Engine:
         out = np.empty(2 * self.V * KP + KP + 2, dtype=np.float64)
         check(self.lib.scs_em_get(self.h, int(restart), SCS_STATS, _ptr(out)))
         n = 2 * self.V * KP
-        return dict(S=out[:n].reshape(2 * self.V, KP), colsum=out[n:n + self.K].copy(), ll=float(out[n + KP]))
+        return dict(S=out[:n].reshape(2 * self.V, KP), colsum=out[n:n + self.K].copy(), ll=float(out[n + KP]),
+                    dense_cells=float(out[n + KP + 1]))   # posterior rows that did not pack (sparse M-step gate)
 
     def em_end(self):
         check(self.lib.scs_em_end(self.h))

@@ -502,3 +502,31 @@ def test_device_exp2_matches_numpy(E):
     assert np.max(np.abs(y[normal] - want[normal]) / ulp) <= 2.0
     sub = fin & (want < 2.0 ** -1022)                                                       # denormals and exact zeros
     assert np.max(np.abs(y[sub] - want[sub])) <= 2.0 ** -1074
+
+
+def test_sparse_mstep_long_rows_with_soft_cells(E):
+    """Pseudo-rows far longer than the sparse M-step's per-lane replay mask covers (few SNVs seen in most of 6000 cells), with
+    2 % unsaturated cells: the flagged-element replay and its whole-row fallback against the tiled SpMM and the oracle."""
+    from oracle import em_oracle as O
+    from scsplit_b200 import synth
+    from scsplit_b200._lib import SCS_P, SCS_W
+    V, N, K = 40, 6000, 5
+    pool = synth.make_pool(V, N, 3, 0.0, 1.5, seed=77)                 # lam = 1.5: ~78 % of the cells per SNV
+    rng = np.random.default_rng(5)
+    W = np.full((N, K), 1e-200)
+    W[np.arange(N), rng.integers(0, K, N)] = 1.0 + (rng.random(N) - 0.5) * 2e-13
+    soft = rng.choice(N, N // 50, replace=False)
+    W[soft] = rng.dirichlet(np.ones(K), soft.size)
+    res = {}
+    for variant in (0, 2):
+        with E(pool.ref, pool.alt) as eng:
+            eng.set_variant(variant)
+            eng.em_begin(np.full((V, K), 0.5))
+            eng.set(SCS_W, W)
+            eng.mstep()
+            res[variant] = (eng.get(SCS_P), eng.stats())
+    assert res[0][1]["dense_cells"] == soft.size
+    P_o, _ = O.mstep(pool.ref, pool.alt, W, O.kalt(pool.ref, pool.alt))
+    assert_close(res[0][0], P_o, RTOL, "sparse P long rows")
+    assert_close(res[2][0], P_o, RTOL, "tiled P long rows")
+    assert np.allclose(res[0][1]["S"], res[2][1]["S"], rtol=1e-12, atol=1e-30)
