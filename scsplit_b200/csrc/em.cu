@@ -206,6 +206,8 @@ static int run_m(scs_ctx* ctx, const int32_t* done, int track, int check_conv) {
     const int sparse_threads = ctx->variant == 0 ? sparse_threads_for(N, em.KP) : 0;
     const bool sparse = sparse_threads > 0;
     const double* gate = sparse ? em.stats + 2 * V * em.KP + em.KP + 1 : nullptr;
+    // N/32: measured at config 3 (tools/soft_phase_probe.py) -- the run's second iteration still has 14 % unsaturated cells,
+    // where the sparse kernel (391 us) loses to the tiled SpMM (363 us); from 2.7 % on (third iteration) it wins
     const double gate_thr = (double)std::max<int64_t>(16, N / 32);
     if (sparse) {
         cudaEvent_t ea = nullptr, eb = nullptr;
