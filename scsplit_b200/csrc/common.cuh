@@ -109,6 +109,7 @@ struct scs_ctx {
     scs::TiledStream TE, TM;   // tile-major copies for the current KP
     double* part = nullptr;    // per-(tile,row) partial sums of the tiled SpMM
     int64_t part_doubles = 0;
+    uint32_t smem_attr_set[2] = {0, 0};  // bit KP/2: this device already has the large-shared-memory attribute of k_spmm_tiled<KP> / k_mstep_sparse<KP>
     int32_t* m_order = nullptr;  // [2V] pseudo-rows of the M stream by descending length (job order of the sparse M-step; built on first use)
     int64_t* sum_alt = nullptr;  // [V] integer row sums (global after comm_init)
     int64_t* sum_ref = nullptr;  // [V]

@@ -98,10 +98,9 @@ int launch_spmm_tiled(scs_ctx* ctx, int kind, int KP, int R, const double* X, in
     dim3 grid((unsigned)ctas, (unsigned)R);
     dim3 cgrid((unsigned)((s.nrows * (KP / 2) + 255) / 256), (unsigned)R);
     SCS_DISPATCH_KP(KP, {
-        static bool attr_set = false;
-        if (!attr_set) {
+        if (!(ctx->smem_attr_set[0] >> (KPc / 2) & 1u)) {       // per context: the attribute belongs to the device
             SCS_CUDA(cudaFuncSetAttribute(k_spmm_tiled<KPc>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_BYTES + 1024));
-            attr_set = true;
+            ctx->smem_attr_set[0] |= 1u << (KPc / 2);
         }
         k_spmm_tiled<KPc><<<grid, TILED_THREADS, smem, ctx->stream>>>(s.nrows, TR, s.xrows, t.tptr, t.tcode, t.seg_ptr, t.seg_tile, t.gb,
                                                                    X, x_stride, ctx->part, part_stride, done, gate, gate_stride, gate_thr);
@@ -216,10 +215,9 @@ static int run_m(scs_ctx* ctx, const int32_t* done, int track, int check_conv) {
         const size_t smem = sparse_smem_bytes(em.h_stride, em.KP, sparse_threads);
         dim3 grid((unsigned)(ctx->sm_count > 0 ? ctx->sm_count : 148), (unsigned)em.R);
         SCS_DISPATCH_KP(em.KP, {
-            static bool attr_set = false;
-            if (!attr_set) {
+            if (!(ctx->smem_attr_set[1] >> (KPc / 2) & 1u)) {
                 SCS_CUDA(cudaFuncSetAttribute(k_mstep_sparse<KPc>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_BYTES + 1024));
-                attr_set = true;
+                ctx->smem_attr_set[1] |= 1u << (KPc / 2);
             }
             k_mstep_sparse<KPc><<<grid, sparse_threads, smem, ctx->stream>>>(ctx->M.nrows, N, em.K, ctx->m_order, ctx->M.lptr, ctx->M.lcode, ctx->M.hptr,
                                                                            ctx->M.hcode, ctx->M.hcnt, em.hq, em.h_stride, em.W, em.stats,
