@@ -291,6 +291,27 @@ __global__ void k_plan_ctas(const int64_t* __restrict__ tptr, int64_t nunits, in
     if (j > ncta) return;
     cu[j] = plan_cut(tptr, 0, nunits, j, ncta);
 }
+// Tile segments of the CTA ranges: CTA j runs the pieces of [cu[j], cu[j+1]) between tile boundaries (a tile owns nrows
+// consecutive units).  At most ncta + ntiles pieces; the unused tail of the arrays is left as empty segments.  One thread:
+// a few hundred steps, once per table width.
+__global__ void k_plan_segments(const int64_t* __restrict__ cu, int ncta, int64_t nrows, int nseg_max, int32_t* __restrict__ seg_ptr,
+                                int32_t* __restrict__ seg_tile, int64_t* __restrict__ seg_lo, int64_t* __restrict__ seg_hi) {
+    if (blockIdx.x || threadIdx.x) return;
+    int n = 0;
+    for (int j = 0; j < ncta; ++j) {
+        seg_ptr[j] = n;
+        for (int64_t tt = cu[j] / nrows; tt * nrows < cu[j + 1]; ++tt) {
+            const int64_t lo = max(cu[j], tt * nrows), hi = min(cu[j + 1], (tt + 1) * nrows);
+            if (lo >= hi || n >= nseg_max) continue;
+            seg_tile[n] = (int32_t)tt;
+            seg_lo[n] = lo;
+            seg_hi[n] = hi;
+            ++n;
+        }
+    }
+    seg_ptr[ncta] = n;
+    for (; n < nseg_max; ++n) { seg_tile[n] = 0; seg_lo[n] = 0; seg_hi[n] = 0; }
+}
 // gb[seg][G] = first unit of row group G inside segment [lo, hi)
 __global__ void k_plan_groups(const int64_t* __restrict__ tptr, const int64_t* __restrict__ seg_lo, const int64_t* __restrict__ seg_hi,
                               int ngroups, int64_t* __restrict__ gb) {
@@ -326,57 +347,32 @@ int build_tiled(scs_ctx* ctx, const Stream& s, TiledStream& t, int KP, int TR, i
     void* tmp = nullptr;
     SCS_CUDA(cudaMallocAsync(&tmp, tb ? tb : 1, ctx->stream));
     cudaError_t e = cub::DeviceScan::InclusiveSum(tmp, tb, t.tptr + 1, t.tptr + 1, t.nunits, st);
-    int64_t total = 0;
-    cudaError_t e2 = cudaMemcpyAsync(&total, t.tptr + t.nunits, sizeof(int64_t), cudaMemcpyDeviceToHost, st);
-    cudaError_t e3 = cudaStreamSynchronize(st);
     cudaFreeAsync(tmp, ctx->stream);
-    SCS_CUDA(e); SCS_CUDA(e2); SCS_CUDA(e3);
+    SCS_CUDA(e);
     ctx->launches += 2;
-    SCS_TRY(dev_alloc(ctx, &t.tcode, total + 64));   // slack: the kernel prefetches one batch past a group's run
+    // Nothing below waits for the device: the stream buffer is sized by its upper bound (every unit is padded by fewer than
+    // `pad` entries) and the work plan is computed where the unit pointers are.
+    const int64_t total_max = s.n_light + t.nunits * (int64_t)(pad > 0 ? pad - 1 : 0);
+    SCS_TRY(dev_alloc(ctx, &t.tcode, total_max + 64));   // slack: the kernel prefetches one batch past a group's run
     k_tile_scatter<<<(unsigned)((s.nrows + 7) / 8), 256, 0, st>>>(s.nrows, t.ntiles, TR, s.lptr, s.lcode, t.tptr, d_ulo, t.tcode);
     cudaFreeAsync(d_ulo, st);
     ctx->launches++;
-    // ---- static work plan: CTA ranges (device), tile segments (host, <= ncta + ntiles of them), group cuts (device)
+    // ---- static work plan: CTA ranges, their tile segments (<= ncta + ntiles of them), group cuts
     t.ncta = ncta;
     t.ngroups = ngroups;
-    int64_t* d_cu = nullptr;
+    t.nseg = ncta + t.ntiles;                            // capacity; seg_ptr[ncta] holds the number in use
+    int64_t *d_cu = nullptr, *d_lo = nullptr, *d_hi = nullptr;
     SCS_CUDA(cudaMallocAsync((void**)&d_cu, (size_t)(ncta + 1) * 8, st));
-    k_plan_ctas<<<(ncta + 1 + 127) / 128, 128, 0, st>>>(t.tptr, t.nunits, ncta, d_cu);
-    ctx->launches++;
-    std::vector<int64_t> cu((size_t)ncta + 1);
-    SCS_CUDA(cudaMemcpyAsync(cu.data(), d_cu, cu.size() * 8, cudaMemcpyDeviceToHost, st));
-    SCS_CUDA(cudaStreamSynchronize(st));
-    cudaFreeAsync(d_cu, st);
-    std::vector<int32_t> seg_ptr((size_t)ncta + 1, 0), seg_tile;
-    std::vector<int64_t> seg_lo, seg_hi;
-    for (int j = 0; j < ncta; ++j) {
-        seg_ptr[j] = (int32_t)seg_tile.size();
-        for (int64_t tt = cu[j] / s.nrows; tt * s.nrows < cu[j + 1]; ++tt) {
-            const int64_t lo = std::max(cu[j], tt * s.nrows), hi = std::min(cu[j + 1], (tt + 1) * s.nrows);
-            if (lo >= hi) continue;
-            seg_tile.push_back((int32_t)tt);
-            seg_lo.push_back(lo);
-            seg_hi.push_back(hi);
-        }
-    }
-    seg_ptr[ncta] = (int32_t)seg_tile.size();
-    t.nseg = (int)seg_tile.size();
-    const int64_t ns = t.nseg ? t.nseg : 1;
-    int64_t *d_lo = nullptr, *d_hi = nullptr;
+    SCS_CUDA(cudaMallocAsync((void**)&d_lo, (size_t)t.nseg * 8, st));
+    SCS_CUDA(cudaMallocAsync((void**)&d_hi, (size_t)t.nseg * 8, st));
     SCS_TRY(dev_alloc(ctx, &t.seg_ptr, ncta + 1));
-    SCS_TRY(dev_alloc(ctx, &t.seg_tile, ns));
-    SCS_TRY(dev_alloc(ctx, &t.gb, ns * (ngroups + 1)));
-    SCS_CUDA(cudaMallocAsync((void**)&d_lo, (size_t)ns * 8, st));
-    SCS_CUDA(cudaMallocAsync((void**)&d_hi, (size_t)ns * 8, st));
-    SCS_CUDA(cudaMemcpyAsync(t.seg_ptr, seg_ptr.data(), seg_ptr.size() * 4, cudaMemcpyHostToDevice, st));
-    if (t.nseg) {
-        SCS_CUDA(cudaMemcpyAsync(t.seg_tile, seg_tile.data(), seg_tile.size() * 4, cudaMemcpyHostToDevice, st));
-        SCS_CUDA(cudaMemcpyAsync(d_lo, seg_lo.data(), seg_lo.size() * 8, cudaMemcpyHostToDevice, st));
-        SCS_CUDA(cudaMemcpyAsync(d_hi, seg_hi.data(), seg_hi.size() * 8, cudaMemcpyHostToDevice, st));
-        k_plan_groups<<<t.nseg, 256, 0, st>>>(t.tptr, d_lo, d_hi, ngroups, t.gb);
-        ctx->launches++;
-    }
-    SCS_CUDA(cudaStreamSynchronize(st));   // host vectors above must outlive the copies
+    SCS_TRY(dev_alloc(ctx, &t.seg_tile, t.nseg));
+    SCS_TRY(dev_alloc(ctx, &t.gb, (int64_t)t.nseg * (ngroups + 1)));
+    k_plan_ctas<<<(ncta + 1 + 127) / 128, 128, 0, st>>>(t.tptr, t.nunits, ncta, d_cu);
+    k_plan_segments<<<1, 32, 0, st>>>(d_cu, ncta, s.nrows, t.nseg, t.seg_ptr, t.seg_tile, d_lo, d_hi);
+    k_plan_groups<<<t.nseg, 256, 0, st>>>(t.tptr, d_lo, d_hi, ngroups, t.gb);
+    ctx->launches += 3;
+    cudaFreeAsync(d_cu, st);
     cudaFreeAsync(d_lo, st);
     cudaFreeAsync(d_hi, st);
     SCS_CUDA(cudaGetLastError());
