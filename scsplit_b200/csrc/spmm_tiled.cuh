@@ -230,21 +230,37 @@ __global__ void __launch_bounds__(256) k_spmm_combine(int64_t nrows, int ntiles,
     const double* prow = part + row * KP + 2 * j;
     const int64_t tstride = nrows * KP;
     int t = 0;
-    for (; t + 8 <= ntiles; t += 8) {
-        double2 p[8];
+    constexpr int CB = 8;   // (12 and 23 in flight measured no better)
+    for (; t + CB <= ntiles; t += CB) {
+        double2 p[CB];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) p[u] = __ldcs(reinterpret_cast<const double2*>(prow + (int64_t)(t + u) * tstride));
+        for (int u = 0; u < CB; ++u) p[u] = __ldcs(reinterpret_cast<const double2*>(prow + (int64_t)(t + u) * tstride));
 #pragma unroll
-        for (int u = 0; u < 8; ++u) { acc.x += p[u].x; acc.y += p[u].y; }
+        for (int u = 0; u < CB; ++u) { acc.x += p[u].x; acc.y += p[u].y; }
     }
     for (; t < ntiles; ++t) {
         const double2 p = __ldcs(reinterpret_cast<const double2*>(prow + (int64_t)t * tstride));
         acc.x += p.x;
         acc.y += p.y;
     }
-    for (int64_t h = hptr[row]; h < hptr[row + 1]; ++h) {
-        const double cnt = (double)hcnt[h];
-        const double2 x = __ldg(reinterpret_cast<const double2*>(X + (int64_t)(hcode[h] >> 1) * KP + 2 * j));
+    // count>1 entries: a few dozen per row, each an index load followed by a dependent table gather -- eight are in flight
+    // before the (ordered) adds, otherwise this short loop is the longest latency chain of the kernel
+    const int64_t hb = hptr[row], he = hptr[row + 1];
+    int64_t h = hb;
+    for (; h + 8 <= he; h += 8) {
+        double cnt[8];
+        double2 x[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            cnt[u] = (double)__ldg(hcnt + h + u);
+            x[u] = __ldg(reinterpret_cast<const double2*>(X + (int64_t)(__ldg(hcode + h + u) >> 1) * KP + 2 * j));
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { acc.x += cnt[u] * x[u].x; acc.y += cnt[u] * x[u].y; }
+    }
+    for (; h < he; ++h) {
+        const double cnt = (double)__ldg(hcnt + h);
+        const double2 x = __ldg(reinterpret_cast<const double2*>(X + (int64_t)(__ldg(hcode + h) >> 1) * KP + 2 * j));
         acc.x += cnt * x.x;
         acc.y += cnt * x.y;
     }
