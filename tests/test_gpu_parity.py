@@ -530,3 +530,27 @@ def test_sparse_mstep_long_rows_with_soft_cells(E):
     assert_close(res[0][0], P_o, RTOL, "sparse P long rows")
     assert_close(res[2][0], P_o, RTOL, "tiled P long rows")
     assert np.allclose(res[0][1]["S"], res[2][1]["S"], rtol=1e-12, atol=1e-30)
+
+
+@pytest.mark.parametrize("N", [40000, 47000, 60000])
+def test_sparse_mstep_thread_budget(N, E):
+    """Pools whose packed posteriors leave room for fewer than 1024 sparse-M-step threads (40k cells: 512; 47k: 256) or for
+    none (60k: the tiled SpMM keeps the M-step): six EM iterations against the tiled-only variant."""
+    from scsplit_b200 import synth
+    from scsplit_b200._lib import SCS_L, SCS_P
+    V, K = 1200, 9
+    pool = synth.make_pool(V, N, 8, 0.05, 0.3, seed=N)
+    lab = np.full(N, -1, dtype=np.int32)
+    for k in range(K):                                    # a few true members per state: saturates within 3 iterations
+        lab[np.flatnonzero((pool.truth == k % 8) & ~pool.is_doublet)[:40]] = k
+    out = {}
+    for variant in (0, 2):
+        with E(pool.ref, pool.alt) as eng:
+            eng.set_variant(variant)
+            eng.em_begin(eng.seed_af(lab, K))
+            eng.em_iterate(6, check_conv=False)
+            out[variant] = (eng.get(SCS_P), eng.get(SCS_L), eng.em_status()[2][0], eng.stats()["dense_cells"])
+    assert out[0][3] < N / 32, "the pool did not saturate: the sparse path was not exercised"
+    assert_close(out[0][0], out[2][0], 1e-10, "P sparse vs tiled, N=%d" % N)
+    assert_close(out[0][1], out[2][1], 1e-10, "L sparse vs tiled, N=%d" % N)
+    assert_close(out[0][2], out[2][2], 1e-10, "LL sparse vs tiled, N=%d" % N)
