@@ -109,7 +109,7 @@ struct scs_ctx {
     scs::TiledStream TE, TM;   // tile-major copies for the current KP
     double* part = nullptr;    // per-(tile,row) partial sums of the tiled SpMM
     int64_t part_doubles = 0;
-    uint32_t smem_attr_set[2] = {0, 0};  // bit KP/2: this device already has the large-shared-memory attribute of k_spmm_tiled<KP> / k_mstep_sparse<KP>
+    uint32_t smem_attr_set[3] = {0, 0, 0};  // bit KP/2: this device already has the large-shared-memory attribute of k_spmm_tiled<KP> / k_mstep_sparse<KP> / k_spmm_tiled<KP, packed>
     int32_t* m_order = nullptr;  // [2V] pseudo-rows of the M stream by descending length (job order of the sparse M-step; built on first use)
     int64_t* sum_alt = nullptr;  // [V] integer row sums (global after comm_init)
     int64_t* sum_ref = nullptr;  // [V]
@@ -158,7 +158,7 @@ int build_layout(scs_ctx* ctx, const int64_t* ref_indptr, const int32_t* ref_ind
                  const int64_t* alt_indptr, const int32_t* alt_indices, const void* alt_data, int data_bytes);
 void free_stream(scs_ctx* ctx, Stream& s);
 void free_tiled(scs_ctx* ctx, TiledStream& t);
-int build_tiled(scs_ctx* ctx, const Stream& s, TiledStream& t, int KP, int TR, int pad, int ncta, int ngroups);
+int build_tiled(scs_ctx* ctx, const Stream& s, TiledStream& t, int KP, int TR, int pad, int ncta, int ngroups, int order_gpw = 0);
 int build_row_order(scs_ctx* ctx, const Stream& s, int32_t** order);   // rows by descending light-entry count, ties by index
 
 // em.cu

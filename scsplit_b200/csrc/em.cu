@@ -85,9 +85,12 @@ int launch_spmm_tiled(scs_ctx* ctx, int kind, int KP, int R, const double* X, in
     TiledStream& t = kind == 0 ? ctx->TE : ctx->TM;
     const int TR = tile_rows_for(KP, s.xrows);
     const int ctas = ctx->sm_count > 0 ? ctx->sm_count : 148;
-    const int ngroups = (TILED_THREADS / 32) * groups_per_warp_for(KP);
+    // the E stream (one E-step per iteration for the whole run) gets the packed, build-time-ordered form where the table
+    // width has one; the M stream is gathered through the tiled kernel only while posteriors are soft and stays as it is
+    const bool packed = kind == 0 && tiled_packed_for(KP);
+    const int ngroups = (TILED_THREADS / 32) * groups_per_warp_for(KP, packed);
     if (t.KP != KP || t.TR != TR || t.ncta != ctas || t.ngroups != ngroups)
-        SCS_TRY(build_tiled(ctx, s, t, KP, TR, unit_pad_for(KP), ctas, ngroups));
+        SCS_TRY(build_tiled(ctx, s, t, KP, TR, unit_pad_for(KP), ctas, ngroups, packed ? groups_per_warp_for(KP, true) : 0));
     const int64_t part_stride = t.nunits * KP;
     if (ctx->part_doubles < part_stride * R) {
         dev_free(ctx, ctx->part);
@@ -98,12 +101,23 @@ int launch_spmm_tiled(scs_ctx* ctx, int kind, int KP, int R, const double* X, in
     dim3 grid((unsigned)ctas, (unsigned)R);
     dim3 cgrid((unsigned)((s.nrows * (KP / 2) + 255) / 256), (unsigned)R);
     SCS_DISPATCH_KP(KP, {
-        if (!(ctx->smem_attr_set[0] >> (KPc / 2) & 1u)) {       // per context: the attribute belongs to the device
-            SCS_CUDA(cudaFuncSetAttribute(k_spmm_tiled<KPc>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_BYTES + 1024));
-            ctx->smem_attr_set[0] |= 1u << (KPc / 2);
+        constexpr bool CAN_PACK = tiled_packed_for(KPc);
+        const int slot = (packed && CAN_PACK) ? 2 : 0;            // smem_attr_set[0] plain, [2] packed instance
+        if (!(ctx->smem_attr_set[slot] >> (KPc / 2) & 1u)) {      // per context: the attribute belongs to the device
+            if (packed && CAN_PACK)
+                SCS_CUDA(cudaFuncSetAttribute(k_spmm_tiled<KPc, CAN_PACK>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_BYTES + 1024));
+            else
+                SCS_CUDA(cudaFuncSetAttribute(k_spmm_tiled<KPc, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_BYTES + 1024));
+            ctx->smem_attr_set[slot] |= 1u << (KPc / 2);
         }
-        k_spmm_tiled<KPc><<<grid, TILED_THREADS, smem, ctx->stream>>>(s.nrows, TR, s.xrows, t.tptr, t.tcode, t.seg_ptr, t.seg_tile, t.gb,
-                                                                   X, x_stride, ctx->part, part_stride, done, gate, gate_stride, gate_thr);
+        if (packed && CAN_PACK)
+            k_spmm_tiled<KPc, CAN_PACK><<<grid, TILED_THREADS, smem, ctx->stream>>>(s.nrows, TR, s.xrows, t.tptr, t.tcode, t.seg_ptr, t.seg_tile,
+                                                                                 t.gb, X, x_stride, ctx->part, part_stride, done, gate,
+                                                                                 gate_stride, gate_thr);
+        else
+            k_spmm_tiled<KPc, false><<<grid, TILED_THREADS, smem, ctx->stream>>>(s.nrows, TR, s.xrows, t.tptr, t.tcode, t.seg_ptr, t.seg_tile,
+                                                                              t.gb, X, x_stride, ctx->part, part_stride, done, gate,
+                                                                              gate_stride, gate_thr);
         k_spmm_combine<KPc><<<cgrid, 256, 0, ctx->stream>>>(s.nrows, t.ntiles, ctx->part, part_stride, s.hptr, s.hcode, s.hcnt, X,
                                                           x_stride, Y, y_stride, done, gate, gate_stride, gate_thr);
     });

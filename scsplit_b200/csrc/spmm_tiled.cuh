@@ -17,11 +17,18 @@ inline int unit_pad_for(int /*KP*/) { return 2; }
 // lanes per row group: the next power of two >= the 16-byte chunks of a table row -- except for 9 chunks (K = 17, the
 // "16 samples + doublets" shape), where 8 lanes read the first 8 chunks (one full 128-byte wavefront) and the ninth chunk
 // of an entry is read by the lane that holds the entry's index ("side" chunk, TileCfg::SIDE)
-constexpr int tiled_group_size(int KP) {
+constexpr int tiled_group_size(int KP, bool packed = false) {
     const int ch = KP / 2;
+    if (packed && ch == 5) return 5;
     return ch <= 1 ? 1 : ch <= 2 ? 2 : ch <= 4 ? 4 : ch <= 9 ? 8 : 16;
 }
-inline int groups_per_warp_for(int KP) { return 32 / tiled_group_size(KP); }
+// "Packed" groups (K = 9: five 16-byte chunks per row): five lanes per group, six groups per warp, so one LDS.128 covers
+// six rows in 30 lanes.  The six rows fit four conflict-free wavefronts only if their bank groups interleave, which is the
+// case when the rows of neighbouring groups are consecutive mod 8 -- the tile-major stream of such a kernel is therefore
+// ordered at build time (layout.cu: k_order_units): the entry at position p of group g's run gets, wherever the unit has
+// one, a row with (row mod 8) == (g + p) mod 8.
+constexpr bool tiled_packed_for(int KP) { return KP / 2 == 5; }
+inline int groups_per_warp_for(int KP, bool packed = false) { return 32 / tiled_group_size(KP, packed); }
 
 inline int tile_rows_for(int KP, int64_t xrows) {
     int64_t tr = TILE_BYTES / (KP * 8);
@@ -63,10 +70,10 @@ __device__ __forceinline__ double2 lds_f64x2(uint32_t addr) {
     return v;
 }
 
-template <int KP>
+template <int KP, bool PACKED = false>
 struct TileCfg {
     static constexpr int CH = KP / 2;                                                       // 16-byte chunks per table row
-    static constexpr int GS = tiled_group_size(KP);                                         // lanes per row group
+    static constexpr int GS = tiled_group_size(KP, PACKED);                                 // lanes per row group
     static constexpr int GPW = 32 / GS;                                                     // row groups per warp
     static constexpr bool SIDE = CH == GS + 1;                                              // one chunk beyond the group
 };
@@ -79,13 +86,13 @@ struct TileCfg {
 // before the current unit's end go to `cur`, entries after it to `nxt` (predicated DADDs); when the stream passes a unit
 // end the unit is flushed and nxt becomes cur.  A batch never crosses a second unit end (it is cut there), so two
 // accumulator sets suffice.  Unit bounds are prefetched two units ahead.
-template <int KP>
+template <int KP, bool PACKED>
 __global__ void __launch_bounds__(TILED_THREADS, 1)
 k_spmm_tiled(int64_t nrows, int TR, int64_t xrows, const int64_t* __restrict__ tptr, const uint16_t* __restrict__ tcode,
              const int32_t* __restrict__ seg_ptr, const int32_t* __restrict__ seg_tile, const int64_t* __restrict__ gb,
              const double* __restrict__ X, int64_t x_stride, double* __restrict__ part, int64_t part_stride,
              const int32_t* __restrict__ done, const double* __restrict__ gate, int64_t gate_stride, double gate_thr) {
-    using C = TileCfg<KP>;
+    using C = TileCfg<KP, PACKED>;
     extern __shared__ __align__(128) unsigned char smem[];
     double* tile = reinterpret_cast<double*>(smem);                           // [(TR + 1) * KP], row TR is all zeros
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + (((size_t)(TR + 1) * KP * 8 + 127) & ~(size_t)127));
@@ -96,8 +103,11 @@ k_spmm_tiled(int64_t nrows, int TR, int64_t xrows, const int64_t* __restrict__ t
     X += (int64_t)r * x_stride;
     part += (int64_t)r * part_stride;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int li = lane & (C::GS - 1);          // lane inside its row group: owns columns 2*li, 2*li+1
-    const int g = lane / C::GS;                 // row group inside the warp
+    // lanes past the last whole group (GS = 5: lanes 30, 31) shadow the last lane of the last group -- same shared address,
+    // so no extra wavefront -- and own no units
+    const bool idle = lane >= C::GS * C::GPW;
+    const int li = idle ? C::GS - 1 : lane % C::GS;   // lane inside its row group: owns columns 2*li, 2*li+1
+    const int g = idle ? C::GPW - 1 : lane / C::GS;   // row group inside the warp
     const int ngroups = (int)(blockDim.x >> 5) * C::GPW;
     const int G = warp * C::GPW + g;
     // 32-bit shared address of this lane's 16-byte column pair inside table row 0; lanes beyond the last chunk
@@ -133,7 +143,7 @@ k_spmm_tiled(int64_t nrows, int TR, int64_t xrows, const int64_t* __restrict__ t
         }
         const int64_t* gbs = gb + (int64_t)seg * (ngroups + 1);
         int64_t u = __ldg(gbs + G);                       // current unit
-        const int64_t uend = __ldg(gbs + G + 1);
+        const int64_t uend = idle ? u : __ldg(gbs + G + 1);
         const bool act = u < uend;                        // (a group without units still takes part in the warp's shuffles)
         int64_t e = act ? __ldg(tptr + u) : 0;            // stream position (entries); even
         const int64_t eend = act ? __ldg(tptr + uend) : 0;
@@ -154,13 +164,13 @@ k_spmm_tiled(int64_t nrows, int TR, int64_t xrows, const int64_t* __restrict__ t
             const int ncur = (int)min((int64_t)nvalid, max((int64_t)0, b1 - e));   // entries of this batch that belong to unit u
             const uint32_t mine = (2 * li < nvalid) ? word : zero_pair;
             if (u < uend) word = __ldcs(reinterpret_cast<const uint32_t*>(tcode + lim) + li);
-            constexpr int UW = C::GS < 4 ? C::GS : C::SIDE ? 2 : 4;   // (the side variant has fewer registers to spare)
+            constexpr int UW = C::GS < 4 ? C::GS : C::SIDE ? 2 : C::GS % 4 ? C::GS : 4;   // divides GS (the side variant has fewer registers to spare)
 #pragma unroll
             for (int j0 = 0; j0 < C::GS; j0 += UW) {
                 double2 v[2 * UW];
 #pragma unroll
                 for (int jj = 0; jj < UW; ++jj) {         // 2*UW LDS.128 in flight per lane before the adds
-                    const uint32_t w = __shfl_sync(0xffffffffu, mine, j0 + jj, C::GS);
+                    const uint32_t w = __shfl_sync(0xffffffffu, mine, g * C::GS + j0 + jj);
                     v[2 * jj] = lds_f64x2(lane_base + (w & 0xffffu) * (KP * 8));
                     v[2 * jj + 1] = lds_f64x2(lane_base + (w >> 16) * (KP * 8));
                 }
