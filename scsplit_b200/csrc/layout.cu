@@ -361,6 +361,7 @@ __global__ void __launch_bounds__(ORDER_WARPS * 32) k_order_units(const int64_t*
     __syncwarp();
     if (n >= 2 && n <= 255) {
         uint64_t cntE = 0;                                            // byte r: entries of class r
+#pragma unroll 8
         for (int i = 0; i < n; ++i) cntE += 1ull << (8 * (in[ua + i] & 7));
         uint64_t cntS = 0, preLE = 0, preLS = 0;                      // slots by class; exclusive prefixes of the surpluses
         int le = 0, ls = 0;
@@ -375,6 +376,7 @@ __global__ void __launch_bounds__(ORDER_WARPS * 32) k_order_units(const int64_t*
             ls += max(sl - en, 0);
         }
         uint64_t run = 0;                                             // byte r: entries of class r placed so far
+#pragma unroll 4
         for (int i = 0; i < n; ++i) {
             const uint16_t v = in[ua + i];
             const int cls = v & 7, sh = 8 * cls;
