@@ -215,7 +215,7 @@ static int run_m(scs_ctx* ctx, const int32_t* done, int track, int check_conv) {
     PhaseSample sample(ctx, 1);
     const int64_t V = ctx->V, N = ctx->N;
     // M-step sums: the sparse kernel when (nearly) all posterior rows are saturated, else the tiled SpMM; both are launched
-    // and the dense-path cell count in the statistics tail (written by k_reduce_stats) gates which one does the work
+    // and the dense-path cell count in the statistics tail (written by the last block of k_bayes, or by k_reduce_stats on the step-level path) gates which one does the work
     const int sparse_threads = ctx->variant == 0 ? sparse_threads_for(N, em.KP) : 0;
     const bool sparse = sparse_threads > 0;
     const double* gate = sparse ? em.stats + 2 * V * em.KP + em.KP + 1 : nullptr;

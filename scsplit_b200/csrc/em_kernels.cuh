@@ -6,7 +6,7 @@
 //                    M-step:  rows = 2V pseudo-rows, X = W[N][KP],             Y = S[2V][KP]    (scSplit:196)
 //   k_bayes          W, per-cell LL, packed sparse posterior word, fixed-order block partials    (scSplit:181-188)
 //   k_colsum_partial the same partials for an injected W (step-level M-step entry)
-//   k_reduce_stats   block partials -> colsum[K], LL, dense-cell count                           (scSplit:188,198)
+//   k_reduce_stats   block partials -> colsum[K], LL, dense-cell count (step-level path; the EM loop does it in k_bayes)  (scSplit:188,198)
 //   k_finalize       S, k_alt -> P, log2 P, log2(1-P)                                             (scSplit:196, 176-177)
 //   update_prior     colsum -> lP_s; LL history; bitwise stop rule (last block of k_finalize)      (scSplit:198, 156-161)
 //   (k_mstep_sparse, the M-step for saturated posteriors, lives in mstep_sparse.cuh)

@@ -78,7 +78,7 @@ def unpack_stats(buf, V, K):
 
 
 def finalize_from_stats(altW, refW, colsum, k_alt):
-    """What every rank computes redundantly after the all-reduce (k_finalize / k_update_prior): scSplit:196,198."""
+    """What every rank computes redundantly after the all-reduce (k_finalize and the prior update in its last block): scSplit:196,198."""
     with np.errstate(divide="ignore", invalid="ignore"):
         P = (altW + k_alt[:, None]) / ((altW + refW) + 1)
         lPs = np.log2(colsum) - np.log2(colsum.sum())
