@@ -87,7 +87,9 @@ int launch_spmm_tiled(scs_ctx* ctx, int kind, int KP, int R, const double* X, in
     const int ctas = ctx->sm_count > 0 ? ctx->sm_count : 148;
     // the E stream (one E-step per iteration for the whole run) gets the packed, build-time-ordered form where the table
     // width has one; the M stream is gathered through the tiled kernel only while posteriors are soft and stays as it is
-    const bool packed = kind == 0 && tiled_packed_for(KP);
+    // (units much longer than the order pass handles -- deep coverage -- keep the plain form, which does not depend on the order)
+    const int64_t ntiles_est = (s.xrows + TR - 1) / TR;
+    const bool packed = kind == 0 && tiled_packed_for(KP) && s.n_light / std::max<int64_t>(1, ntiles_est * s.nrows) <= 160;
     const int ngroups = (TILED_THREADS / 32) * groups_per_warp_for(KP, packed);
     if (t.KP != KP || t.TR != TR || t.ncta != ctas || t.ngroups != ngroups)
         SCS_TRY(build_tiled(ctx, s, t, KP, TR, unit_pad_for(KP), ctas, ngroups, packed ? groups_per_warp_for(KP, true) : 0));

@@ -342,16 +342,17 @@ __global__ void k_unit_phase(const int64_t* __restrict__ tptr, const int64_t* __
 // writes the range back.  (A warp per unit spends its time in shuffles and waits: 0.25 ms at config 3 against 0.05 ms.)
 constexpr int ORDER_WARPS = 4, ORDER_CAP = 2816;     // entries a warp can stage (32 units of ~66 entries are ~2100)
 __global__ void __launch_bounds__(ORDER_WARPS * 32) k_order_units(const int64_t* __restrict__ tptr, uint16_t* __restrict__ tcode,
-                                                                 const uint8_t* __restrict__ phase, int64_t nunits) {
+                                                                 const uint8_t* __restrict__ phase, int64_t nunits, int upw) {
     __shared__ __align__(16) uint16_t s_in[ORDER_WARPS][ORDER_CAP], s_out[ORDER_WARPS][ORDER_CAP];
     const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
-    const int64_t U0 = ((int64_t)blockIdx.x * ORDER_WARPS + wl) * 32;
+    const int64_t U0 = ((int64_t)blockIdx.x * ORDER_WARPS + wl) * upw;   // upw (<= 32) units per warp: what usually fits the staging
     if (U0 >= nunits) return;
-    const int64_t Ul = min(U0 + lane, nunits - 1);                    // lanes past the last unit shadow it and do nothing
-    const int64_t e0 = tptr[U0], e1 = tptr[min(U0 + 32, nunits)];
+    const int64_t Uend = min(U0 + upw, nunits);
+    const int64_t Ul = min(U0 + lane, Uend - 1);                      // lanes past the last unit shadow it and do nothing
+    const int64_t e0 = tptr[U0], e1 = tptr[Uend];
     const int len = (int)min(e1 - e0, (int64_t)ORDER_CAP + 1);
     if (len < 2 || len > ORDER_CAP) return;                           // (over-long ranges keep their natural order)
-    const int ua = (int)(tptr[Ul] - e0), n = (U0 + lane < nunits) ? (int)(tptr[Ul + 1] - tptr[Ul]) : 0;
+    const int ua = (int)(tptr[Ul] - e0), n = (U0 + lane < Uend) ? (int)(tptr[Ul + 1] - tptr[Ul]) : 0;
     const int ph = phase[Ul];                                         // slot p of this unit wants class (ph + p) & 7
     uint16_t* in = s_in[wl];
     uint16_t* out = s_out[wl];
@@ -461,8 +462,11 @@ int build_tiled(scs_ctx* ctx, const Stream& s, TiledStream& t, int KP, int TR, i
         SCS_CUDA(cudaMemsetAsync(d_phase, 0, (size_t)t.nunits, st));
         const int64_t runs = (int64_t)t.nseg * ngroups;
         k_unit_phase<<<(unsigned)((runs + 255) / 256), 256, 0, st>>>(t.tptr, t.gb, ngroups, order_gpw, t.nseg, d_phase);
-        k_order_units<<<(unsigned)((t.nunits + 32 * ORDER_WARPS - 1) / (32 * ORDER_WARPS)), ORDER_WARPS * 32, 0, st>>>(t.tptr, t.tcode, d_phase,
-                                                                                                                     t.nunits);
+        // units per warp: two thirds of the staging buffer at the average (padded) unit length, so that ordinary ranges fit
+        const int64_t avg = std::max<int64_t>(2, (s.n_light + t.nunits) / std::max<int64_t>(t.nunits, 1));
+        const int upw = (int)std::min<int64_t>(32, std::max<int64_t>(1, (int64_t)ORDER_CAP * 2 / 3 / avg));
+        const int64_t owarps = (t.nunits + upw - 1) / upw;
+        k_order_units<<<(unsigned)((owarps + ORDER_WARPS - 1) / ORDER_WARPS), ORDER_WARPS * 32, 0, st>>>(t.tptr, t.tcode, d_phase, t.nunits, upw);
         cudaFreeAsync(d_phase, st);
         ctx->launches += 2;
     }

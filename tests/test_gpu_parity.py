@@ -554,3 +554,27 @@ def test_sparse_mstep_thread_budget(N, E):
     assert_close(out[0][0], out[2][0], 1e-10, "P sparse vs tiled, N=%d" % N)
     assert_close(out[0][1], out[2][1], 1e-10, "L sparse vs tiled, N=%d" % N)
     assert_close(out[0][2], out[2][2], 1e-10, "LL sparse vs tiled, N=%d" % N)
+
+
+@pytest.mark.parametrize("V,lam", [(6000, 0.1), (3000, 0.5), (20000, 0.01)])
+def test_estep_k9_unit_lengths(V, lam, E):
+    """K = 9 E-step across unit lengths: ~120 entries per (cell, tile) unit (packed groups, fewer units per order-pass warp),
+    ~470 (too long for the order pass: the plain 8-lane form is chosen) and ~3 (mostly padding); three iterations vs the oracle."""
+    from oracle import em_oracle as O
+    from scsplit_b200 import synth
+    from scsplit_b200._lib import SCS_L, SCS_P, SCS_W
+    N, K = 384, 9
+    pool = synth.make_pool(V, N, 8, 0.05, lam, seed=V)
+    rng = np.random.default_rng(V)
+    lab = np.full(N, -1, dtype=np.int32)
+    pick = rng.choice(N, 3 * K, replace=False)
+    lab[pick] = np.arange(3 * K) % K
+    with E(pool.ref, pool.alt) as eng:
+        k_alt = eng.kalt()
+        P0 = eng.seed_af(lab, K)
+        eng.em_begin(P0)
+        eng.em_iterate(3, check_conv=False)
+        want = O.run_em(pool.ref, pool.alt, P0, k_alt, fixed_iters=3)
+        assert_close(eng.get(SCS_L), want["L"], RTOL, "L V=%d" % V)
+        assert_close(eng.get(SCS_W), want["W"], 1e-7, "W V=%d" % V)
+        assert_close(eng.get(SCS_P), want["P"], RTOL, "P V=%d" % V)
