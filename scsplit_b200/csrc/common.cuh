@@ -74,6 +74,20 @@ struct TiledStream {
 
 struct NcclApi;  // dlopen'ed function table (comm.cu)
 
+// Which kernel does a restart's M-step sums: the sparse kernel (saturated posteriors) or the tiled SpMM.  The decision is a
+// function of the restart's own history only -- `sat[r]` latches once the restart's dense-row count has fallen to the
+// saturation threshold, `dense` is the count of the current iteration -- so a restart takes the same path (hence gives
+// the same bits) whatever else is batched with it.  dense == nullptr: no gating (the kernel always runs).
+struct Gate {
+    const double* dense = nullptr;   // [r * stride]: posterior rows of restart r that do not pack into a sparse word
+    int64_t stride = 0;
+    double thr = 0.0;
+    const int32_t* sat = nullptr;    // [R] latched "saturated" flags (k_bayes)
+};
+__device__ __forceinline__ bool gate_takes_sparse(const Gate& g, int r) {
+    return (g.sat && g.sat[r]) || g.dense[(int64_t)r * g.stride] <= g.thr;
+}
+
 struct EmState {
     int R = 0, K = 0, KP = 0, max_iter = 0;
     int64_t stats_stride = 0;   // doubles per restart in `stats`
@@ -84,6 +98,7 @@ struct EmState {
     double* stats = nullptr;    // [R][2V*KP + KP + 2]: S (alt/ref posterior-weighted sums), colsum[KP], LL, pad
     double* lps = nullptr;      // [R][KP]
     double* partial = nullptr;  // [R][nblk][KP+2] per-block column mass, LL, dense-path cell count (fixed-order reduction)
+    int32_t* sat = nullptr;     // [R] latched: the restart's dense-row count has been at or below the saturation threshold
     uint32_t* hq = nullptr;     // [R][h_stride] packed (state, 1 - weight) of a saturated posterior row, or SPARSE_DENSE
     int64_t h_stride = 0;       // N rounded up to 4 (16-byte multiples for the bulk copy)
     int32_t* sched = nullptr;   // [R][2] row tickets / finished-CTA count of the sparse M-step, then [R] k_finalize and [R] k_bayes block counts (self-resetting)
@@ -153,6 +168,34 @@ void dev_free(scs_ctx* ctx, T*& p) {
 
 inline int round_even(int k) { return (k + 1) & ~1; }
 
+// Stream-ordered temporaries of one build step: everything allocated through it goes back to the pool when the scope
+// ends, on every path out (the early error returns included).
+struct Scratch {
+    cudaStream_t st;
+    std::vector<void*> ptrs;
+    explicit Scratch(cudaStream_t s) : st(s) {}
+    Scratch(const Scratch&) = delete;
+    Scratch& operator=(const Scratch&) = delete;
+    template <typename T>
+    int get(T** p, int64_t n) {
+        *p = nullptr;
+        void* q = nullptr;
+        SCS_CUDA(cudaMallocAsync(&q, (size_t)(n > 0 ? n : 1) * sizeof(T), st));
+        ptrs.push_back(q);
+        *p = (T*)q;
+        return 0;
+    }
+    int get_bytes(void** p, size_t bytes) {
+        *p = nullptr;
+        SCS_CUDA(cudaMallocAsync(p, bytes ? bytes : 1, st));
+        ptrs.push_back(*p);
+        return 0;
+    }
+    ~Scratch() {
+        for (void* q : ptrs) cudaFreeAsync(q, st);
+    }
+};
+
 // layout.cu
 int build_layout(scs_ctx* ctx, const int64_t* ref_indptr, const int32_t* ref_indices, const void* ref_data,
                  const int64_t* alt_indptr, const int32_t* alt_indices, const void* alt_data, int data_bytes);
@@ -163,7 +206,7 @@ int build_row_order(scs_ctx* ctx, const Stream& s, int32_t** order);   // rows b
 
 // em.cu
 int launch_spmm(scs_ctx* ctx, int kind /*0=E,1=M*/, int KP, int R, const double* X, int64_t x_stride, double* Y,
-                int64_t y_stride, const int32_t* done, const double* gate = nullptr, int64_t gate_stride = 0, double gate_thr = 0.0);
+                int64_t y_stride, const int32_t* done, Gate gate = Gate());
 int em_free(scs_ctx* ctx);
 // host [rows][K] <-> device [rows][KP] through a staging buffer and a (un)pitch kernel (strided 2-D copies of small rows are slow)
 int upload_pitched(scs_ctx* ctx, double* dst_dev, const double* host, int64_t rows, int K, int KP);

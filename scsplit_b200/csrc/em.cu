@@ -57,14 +57,14 @@ static int timing_end(scs_ctx* ctx, int kind, cudaEvent_t a, cudaEvent_t b) {
 }
 
 int launch_spmm(scs_ctx* ctx, int kind, int KP, int R, const double* X, int64_t x_stride, double* Y, int64_t y_stride,
-                const int32_t* done, const double* gate, int64_t gate_stride, double gate_thr) {
+                const int32_t* done, Gate gate) {
     const Stream& s = kind == 0 ? ctx->E : ctx->M;
     cudaEvent_t ea, eb;
     SCS_TRY(timing_begin(ctx, &ea, &eb));
     int variant = ctx->variant;
     if (variant == 0) variant = tiled_supported(ctx, kind, KP) ? 2 : 1;
     if (variant == 2) {
-        SCS_TRY(launch_spmm_tiled(ctx, kind, KP, R, X, x_stride, Y, y_stride, done, gate, gate_stride, gate_thr));
+        SCS_TRY(launch_spmm_tiled(ctx, kind, KP, R, X, x_stride, Y, y_stride, done, gate));
     } else {
         const int WPB = 8;
         dim3 grid((unsigned)((s.nrows + WPB - 1) / WPB), (unsigned)R);
@@ -80,7 +80,7 @@ int launch_spmm(scs_ctx* ctx, int kind, int KP, int R, const double* X, int64_t 
 bool tiled_supported(scs_ctx*, int, int KP) { return KP >= 2 && KP <= 32 && (KP % 2) == 0; }
 
 int launch_spmm_tiled(scs_ctx* ctx, int kind, int KP, int R, const double* X, int64_t x_stride, double* Y, int64_t y_stride,
-                      const int32_t* done, const double* gate, int64_t gate_stride, double gate_thr) {
+                      const int32_t* done, Gate gate) {
     const Stream& s = kind == 0 ? ctx->E : ctx->M;
     TiledStream& t = kind == 0 ? ctx->TE : ctx->TM;
     const int TR = tile_rows_for(KP, s.xrows);
@@ -114,14 +114,12 @@ int launch_spmm_tiled(scs_ctx* ctx, int kind, int KP, int R, const double* X, in
         }
         if (packed && CAN_PACK)
             k_spmm_tiled<KPc, CAN_PACK><<<grid, TILED_THREADS, smem, ctx->stream>>>(s.nrows, TR, s.xrows, t.tptr, t.tcode, t.seg_ptr, t.seg_tile,
-                                                                                 t.gb, X, x_stride, ctx->part, part_stride, done, gate,
-                                                                                 gate_stride, gate_thr);
+                                                                                 t.gb, X, x_stride, ctx->part, part_stride, done, gate);
         else
             k_spmm_tiled<KPc, false><<<grid, TILED_THREADS, smem, ctx->stream>>>(s.nrows, TR, s.xrows, t.tptr, t.tcode, t.seg_ptr, t.seg_tile,
-                                                                              t.gb, X, x_stride, ctx->part, part_stride, done, gate,
-                                                                              gate_stride, gate_thr);
+                                                                              t.gb, X, x_stride, ctx->part, part_stride, done, gate);
         k_spmm_combine<KPc><<<cgrid, 256, 0, ctx->stream>>>(s.nrows, t.ntiles, ctx->part, part_stride, s.hptr, s.hcode, s.hcnt, X,
-                                                          x_stride, Y, y_stride, done, gate, gate_stride, gate_thr);
+                                                          x_stride, Y, y_stride, done, gate);
     });
     ctx->launches += 2;
     return 0;
@@ -130,7 +128,7 @@ int launch_spmm_tiled(scs_ctx* ctx, int kind, int KP, int R, const double* X, in
 int em_free(scs_ctx* ctx) {
     EmState& em = ctx->em;
     dev_free(ctx, em.T); dev_free(ctx, em.P); dev_free(ctx, em.L); dev_free(ctx, em.W); dev_free(ctx, em.stats); dev_free(ctx, em.lps);
-    dev_free(ctx, em.hq); dev_free(ctx, em.sched);
+    dev_free(ctx, em.hq); dev_free(ctx, em.sched); dev_free(ctx, em.sat);
     dev_free(ctx, em.partial); dev_free(ctx, em.hist); dev_free(ctx, em.ll_prev); dev_free(ctx, em.iters); dev_free(ctx, em.done);
     em = EmState();
     return 0;
@@ -206,7 +204,8 @@ static int run_e(scs_ctx* ctx, const int32_t* done) {
     dim3 grid((unsigned)em.nblk, (unsigned)em.R);
     SCS_DISPATCH_KP(em.KP, (k_bayes<KPc><<<grid, 1024, 0, ctx->stream>>>(N, em.K, em.L, em.W, em.lps, em.partial, em.nblk, em.hq,
                                                                               em.h_stride, done, em.stats + 2 * V * em.KP,
-                                                                              em.stats_stride, em.sched + 3 * em.R)));
+                                                                              em.stats_stride, em.sched + 3 * em.R, em.sat,
+                                                                              (double)std::max<int64_t>(4, N / 128))));
     ctx->launches += 1;
     SCS_CUDA(cudaGetLastError());
     return 0;
@@ -220,10 +219,15 @@ static int run_m(scs_ctx* ctx, const int32_t* done, int track, int check_conv) {
     // and the dense-path cell count in the statistics tail (written by the last block of k_bayes, or by k_reduce_stats on the step-level path) gates which one does the work
     const int sparse_threads = ctx->variant == 0 ? sparse_threads_for(N, em.KP) : 0;
     const bool sparse = sparse_threads > 0;
-    const double* gate = sparse ? em.stats + 2 * V * em.KP + em.KP + 1 : nullptr;
+    Gate gate;
     // N/32: measured at config 3 (tools/soft_phase_probe.py) -- the run's second iteration still has 14 % unsaturated cells,
     // where the sparse kernel (391 us) loses to the tiled SpMM (363 us); from 2.7 % on (third iteration) it wins
-    const double gate_thr = (double)std::max<int64_t>(16, N / 32);
+    if (sparse) {
+        gate.dense = em.stats + 2 * V * em.KP + em.KP + 1;
+        gate.stride = em.stats_stride;
+        gate.thr = (double)std::max<int64_t>(16, N / 32);
+        gate.sat = em.sat;
+    }
     if (sparse) {
         cudaEvent_t ea = nullptr, eb = nullptr;
         SCS_TRY(timing_begin(ctx, &ea, &eb));
@@ -237,16 +241,15 @@ static int run_m(scs_ctx* ctx, const int32_t* done, int track, int check_conv) {
             }
             k_mstep_sparse<KPc><<<grid, sparse_threads, smem, ctx->stream>>>(ctx->M.nrows, N, em.K, ctx->m_order, ctx->M.lptr, ctx->M.lcode, ctx->M.hptr,
                                                                            ctx->M.hcode, ctx->M.hcnt, em.hq, em.h_stride, em.W, em.stats,
-                                                                           em.stats_stride, em.sparse_only ? nullptr : gate, em.stats_stride,
-                                                                           gate_thr, done, em.sched);
+                                                                           em.stats_stride, gate, done, em.sched);
         });
         ctx->launches++;
         SCS_TRY(timing_end(ctx, 2, ea, eb));
     }
-    // (the sparse kernel is correct for ANY number of unsaturated cells, only slower; once a poll has seen every restart
-    // saturated the tiled pair is not launched at all until a later poll says otherwise)
+    // (the sparse kernel is correct for ANY number of unsaturated cells, only slower; once a poll has seen the latch of every
+    // live restart set, the tiled pair -- which those restarts can no longer take -- is not launched at all)
     if (!(sparse && em.sparse_only))
-        SCS_TRY(launch_spmm(ctx, 1, em.KP, em.R, em.W, N * em.KP, em.stats, em.stats_stride, done, gate, em.stats_stride, gate_thr));
+        SCS_TRY(launch_spmm(ctx, 1, em.KP, em.R, em.W, N * em.KP, em.stats, em.stats_stride, done, gate));
     if (ctx->world > 1) SCS_TRY(comm_allreduce_f64(ctx, em.stats, (int64_t)em.R * em.stats_stride));
     dim3 grid((unsigned)((V * em.KP + 255) / 256), (unsigned)em.R);
     PriorArgs prior;
@@ -327,6 +330,8 @@ int scs_em_begin(scs_ctx* ctx, int R, int K, const double* P0, int max_iter) {
     SCS_TRY(dev_alloc(ctx, &em.hq, (int64_t)R * em.h_stride));
     k_fill_u32<<<(unsigned)((R * em.h_stride + 255) / 256), 256, 0, ctx->stream>>>(em.hq, R * em.h_stride, SPARSE_DENSE);
     ctx->launches++;
+    SCS_TRY(dev_alloc(ctx, &em.sat, R));
+    SCS_CUDA(cudaMemsetAsync(em.sat, 0, (size_t)R * 4, ctx->stream));
     SCS_TRY(dev_alloc(ctx, &em.sched, 4 * R));   // [R][2] sparse M-step tickets, [R] k_finalize and [R] k_bayes block counts
     SCS_CUDA(cudaMemsetAsync(em.sched, 0, (size_t)R * 16, ctx->stream));
     SCS_TRY(dev_alloc(ctx, &em.hist, (int64_t)R * max_iter));
@@ -382,10 +387,8 @@ int scs_em_iterate(scs_ctx* ctx, int n_iter, int check_conv) {
     EmState& em = ctx->em;
     const int32_t* done = check_conv ? em.done : nullptr;
     std::vector<int32_t> h_done((size_t)em.R);
-    std::vector<double> h_dense((size_t)em.R);
+    std::vector<int32_t> h_sat((size_t)em.R);
     const int POLL = 8;   // iterations between host polls of the device-side convergence flags and saturation counts
-    const double* d_dense = em.stats + 2 * ctx->V * em.KP + em.KP + 1;
-    const double dense_thr = (double)std::max<int64_t>(4, ctx->N / 128);
     if (!ctx->ev_iter[0]) { SCS_CUDA(cudaEventCreate(&ctx->ev_iter[0])); SCS_CUDA(cudaEventCreate(&ctx->ev_iter[1])); }
     SCS_CUDA(cudaEventRecord(ctx->ev_iter[0], ctx->stream));
     for (int i = 0; i < n_iter; ++i) {
@@ -393,13 +396,12 @@ int scs_em_iterate(scs_ctx* ctx, int n_iter, int check_conv) {
         SCS_TRY(run_m(ctx, done, 1, check_conv));
         if ((i + 1) % POLL == 0 || (check_conv && i + 1 == n_iter)) {
             SCS_CUDA(cudaMemcpyAsync(h_done.data(), em.done, (size_t)em.R * 4, cudaMemcpyDeviceToHost, ctx->stream));
-            SCS_CUDA(cudaMemcpy2DAsync(h_dense.data(), 8, d_dense, (size_t)em.stats_stride * 8, 8, (size_t)em.R, cudaMemcpyDeviceToHost,
-                                       ctx->stream));
+            SCS_CUDA(cudaMemcpyAsync(h_sat.data(), em.sat, (size_t)em.R * 4, cudaMemcpyDeviceToHost, ctx->stream));
             SCS_CUDA(cudaStreamSynchronize(ctx->stream));
             bool all = true, saturated = true;
             for (int r = 0; r < em.R; ++r) {
                 all = all && h_done[r];
-                if (!(check_conv && h_done[r])) saturated = saturated && (h_dense[r] <= dense_thr);
+                if (!(check_conv && h_done[r])) saturated = saturated && h_sat[r];
             }
             em.sparse_only = saturated ? 1 : 0;
             if (check_conv && all) break;

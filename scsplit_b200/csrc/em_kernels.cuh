@@ -229,7 +229,7 @@ __global__ void __launch_bounds__(1024) k_bayes(int64_t N, int K, const double* 
                                                const double* __restrict__ lps, double* __restrict__ partial, int nblk,
                                                uint32_t* __restrict__ hq, int64_t h_stride, const int32_t* __restrict__ done,
                                                double* __restrict__ tail /* stats + tail_off */, int64_t stats_stride,
-                                               int32_t* __restrict__ count) {
+                                               int32_t* __restrict__ count, int32_t* __restrict__ sat, double sat_thr) {
     using C = BayesCfg<KP>;
     const int r = blockIdx.y;
     if (done && done[r]) return;
@@ -280,7 +280,13 @@ __global__ void __launch_bounds__(1024) k_bayes(int64_t N, int K, const double* 
     if (!s_last) return;
     __threadfence();
     reduce_partials(KP, KP + 2, partial + (int64_t)r * nblk * (KP + 2), nblk, tail + (int64_t)r * stats_stride, 1);
-    if (threadIdx.x == 0) count[r] = 0;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        count[r] = 0;
+        // latch: from the first iteration whose dense-row count is at or below the saturation threshold the sparse M-step
+        // owns this restart for the rest of the run (Gate, common.cuh)
+        if (sat && tail[(int64_t)r * stats_stride + KP + 1] <= sat_thr) sat[r] = 1;
+    }
 }
 
 // column mass and packed form of an arbitrary W (step-level M-step entry): same block mapping and order as k_bayes

@@ -292,25 +292,37 @@ __global__ void k_plan_ctas(const int64_t* __restrict__ tptr, int64_t nunits, in
     cu[j] = plan_cut(tptr, 0, nunits, j, ncta);
 }
 // Tile segments of the CTA ranges: CTA j runs the pieces of [cu[j], cu[j+1]) between tile boundaries (a tile owns nrows
-// consecutive units).  At most ncta + ntiles pieces; the unused tail of the arrays is left as empty segments.  One thread:
-// a few hundred steps, once per table width.
-__global__ void k_plan_segments(const int64_t* __restrict__ cu, int ncta, int64_t nrows, int nseg_max, int32_t* __restrict__ seg_ptr,
-                                int32_t* __restrict__ seg_tile, int64_t* __restrict__ seg_lo, int64_t* __restrict__ seg_hi) {
-    if (blockIdx.x || threadIdx.x) return;
-    int n = 0;
-    for (int j = 0; j < ncta; ++j) {
+// consecutive units).  At most ncta + ntiles pieces; the unused tail of the arrays is left as empty segments.  One block:
+// thread j counts the pieces of CTA j, a shared-memory scan places them, thread j writes them.
+__global__ void __launch_bounds__(1024) k_plan_segments(const int64_t* __restrict__ cu, int ncta, int64_t nrows, int nseg_max,
+                                                        int32_t* __restrict__ seg_ptr, int32_t* __restrict__ seg_tile,
+                                                        int64_t* __restrict__ seg_lo, int64_t* __restrict__ seg_hi) {
+    __shared__ int s_off[1025];
+    const int j = threadIdx.x;
+    int64_t lo_u = 0, hi_u = 0;
+    int cnt = 0;
+    if (j < ncta) {
+        lo_u = cu[j];
+        hi_u = cu[j + 1];
+        if (hi_u > lo_u) cnt = (int)((hi_u - 1) / nrows - lo_u / nrows) + 1;   // every tile touched holds at least one unit
+    }
+    s_off[j + 1] = cnt;
+    if (j == 0) s_off[0] = 0;
+    __syncthreads();
+    if (j == 0)
+        for (int i = 1; i <= ncta; ++i) s_off[i] = min(s_off[i] + s_off[i - 1], nseg_max);
+    __syncthreads();
+    if (j < ncta) {
+        int n = s_off[j];
         seg_ptr[j] = n;
-        for (int64_t tt = cu[j] / nrows; tt * nrows < cu[j + 1]; ++tt) {
-            const int64_t lo = max(cu[j], tt * nrows), hi = min(cu[j + 1], (tt + 1) * nrows);
-            if (lo >= hi || n >= nseg_max) continue;
+        for (int64_t tt = lo_u / nrows; tt * nrows < hi_u && n < s_off[j + 1]; ++tt, ++n) {
             seg_tile[n] = (int32_t)tt;
-            seg_lo[n] = lo;
-            seg_hi[n] = hi;
-            ++n;
+            seg_lo[n] = max(lo_u, tt * nrows);
+            seg_hi[n] = min(hi_u, (tt + 1) * nrows);
         }
     }
-    seg_ptr[ncta] = n;
-    for (; n < nseg_max; ++n) { seg_tile[n] = 0; seg_lo[n] = 0; seg_hi[n] = 0; }
+    if (j == 0) seg_ptr[ncta] = s_off[ncta];
+    for (int n = s_off[ncta] + j; n < nseg_max; n += blockDim.x) { seg_tile[n] = 0; seg_lo[n] = 0; seg_hi[n] = 0; }
 }
 // gb[seg][G] = first unit of row group G inside segment [lo, hi)
 __global__ void k_plan_groups(const int64_t* __restrict__ tptr, const int64_t* __restrict__ seg_lo, const int64_t* __restrict__ seg_hi,
@@ -415,6 +427,7 @@ void free_tiled(scs_ctx* ctx, TiledStream& t) {
 
 int build_tiled(scs_ctx* ctx, const Stream& s, TiledStream& t, int KP, int TR, int pad, int ncta, int ngroups, int order_gpw) {
     free_tiled(ctx, t);
+    SCS_CHECK(ncta >= 1 && ncta <= 1024, "work plan supports 1..1024 CTAs (got %d)", ncta);
     t.KP = KP;
     t.TR = TR;
     t.ntiles = (int)((s.xrows + TR - 1) / TR);
@@ -422,43 +435,41 @@ int build_tiled(scs_ctx* ctx, const Stream& s, TiledStream& t, int KP, int TR, i
     cudaStream_t st = ctx->stream;
     SCS_TRY(dev_alloc(ctx, &t.tptr, t.nunits + 1));
     SCS_CUDA(cudaMemsetAsync(t.tptr, 0, sizeof(int64_t), st));
+    Scratch tmps(st);
     int32_t* d_ulo = nullptr;
-    SCS_CUDA(cudaMallocAsync((void**)&d_ulo, (size_t)t.nunits * 4, st));
+    SCS_TRY(tmps.get(&d_ulo, t.nunits));
     k_tile_counts<<<(unsigned)((t.nunits + 255) / 256), 256, 0, st>>>(s.nrows, t.ntiles, TR, pad, s.lptr, s.lcode, t.tptr + 1, d_ulo);
     ctx->launches++;
     size_t tb = 0;
     SCS_CUDA(cub::DeviceScan::InclusiveSum(nullptr, tb, t.tptr + 1, t.tptr + 1, t.nunits, st));
     void* tmp = nullptr;
-    SCS_CUDA(cudaMallocAsync(&tmp, tb ? tb : 1, ctx->stream));
-    cudaError_t e = cub::DeviceScan::InclusiveSum(tmp, tb, t.tptr + 1, t.tptr + 1, t.nunits, st);
-    cudaFreeAsync(tmp, ctx->stream);
-    SCS_CUDA(e);
+    SCS_TRY(tmps.get_bytes(&tmp, tb));
+    SCS_CUDA(cub::DeviceScan::InclusiveSum(tmp, tb, t.tptr + 1, t.tptr + 1, t.nunits, st));
     ctx->launches += 2;
     // Nothing below waits for the device: the stream buffer is sized by its upper bound (every unit is padded by fewer than
     // `pad` entries) and the work plan is computed where the unit pointers are.
     const int64_t total_max = s.n_light + t.nunits * (int64_t)(pad > 0 ? pad - 1 : 0);
     SCS_TRY(dev_alloc(ctx, &t.tcode, total_max + 64));   // slack: the kernel prefetches one batch past a group's run
     k_tile_scatter<<<(unsigned)((s.nrows + 7) / 8), 256, 0, st>>>(s.nrows, t.ntiles, TR, s.lptr, s.lcode, t.tptr, d_ulo, t.tcode);
-    cudaFreeAsync(d_ulo, st);
     ctx->launches++;
     // ---- static work plan: CTA ranges, their tile segments (<= ncta + ntiles of them), group cuts
     t.ncta = ncta;
     t.ngroups = ngroups;
     t.nseg = ncta + t.ntiles;                            // capacity; seg_ptr[ncta] holds the number in use
     int64_t *d_cu = nullptr, *d_lo = nullptr, *d_hi = nullptr;
-    SCS_CUDA(cudaMallocAsync((void**)&d_cu, (size_t)(ncta + 1) * 8, st));
-    SCS_CUDA(cudaMallocAsync((void**)&d_lo, (size_t)t.nseg * 8, st));
-    SCS_CUDA(cudaMallocAsync((void**)&d_hi, (size_t)t.nseg * 8, st));
+    SCS_TRY(tmps.get(&d_cu, ncta + 1));
+    SCS_TRY(tmps.get(&d_lo, t.nseg));
+    SCS_TRY(tmps.get(&d_hi, t.nseg));
     SCS_TRY(dev_alloc(ctx, &t.seg_ptr, ncta + 1));
     SCS_TRY(dev_alloc(ctx, &t.seg_tile, t.nseg));
     SCS_TRY(dev_alloc(ctx, &t.gb, (int64_t)t.nseg * (ngroups + 1)));
     k_plan_ctas<<<(ncta + 1 + 127) / 128, 128, 0, st>>>(t.tptr, t.nunits, ncta, d_cu);
-    k_plan_segments<<<1, 32, 0, st>>>(d_cu, ncta, s.nrows, t.nseg, t.seg_ptr, t.seg_tile, d_lo, d_hi);
+    k_plan_segments<<<1, 1024, 0, st>>>(d_cu, ncta, s.nrows, t.nseg, t.seg_ptr, t.seg_tile, d_lo, d_hi);
     k_plan_groups<<<t.nseg, 256, 0, st>>>(t.tptr, d_lo, d_hi, ngroups, t.gb);
     ctx->launches += 3;
     if (order_gpw > 0) {                                 // packed row groups: order the entries inside the units (see k_order_units)
         uint8_t* d_phase = nullptr;
-        SCS_CUDA(cudaMallocAsync((void**)&d_phase, (size_t)t.nunits, st));
+        SCS_TRY(tmps.get(&d_phase, t.nunits));
         SCS_CUDA(cudaMemsetAsync(d_phase, 0, (size_t)t.nunits, st));
         const int64_t runs = (int64_t)t.nseg * ngroups;
         k_unit_phase<<<(unsigned)((runs + 255) / 256), 256, 0, st>>>(t.tptr, t.gb, ngroups, order_gpw, t.nseg, d_phase);
@@ -467,12 +478,8 @@ int build_tiled(scs_ctx* ctx, const Stream& s, TiledStream& t, int KP, int TR, i
         const int upw = (int)std::min<int64_t>(32, std::max<int64_t>(1, (int64_t)ORDER_CAP * 2 / 3 / avg));
         const int64_t owarps = (t.nunits + upw - 1) / upw;
         k_order_units<<<(unsigned)((owarps + ORDER_WARPS - 1) / ORDER_WARPS), ORDER_WARPS * 32, 0, st>>>(t.tptr, t.tcode, d_phase, t.nunits, upw);
-        cudaFreeAsync(d_phase, st);
         ctx->launches += 2;
     }
-    cudaFreeAsync(d_cu, st);
-    cudaFreeAsync(d_lo, st);
-    cudaFreeAsync(d_hi, st);
     SCS_CUDA(cudaGetLastError());
     return 0;
 }
@@ -505,16 +512,17 @@ int build_layout(scs_ctx* ctx, const int64_t* ref_indptr, const int32_t* ref_ind
     ctx->nnz_alt = nA;
     cudaStream_t st = ctx->stream;
 
-    // ---- host -> device (raw CSR of both matrices); temporaries, freed before returning
+    // ---- host -> device (raw CSR of both matrices); temporaries: returned to the pool on every path out of this function
+    Scratch tmp(st);
     int64_t *a_ptr = nullptr, *r_ptr = nullptr;
     int32_t *a_idx = nullptr, *r_idx = nullptr;
     void *a_val = nullptr, *r_val = nullptr;
-    SCS_CUDA(cudaMallocAsync((void**)&a_ptr, (V + 1) * sizeof(int64_t), ctx->stream));
-    SCS_CUDA(cudaMallocAsync((void**)&r_ptr, (V + 1) * sizeof(int64_t), ctx->stream));
-    SCS_CUDA(cudaMallocAsync((void**)&a_idx, (size_t)(nA ? nA : 1) * 4, ctx->stream));
-    SCS_CUDA(cudaMallocAsync((void**)&r_idx, (size_t)(nR ? nR : 1) * 4, ctx->stream));
-    SCS_CUDA(cudaMallocAsync(&a_val, (size_t)(nA ? nA : 1) * data_bytes, ctx->stream));
-    SCS_CUDA(cudaMallocAsync(&r_val, (size_t)(nR ? nR : 1) * data_bytes, ctx->stream));
+    SCS_TRY(tmp.get(&a_ptr, V + 1));
+    SCS_TRY(tmp.get(&r_ptr, V + 1));
+    SCS_TRY(tmp.get(&a_idx, nA));
+    SCS_TRY(tmp.get(&r_idx, nR));
+    SCS_TRY(tmp.get_bytes(&a_val, (size_t)nA * data_bytes));
+    SCS_TRY(tmp.get_bytes(&r_val, (size_t)nR * data_bytes));
     SCS_CUDA(cudaMemcpyAsync(a_ptr, alt_indptr, (V + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
     SCS_CUDA(cudaMemcpyAsync(r_ptr, ref_indptr, (V + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
     if (nA) SCS_CUDA(cudaMemcpyAsync(a_idx, alt_indices, (size_t)nA * 4, cudaMemcpyHostToDevice, st));
@@ -526,8 +534,8 @@ int build_layout(scs_ctx* ctx, const int64_t* ref_indptr, const int32_t* ref_ind
     trace.mark("alloc + H2D");
     int* err = nullptr;
     unsigned long long* ndup = nullptr;
-    SCS_CUDA(cudaMallocAsync((void**)&err, sizeof(int), ctx->stream));
-    SCS_CUDA(cudaMallocAsync((void**)&ndup, sizeof(unsigned long long), ctx->stream));
+    SCS_TRY(tmp.get(&err, 1));
+    SCS_TRY(tmp.get(&ndup, 1));
     SCS_CUDA(cudaMemsetAsync(err, 0, sizeof(int), st));
     SCS_CUDA(cudaMemsetAsync(ndup, 0, sizeof(unsigned long long), st));
 
@@ -536,9 +544,9 @@ int build_layout(scs_ctx* ctx, const int64_t* ref_indptr, const int32_t* ref_ind
     M.nrows = 2 * V;
     M.xrows = N;
     int64_t *cntL = nullptr, *cntH = nullptr, *rowsum = nullptr;
-    SCS_CUDA(cudaMallocAsync((void**)&cntL, 2 * V * sizeof(int64_t), ctx->stream));
-    SCS_CUDA(cudaMallocAsync((void**)&cntH, 2 * V * sizeof(int64_t), ctx->stream));
-    SCS_CUDA(cudaMallocAsync((void**)&rowsum, 2 * V * sizeof(int64_t), ctx->stream));
+    SCS_TRY(tmp.get(&cntL, 2 * V));
+    SCS_TRY(tmp.get(&cntH, 2 * V));
+    SCS_TRY(tmp.get(&rowsum, 2 * V));
     const int WPB = 8;  // warps per block
     unsigned gridPR = (unsigned)((2 * V + WPB - 1) / WPB);
     k_count_rows<<<gridPR, WPB * 32, 0, st>>>(V, a_ptr, a_val, r_ptr, r_val, data_bytes, cntL, cntH, rowsum, err);
@@ -562,13 +570,13 @@ int build_layout(scs_ctx* ctx, const int64_t* ref_indptr, const int32_t* ref_ind
     uint32_t *lkey = nullptr, *lval = nullptr, *hkey = nullptr, *lkey_s = nullptr, *hkey_s = nullptr;
     uint64_t *hval = nullptr, *hval_s = nullptr;
     const int64_t nl = M.n_light ? M.n_light : 1, nh = M.n_heavy ? M.n_heavy : 1;
-    SCS_CUDA(cudaMallocAsync((void**)&lkey, nl * 4, ctx->stream));
-    SCS_CUDA(cudaMallocAsync((void**)&lval, nl * 4, ctx->stream));
-    SCS_CUDA(cudaMallocAsync((void**)&lkey_s, nl * 4, ctx->stream));
-    SCS_CUDA(cudaMallocAsync((void**)&hkey, nh * 4, ctx->stream));
-    SCS_CUDA(cudaMallocAsync((void**)&hkey_s, nh * 4, ctx->stream));
-    SCS_CUDA(cudaMallocAsync((void**)&hval, nh * 8, ctx->stream));
-    SCS_CUDA(cudaMallocAsync((void**)&hval_s, nh * 8, ctx->stream));
+    SCS_TRY(tmp.get(&lkey, nl));
+    SCS_TRY(tmp.get(&lval, nl));
+    SCS_TRY(tmp.get(&lkey_s, nl));
+    SCS_TRY(tmp.get(&hkey, nh));
+    SCS_TRY(tmp.get(&hkey_s, nh));
+    SCS_TRY(tmp.get(&hval, nh));
+    SCS_TRY(tmp.get(&hval_s, nh));
     k_fill_M<<<gridPR, WPB * 32, 0, st>>>(V, N, a_ptr, a_idx, a_val, r_ptr, r_idx, r_val, data_bytes, M.lptr, M.hptr,
                                           M.lcode, M.hcode, M.hcnt, lkey, lval, hkey, hval, ndup, err);
     ctx->launches++;
@@ -607,9 +615,6 @@ int build_layout(scs_ctx* ctx, const int64_t* ref_indptr, const int32_t* ref_ind
     SCS_CUDA(cudaStreamSynchronize(st));
     SCS_CUDA(cudaGetLastError());
     trace.mark("ptrs, sums, kalt");
-    cudaFreeAsync(a_ptr, ctx->stream); cudaFreeAsync(r_ptr, ctx->stream); cudaFreeAsync(a_idx, ctx->stream); cudaFreeAsync(r_idx, ctx->stream); cudaFreeAsync(a_val, ctx->stream); cudaFreeAsync(r_val, ctx->stream);
-    cudaFreeAsync(cntL, ctx->stream); cudaFreeAsync(cntH, ctx->stream); cudaFreeAsync(rowsum, ctx->stream); cudaFreeAsync(err, ctx->stream); cudaFreeAsync(ndup, ctx->stream);
-    cudaFreeAsync(lkey, ctx->stream); cudaFreeAsync(lval, ctx->stream); cudaFreeAsync(lkey_s, ctx->stream); cudaFreeAsync(hkey, ctx->stream); cudaFreeAsync(hkey_s, ctx->stream); cudaFreeAsync(hval, ctx->stream); cudaFreeAsync(hval_s, ctx->stream);
     SCS_CHECK(herr != 2, "column index out of range [0, N)");
     SCS_CHECK(herr != 3, "CSR column indices must be sorted and duplicate-free within each row");
     SCS_CHECK(herr == 0, "invalid count matrix (code %d)", herr);

@@ -99,12 +99,11 @@ k_mstep_sparse(int64_t nrows, int64_t N, int K, const int32_t* __restrict__ orde
                const uint32_t* __restrict__ lcode,
                const int64_t* __restrict__ hptr, const uint32_t* __restrict__ hcode, const int32_t* __restrict__ hcnt,
                const uint32_t* __restrict__ hq, int64_t h_stride, const double* __restrict__ W, double* __restrict__ S,
-               int64_t s_stride, const double* __restrict__ gate, int64_t gate_stride, double gate_thr,
-               const int32_t* __restrict__ done, int32_t* __restrict__ sched) {
+               int64_t s_stride, const Gate gate, const int32_t* __restrict__ done, int32_t* __restrict__ sched) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int r = blockIdx.y;
     if (done && done[r]) return;
-    if (gate && gate[(int64_t)r * gate_stride] > gate_thr) return;   // too many unsaturated cells: the tiled SpMM runs instead
+    if (gate.dense && !gate_takes_sparse(gate, r)) return;   // too many unsaturated cells: the tiled SpMM runs instead
     const size_t ACC_BYTES = (size_t)blockDim.x * KP * 8;
     unsigned char* s_tab = smem + ACC_BYTES;
     uint64_t* bar = reinterpret_cast<uint64_t*>(s_tab + sparse_tab_bytes(h_stride));

@@ -160,21 +160,6 @@ __global__ void k_pa_codes(int64_t n, const int64_t* __restrict__ n_ref, const i
         default: scs::set_error("unsupported KP=%d", KP_); return 1; \
     }
 
-struct Scratch {   // stream-ordered scratch buffers, returned to the pool on scope exit
-    cudaStream_t st;
-    std::vector<void*> ptrs;
-    explicit Scratch(scs_ctx* ctx) : st(ctx->stream) {}
-    ~Scratch() { for (void* p : ptrs) cudaFreeAsync(p, st); }
-    template <typename T>
-    int get(T** p, int64_t n) {
-        *p = nullptr;
-        cudaError_t e = cudaMallocAsync((void**)p, (size_t)(n > 0 ? n : 1) * sizeof(T), st);
-        if (e != cudaSuccess) { set_error("cudaMalloc of %lld bytes failed: %s", (long long)(n * sizeof(T)), cudaGetErrorString(e)); return 1; }
-        ptrs.push_back(*p);
-        return 0;
-    }
-};
-
 }  // namespace scs
 
 using namespace scs;
@@ -190,7 +175,7 @@ int scs_seed_af(scs_ctx* ctx, int R, int K, const int32_t* labels, double* P0_ou
     const int KP = round_even(K);
     const int64_t stride = 2 * V * KP;
     cudaStream_t st = ctx->stream;
-    Scratch s(ctx);
+    Scratch s(ctx->stream);
     int32_t* d_lab; double *d_W, *d_S, *d_P;
     SCS_TRY(s.get(&d_lab, (int64_t)R * N));
     SCS_TRY(s.get(&d_W, (int64_t)R * N * KP));
@@ -215,7 +200,7 @@ int scs_pattern_counts(scs_ctx* ctx, const uint8_t* keep_rows, const uint8_t* ke
     SCS_CUDA(cudaSetDevice(ctx->device));
     const int64_t V = ctx->V, N = ctx->N;
     cudaStream_t st = ctx->stream;
-    Scratch s(ctx);
+    Scratch s(ctx->stream);
     uint8_t *d_kr = nullptr, *d_kc = nullptr;
     int64_t *d_rc, *d_cc;
     SCS_TRY(s.get(&d_rc, V));
@@ -247,7 +232,7 @@ int scs_doublet_scores(scs_ctx* ctx, int K, const double* P, const uint8_t* mask
     const int KP = round_even(K);
     const int nblk = (int)((N + CELL_BLOCK - 1) / CELL_BLOCK);
     cudaStream_t st = ctx->stream;
-    Scratch s(ctx);
+    Scratch s(ctx->stream);
     double *d_P, *d_T, *d_L, *d_part, *d_out;
     uint8_t* d_mask;
     SCS_TRY(s.get(&d_P, V * KP));
@@ -279,7 +264,7 @@ int scs_refine_scores(scs_ctx* ctx, int K, const double* P, const int32_t* label
     SCS_CUDA(cudaSetDevice(ctx->device));
     const int64_t V = ctx->V, N = ctx->N;
     cudaStream_t st = ctx->stream;
-    Scratch s(ctx);
+    Scratch s(ctx->stream);
     double *d_P, *d_out;
     int32_t* d_lab;
     SCS_TRY(s.get(&d_P, V * K));
@@ -303,7 +288,7 @@ int scs_cluster_counts(scs_ctx* ctx, int K, const int32_t* labels, int64_t* n_re
     SCS_CUDA(cudaSetDevice(ctx->device));
     const int64_t V = ctx->V, N = ctx->N;
     cudaStream_t st = ctx->stream;
-    Scratch s(ctx);
+    Scratch s(ctx->stream);
     int64_t* d_cnt;   // [2][V][K]: ref then alt, contiguous for one all-reduce
     int32_t* d_lab;
     int8_t* d_pa;

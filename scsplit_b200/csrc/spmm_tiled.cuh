@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(TILED_THREADS, 1)
 k_spmm_tiled(int64_t nrows, int TR, int64_t xrows, const int64_t* __restrict__ tptr, const uint16_t* __restrict__ tcode,
              const int32_t* __restrict__ seg_ptr, const int32_t* __restrict__ seg_tile, const int64_t* __restrict__ gb,
              const double* __restrict__ X, int64_t x_stride, double* __restrict__ part, int64_t part_stride,
-             const int32_t* __restrict__ done, const double* __restrict__ gate, int64_t gate_stride, double gate_thr) {
+             const int32_t* __restrict__ done, const Gate gate) {
     using C = TileCfg<KP, PACKED>;
     extern __shared__ __align__(128) unsigned char smem[];
     double* tile = reinterpret_cast<double*>(smem);                           // [(TR + 1) * KP], row TR is all zeros
@@ -99,7 +99,7 @@ k_spmm_tiled(int64_t nrows, int TR, int64_t xrows, const int64_t* __restrict__ t
 
     const int r = blockIdx.y;
     if (done && done[r]) return;
-    if (gate && gate[(int64_t)r * gate_stride] <= gate_thr) return;   // the sparse M-step kernel handles this restart
+    if (gate.dense && gate_takes_sparse(gate, r)) return;   // the sparse M-step kernel handles this restart
     X += (int64_t)r * x_stride;
     part += (int64_t)r * part_stride;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -223,11 +223,11 @@ __global__ void __launch_bounds__(256) k_spmm_combine(int64_t nrows, int ntiles,
                                                       const int64_t* __restrict__ hptr, const uint32_t* __restrict__ hcode,
                                                       const int32_t* __restrict__ hcnt, const double* __restrict__ X, int64_t x_stride,
                                                       double* __restrict__ Y, int64_t y_stride, const int32_t* __restrict__ done,
-                                                      const double* __restrict__ gate, int64_t gate_stride, double gate_thr) {
+                                                      const Gate gate) {
     constexpr int CH = KP / 2;
     const int r = blockIdx.y;
     if (done && done[r]) return;
-    if (gate && gate[(int64_t)r * gate_stride] <= gate_thr) return;
+    if (gate.dense && gate_takes_sparse(gate, r)) return;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nrows * CH) return;
     const int64_t row = i / CH;
@@ -279,6 +279,6 @@ __global__ void __launch_bounds__(256) k_spmm_combine(int64_t nrows, int ntiles,
 
 bool tiled_supported(scs_ctx* ctx, int kind, int KP);
 int launch_spmm_tiled(scs_ctx* ctx, int kind, int KP, int R, const double* X, int64_t x_stride, double* Y, int64_t y_stride,
-                      const int32_t* done, const double* gate, int64_t gate_stride, double gate_thr);
+                      const int32_t* done, Gate gate);
 
 }  // namespace scs

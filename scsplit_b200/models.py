@@ -26,20 +26,28 @@ _ENGINES = {}
 
 
 def get_engine(base_calls_mtx, device=0):
-    """One device-resident copy of the count matrices per (ref, alt) pair, shared by every restart's `models`."""
-    key = (id(base_calls_mtx[0]), id(base_calls_mtx[1]), device)
-    eng = _ENGINES.get(key)
-    if eng is None or eng.h is None:
-        for k in [k for k in _ENGINES if k[2] == device]:
-            _ENGINES.pop(k).close()
-        eng = Engine(base_calls_mtx[0], base_calls_mtx[1], device=device)
-        _ENGINES[key] = eng
+    """One device-resident copy of the count matrices per (ref, alt) pair, shared by every restart's `models`.
+
+    The cache entry holds the two matrices themselves, so their ids cannot be recycled by another pool while the
+    engine lives, and a hit is re-checked against shape and nnz.
+    """
+    ref, alt = base_calls_mtx[0], base_calls_mtx[1]
+    key = (id(ref), id(alt), device)
+    hit = _ENGINES.get(key)
+    if hit is not None:
+        eng, kref, kalt, sig = hit
+        if eng.h is not None and kref is ref and kalt is alt and sig == (ref.shape, ref.nnz, alt.shape, alt.nnz):
+            return eng
+    for k in [k for k in _ENGINES if k[2] == device]:
+        _ENGINES.pop(k)[0].close()
+    eng = Engine(ref, alt, device=device)
+    _ENGINES[key] = (eng, ref, alt, (ref.shape, ref.nnz, alt.shape, alt.nnz))
     return eng
 
 
 def release_engines():
     for k in list(_ENGINES):
-        _ENGINES.pop(k).close()
+        _ENGINES.pop(k)[0].close()
 
 
 def _log(output, text):
