@@ -12,7 +12,11 @@ metric configuration: 30,000 SNVs x 20,000 cells, 8 samples + doublet state (K =
           model_af and LL, all inside the timed region.
 N > 1 (torchrun): independent restarts are sharded over the GPUs (preferred for this
 config), every rank runs the same pool from a different initialisation, no data-path collective -> weak scaling.
-`--mode cells` instead shards the CELLS and all-reduces the M-step statistics with NCCL every iteration.
+Every run then adds a second leg under the key `cells_c4`: BASELINE config 4 (60k SNVs x 200k cells, K = 17) with the
+CELLS sharded over the N GPUs and the M-step statistics all-reduced by NCCL every iteration (at N = 1: the whole pool on
+one GPU, the anchor of that strong-scaling curve).  `--mode cells` runs the main leg itself cell-sharded.
+Further keys of the N = 1 line: `regimes` (soft-posterior start of a run, whole run to the stop rule), `small_configs`
+(configs 1 and 2 next to their roofline times), `cpu_baseline`.
 """
 import argparse
 import json
@@ -157,15 +161,19 @@ def reference_models(pool, K, P0):
     return step, "port"
 
 
+def workload_string(name, V, N, K, nnz_union):
+    return "%s: %d SNVs x %d cells, K=%d states incl. doublet state, Poisson lam=0.05, nnz(union)=%d" % (name, V, N, K, nnz_union)
+
+
 def time_reference(pool, K, n_steps, n_warm, budget_s):
-    """Time the reference's E+M iteration on a column sample sized for `budget_s` seconds in total."""
+    """Time the reference's E+M iteration (scSplit:165-198).  The whole pool when n_steps + n_warm iterations fit `budget_s`
+    seconds (6.6 s per iteration at config 3 on one core), otherwise a stated column sample scaled to the pool."""
     from oracle import em_oracle as O
     V, N = pool.ref.shape
     full_s = 8.7 * (pool.ref.nnz + pool.alt.nnz) / 29.4e6 * K / 9.0   # measured at this shape: BASELINE.md section 2
     frac = min(1.0, budget_s / max(full_s * (n_steps + n_warm), 1e-9))
-    n_s = max(200, int(N * frac))
-    n_s = min(N, n_s)
-    sub = pool._replace(ref=pool.ref[:, :n_s].tocsr(), alt=pool.alt[:, :n_s].tocsr(), barcodes=pool.barcodes[:n_s])
+    n_s = N if frac >= 1.0 else min(N, max(200, int(N * frac)))
+    sub = pool if n_s == N else pool._replace(ref=pool.ref[:, :n_s].tocsr(), alt=pool.alt[:, :n_s].tocsr(), barcodes=pool.barcodes[:n_s])
     k_alt = O.kalt(sub.ref, sub.alt)
     P0 = O.seed_af(sub.ref, sub.alt, k_alt, random_seed_labels(n_s, K, 0), K)
     step, kind = reference_models(sub, K, P0)
@@ -175,26 +183,28 @@ def time_reference(pool, K, n_steps, n_warm, budget_s):
     for _ in range(n_steps):
         step()
     dt = (time.perf_counter() - t0) / n_steps
-    # cost is linear in the number of stored entries, i.e. in cells at fixed depth: scale the sample to the full pool
+    # cost is linear in the number of stored entries, i.e. in cells at fixed depth: a sample is scaled to the full pool
     full_iter_s = dt * (N / n_s)
-    sample = "%d timed + %d warm-up E+M iterations on the first %d of %d cells (all %d SNVs, K=%d); %s" % (
-        n_steps, n_warm, n_s, N, V, K, "scaled x%.2f to the full pool" % (N / n_s) if n_s < N else "full pool")
-    return dict(value=1.0 / full_iter_s, unit=UNIT, cores=1, kind=kind, sample=sample), dt
+    sample = "%d timed + %d warm-up E+M iterations on %s (all %d SNVs, K=%d)" % (
+        n_steps, n_warm, "the full pool of %d cells" % N if n_s == N else "the first %d of %d cells, scaled x%.2f to the full pool" % (n_s, N, N / n_s), V, K)
+    return dict(value=1.0 / full_iter_s, unit=UNIT, cores=1, kind=kind, sample=sample, same_config=bool(n_s == N)), dt
 
 
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    from scsplit_b200 import synth
     cfg, pool = workload(args.workload)
     K = cfg["K"]
-    base, dt = time_reference(pool, K, args.steps, args.warmup, budget_s=150.0)
+    # the whole pool for up to 40 iterations (the driver asks for 20 + 5: ~3 minutes at config 3); more than that is sampled
+    base, dt = time_reference(pool, K, args.steps, args.warmup, budget_s=8.7 * 40)
     V, N = pool.ref.shape
     line = {
         "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 / base["value"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "%s: %d SNVs x %d cells, K=%d states incl. doublet state, Poisson lam=0.05" % (args.workload, V, N, K),
+        "config": {"workload": workload_string(args.workload, V, N, K, synth.union_nnz(pool.ref, pool.alt)),
                    "host_cores_available": os.cpu_count(), "note": "the reference is single-threaded on this path (scipy sparsetools, pandas)"},
         "cpu_baseline": base,
         "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -222,11 +232,153 @@ def e2e_call(Engine, csr, P0_pinned, out_W, out_P, iters, device):
     return float(ll[0])
 
 
+def join_comm(eng, Engine, rank, world):
+    """Carry rank 0's NCCL unique id to every rank (torch.distributed) and join the library's communicator."""
+    import torch
+    import torch.distributed as dist
+    uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        uid = torch.from_numpy(Engine.comm_unique_id()).cuda()
+    dist.broadcast(uid, 0)
+    eng.comm_init(uid.cpu().numpy(), rank, world)
+
+
+def timed_iterations(eng, steps, warmup, local, barrier):
+    """W untimed + K timed iterations on the resident pool; device time from CUDA events on the library's stream."""
+    import torch
+    eng.em_iterate(warmup, check_conv=False)
+    eng.set_timing(True, every=KERNEL_TIMING_EVERY)
+    eng.kernel_times(reset=True)
+    barrier()
+    n0 = eng.launch_count()
+    with ClockSampler(local) as clk:
+        t0 = time.perf_counter()
+        eng.em_iterate(steps, check_conv=False)          # K steps on one stream; the host only polls flags every 8th
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+    out = dict(dev_s=eng.last_ms() / 1000.0, wall=wall, launches=eng.launch_count() - n0, kt=eng.kernel_times(reset=True), clocks=clk.summary())
+    eng.set_timing(False)
+    barrier()
+    return out
+
+
+def max_over_ranks(values, world):
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor(values, dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return [float(x) for x in t]
+
+
+def cells_leg(args, rank, world, local, barrier):
+    """BASELINE config 4 with the cells sharded over the ranks and the statistics all-reduced by NCCL every iteration
+    (world = 1: the whole pool on one GPU).  Returns the dict printed under `cells_c4` (rank 0) or None."""
+    import torch
+    import torch.distributed as dist
+    from scsplit_b200 import synth
+    from scsplit_b200.engine import Engine
+    name = "c4"
+    cfg = synth.CONFIGS[name]
+    N_total, V, K = cfg["N"], cfg["V"], cfg["K"]
+    per = (N_total + world - 1) // world
+    lo, hi = rank * per, min(N_total, (rank + 1) * per)
+    steps, warmup = min(args.steps, 40), min(args.warmup, 8)
+    # phase 1 (host memory and time: ~75 M entries per 25k cells): every rank reports whether it got its shard up
+    eng, err, gen_s = None, None, 0.0
+    try:
+        import psutil
+        need = 45e9 * (hi - lo) / N_total * world        # ~45 GB of host memory in flight for the whole pool on one box
+        if psutil.virtual_memory().available < need:
+            raise MemoryError("host has %.0f GB available, the config-4 shards of this box need ~%.0f GB" % (psutil.virtual_memory().available / 1e9, need / 1e9))
+        t0 = time.perf_counter()
+        workers = max(1, (os.cpu_count() or 1) // world - 1)
+        pool = synth.make_config(name, cell_lo=lo, cell_hi=hi, workers=workers)
+        gen_s = time.perf_counter() - t0
+        eng = Engine(pool.ref, pool.alt, device=local)
+        del pool
+    except Exception as exc:
+        err = "%s: %s" % (type(exc).__name__, exc)
+    ok = torch.tensor([0 if err else 1], dtype=torch.int64, device="cuda")
+    if world > 1:
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    if int(ok[0]) == 0:
+        if eng is not None:
+            eng.close()
+        return {"skipped": err or "another rank could not set up its shard"} if rank == 0 else None
+    with eng:
+        if world > 1:
+            join_comm(eng, Engine, rank, world)
+        info = eng.layout_info()
+        nnzU = torch.tensor([info["nnz_union"]], dtype=torch.int64, device="cuda")
+        if world > 1:
+            dist.all_reduce(nnzU)
+        lab = random_seed_labels(N_total, K, 0)[lo:hi]
+        eng.em_begin(eng.seed_af(lab, K), max_iter=steps + warmup + 1)
+        einfo = eng.em_info()
+        res = timed_iterations(eng, steps, warmup, local, barrier)
+        it, cv, ll = eng.em_status()
+    dev_s, wall = max_over_ranks([res["dev_s"], res["wall"]], world)
+    if rank != 0:
+        return None
+    kt = res["kt"]
+    eb, mb = algorithmic_bytes(V, N_total, K, int(nnzU[0]))
+    peak, _ = load_peaks()
+    return {
+        "workload": workload_string(name, V, N_total, K, int(nnzU[0])),
+        "parallelism": "cells sharded over %d GPUs (%d cells each), statistics all-reduced by NCCL in %s per iteration, overlapped with the M-step kernels" % (
+            world, per, "5 pieces" if kt["allreduce_n"] else "one piece") if world > 1 else "single GPU, whole pool",
+        "n_gpus": world, "steps": steps, "warmup": warmup, "value": steps / dev_s, "unit": UNIT, "ms_per_step": 1000.0 * dev_s / steps,
+        "scaling": "strong", "e_us": kt["e_us"], "m_us": kt["m_us"], "allreduce_us": kt["allreduce_us"],
+        "allreduce_pieces_timed": kt["allreduce_n"], "allreduce_doubles": 2 * V * (K + (K & 1)) + (K + (K & 1)) + 2,
+        "estep": "fixed point, %d-byte rows, F=%d" % (16 * einfo["q_lanes"], einfo["q_frac_bits"]) if einfo["q_lanes"] else "fp64",
+        "hbm_frac_of_iteration": (eb + mb) / world / (dev_s / steps) / 1e9 / peak,
+        "last_ll": float(ll[0]), "host_generation_s": gen_s, "clocks": res["clocks"],
+    }
+
+
+def regime_times(Engine, pool, P0, local):
+    """One restart the way `scSplit run` runs it: from the seed to the reference's stop rule (scSplit:155-161)."""
+    out = {}
+    with Engine(pool.ref, pool.alt, device=local) as eng:
+        eng.em_begin(P0)
+        eng.em_iterate(2, check_conv=False)               # the soft-posterior start: tiled M-step, not the sparse kernel
+        out["soft_ms_per_step"] = eng.last_ms() / 2
+        eng.em_begin(P0)
+        t0 = time.perf_counter()
+        eng.em_run()
+        wall = time.perf_counter() - t0
+        it, cv, ll = eng.em_status()
+        out["whole_run"] = {"iterations": int(it[0]), "converged": bool(cv[0]), "device_ms": eng.last_ms(), "wall_ms": 1000.0 * wall,
+                            "iter_per_s": float(it[0]) / (eng.last_ms() / 1000.0), "ll": float(ll[0])}
+    return out
+
+
+def small_config_times(Engine, local):
+    """Configs 1 and 2: iterations that are a few microseconds of HBM time, i.e. launch-bound."""
+    from scsplit_b200 import synth
+    peak, _ = load_peaks()
+    out = {}
+    for name in ("c1", "c2"):
+        cfg, pool = workload(name)
+        K = cfg["K"]
+        V, N = pool.ref.shape
+        with Engine(pool.ref, pool.alt, device=local) as eng:
+            eng.em_begin(eng.seed_af(random_seed_labels(N, K, 0), K), max_iter=400)
+            eng.em_iterate(20, check_conv=False)
+            n0 = eng.launch_count()
+            eng.em_iterate(200, check_conv=False)
+            eb, mb = algorithmic_bytes(V, N, K, synth.union_nnz(pool.ref, pool.alt))
+            out[name] = {"us_per_iteration": eng.last_ms() * 1000.0 / 200, "hbm_roofline_us": (eb + mb) / peak / 1e3,
+                         "launches_per_iteration": (eng.launch_count() - n0) / 200.0, "shape": "%d x %d, K=%d" % (V, N, K)}
+    return out
+
+
 def run_cuda_arm(args):
     import torch
     import torch.distributed as dist
     from scipy.sparse import csr_matrix
-    from scsplit_b200 import _lib
+    from scsplit_b200 import _lib, synth
     from scsplit_b200.engine import Engine
 
     rank = int(os.environ.get("RANK", "0"))
@@ -256,9 +408,7 @@ def run_cuda_arm(args):
         torch.cuda.synchronize()
 
     cells_mode = args.mode == "cells" and world > 1
-    cfg, pool = (None, None)
     if cells_mode:
-        from scsplit_b200 import synth
         cfg = synth.CONFIGS[args.workload]
         per = (cfg["N"] + world - 1) // world
         lo, hi = rank * per, min(cfg["N"], (rank + 1) * per)
@@ -268,16 +418,11 @@ def run_cuda_arm(args):
     K = cfg["K"]
     V, n_local = pool.ref.shape
     N_total = cfg["N"]
-    from scsplit_b200 import synth
     nnzU_local = synth.union_nnz(pool.ref, pool.alt)
 
     eng = Engine(pool.ref, pool.alt, device=local)
     if cells_mode:
-        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            uid = torch.from_numpy(Engine.comm_unique_id()).cuda()
-        dist.broadcast(uid, 0)
-        eng.comm_init(uid.cpu().numpy(), rank, world)
+        join_comm(eng, Engine, rank, world)
     info = eng.layout_info()
     assert info["nnz_union"] == nnzU_local
     nnzU_total = nnzU_local
@@ -291,25 +436,10 @@ def run_cuda_arm(args):
         lab = lab[lo:hi]
     P0 = eng.seed_af(lab, K)
     eng.em_begin(P0, max_iter=max(args.steps + args.warmup + 1, 300))
-    eng.em_iterate(args.warmup, check_conv=False)
-    eng.set_timing(True, every=KERNEL_TIMING_EVERY)
-    eng.kernel_times(reset=True)
-    barrier()
-    n0 = eng.launch_count()
-    with ClockSampler(local) as clk:
-        t0 = time.perf_counter()
-        eng.em_iterate(args.steps, check_conv=False)     # K steps, one stream, no host sync inside
-        torch.cuda.synchronize()
-        wall = time.perf_counter() - t0
-    dev_s = eng.last_ms() / 1000.0
-    launches = eng.launch_count() - n0
-    kt = eng.kernel_times(reset=True)
-    eng.set_timing(False)
-    barrier()
-    t = torch.tensor([dev_s, wall], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_s, wall = float(t[0]), float(t[1])
+    einfo = eng.em_info()
+    res = timed_iterations(eng, args.steps, args.warmup, local, barrier)
+    dev_s, wall = max_over_ranks([res["dev_s"], res["wall"]], world)
+    launches, kt, clocks = res["launches"], res["kt"], res["clocks"]
     it, cv, ll = eng.em_status()
 
     # ---- end to end through the host API, pinned host buffers (rank-local; restart-sharded => N independent calls)
@@ -335,10 +465,7 @@ def run_cuda_arm(args):
             e2e_call(Engine, (pr, pa), P0p, outW, outP, 1, local)
         torch.cuda.synchronize()
         strict_s = (time.perf_counter() - t0) / n_e2e
-        t = torch.tensor([e2e_s, strict_s], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s, strict_s = float(t[0]), float(t[1])
+        e2e_s, strict_s = max_over_ranks([e2e_s, strict_s], world)
         h2d = sum(a.nbytes for m in (pr, pa) for a in (m.data, m.indices, m.indptr)) + P0p.nbytes
         d2h = outW.nbytes + outP.nbytes + 16
         e2e = {"value": world * E2E_ITERS / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
@@ -346,6 +473,18 @@ def run_cuda_arm(args):
                "what": "Engine(ref,alt) from pinned host CSR (H2D + device layout build) + em_begin(P0) + %d iterations + D2H of P_s_c, model_af, LL; one call = one restart (scSplit:477-480)" % E2E_ITERS,
                "strict_one_iteration_per_call": {"value": world * 1.0 / strict_s, "unit": UNIT, "ms_per_call": 1000.0 * strict_s}}
     eng.close()
+
+    # ---- N = 1 extras: how a real run starts and ends, the launch-bound small configurations
+    extras = {}
+    if world == 1 and rank == 0 and not args.quick:
+        extras["regimes"] = dict(saturated_ms_per_step=1000.0 * dev_s / args.steps, **regime_times(Engine, pool, P0, local))
+        extras["small_configs"] = small_config_times(Engine, local)
+
+    # ---- second leg: config 4, cells sharded over the ranks, NCCL all-reduce per iteration (N = 1: the anchor)
+    cells = None
+    if not cells_mode and not args.no_cells_leg and not args.quick:
+        del pool
+        cells = cells_leg(args, rank, world, local, barrier)   # (set-up failures, e.g. host memory, come back as {"skipped": why})
 
     if rank != 0:
         if world > 1:
@@ -355,11 +494,12 @@ def run_cuda_arm(args):
     eb, mb = algorithmic_bytes(V, n_local, K, nnzU_local)
     dom = "E" if kt["e_us"] >= kt["m_us"] else "M"
     dom_bytes, dom_us = (eb, kt["e_us"]) if dom == "E" else (mb, kt["m_us"])
-    traffic = None
+    traffic, traffic_src = None, None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath) and args.workload == "c3" and not cells_mode:   # the capture is of this configuration only
         with open(tpath) as f:
-            traffic = json.load(f).get(dom)
+            tj = json.load(f)
+        traffic, traffic_src = tj.get(dom), "static: %s (not measured in this run)" % tj.get("source", "profiles/traffic.json")
     iters_total = world * args.steps if not cells_mode else args.steps
     value = iters_total / dev_s
     line = {
@@ -367,21 +507,24 @@ def run_cuda_arm(args):
         "ms_per_step": 1000.0 * dev_s / args.steps, "higher_is_better": True,
         "scaling": "strong" if cells_mode else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {
-            "workload": "%s: %d SNVs x %d cells, K=%d states incl. doublet state, Poisson lam=0.05, nnz(union)=%d" % (
-                args.workload, V, N_total, K, nnzU_total),
+            "workload": workload_string(args.workload, V, N_total, K, nnzU_total),
             "parallelism": ("cells sharded over %d GPUs, NCCL all-reduce of 2VK+K+1 doubles per iteration" % world) if cells_mode
             else ("%d independent restarts, one per GPU, no collective" % world if world > 1 else "single GPU, one restart"),
             "l2": "inputs larger than L2: two entry streams of %.0f MB each are read per step vs %.0f MB of L2; no flush" % (
                 info["light"] * 4 / 1e6 + info["heavy"] * 8 / 1e6, L2_BYTES / 1e6),
             "init": "seed P from 3 random cells per state through scs_seed_af (the reference's trim/PCA/KMeans initialiser is host code outside the step)",
+            "regime": "saturated posteriors (after %d warm-up iterations): E-step + sparse M-step; the soft start of a run is under `regimes`" % args.warmup,
+            "estep": ("log tables in %d-bit fixed point (F=%d), %d-byte rows, exact integer accumulation; fp64 per restart when a table does not fit" % (
+                6 + einfo["q_frac_bits"], einfo["q_frac_bits"], 16 * einfo["q_lanes"])) if einfo["q_lanes"] else "fp64 tables and accumulation",
         },
         "cell_snv_per_sec": value * V * N_total,
         "wall_ms_per_step": 1000.0 * wall / args.steps,
-        "clocks": clk.summary(),
+        "clocks": clocks,
         "gpu_launches": int(launches),
         "last_ll": float(ll[0]),
-        "roofline": {"bound": "hbm", "kernel": "E-step SpMM" if dom == "E" else "M-step SpMM", "achieved": dom_bytes / (dom_us * 1e-6) / 1e9,
-                     "peak": peak, "unit": "GB/s", "frac": dom_bytes / (dom_us * 1e-6) / 1e9 / peak, "traffic": traffic,
+        "roofline": {"bound": "hbm", "kernel": "E-step sums (k_estep_q + k_combine_q)" if dom == "E" and einfo["q_lanes"] else "E-step SpMM" if dom == "E" else "M-step sums",
+                     "achieved": dom_bytes / (dom_us * 1e-6) / 1e9,
+                     "peak": peak, "unit": "GB/s", "frac": dom_bytes / (dom_us * 1e-6) / 1e9 / peak, "traffic": traffic, "traffic_source": traffic_src,
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": int(dom_bytes), "avg_launch_us": dom_us,
                      "e_step": {"us": kt["e_us"], "bytes": int(eb), "GBps": eb / max(kt["e_us"], 1e-9) / 1e3, "launches_timed": kt["e_n"]},
                      "m_step": {"us": kt["m_us"], "bytes": int(mb), "GBps": mb / max(kt["m_us"], 1e-9) / 1e3, "launches_timed": kt["m_n"]},
@@ -389,7 +532,11 @@ def run_cuda_arm(args):
     }
     if e2e:
         line["e2e"] = e2e
-    if world == 1 and not args.no_cpu_baseline:
+    line.update(extras)
+    if cells is not None:
+        line["cells_c4"] = cells
+    if world == 1 and not args.no_cpu_baseline and not args.quick:
+        _, pool = workload(args.workload)
         base, _ = time_reference(pool, K, 2, 1, budget_s=30.0)
         line["cpu_baseline"] = base
     print(json.dumps(line))
@@ -406,6 +553,8 @@ def main():
     ap.add_argument("--workload", default="c3", choices=["c1", "c2", "c3", "c4", "c5"])
     ap.add_argument("--mode", default="restarts", choices=["restarts", "cells"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cells-leg", action="store_true", help="skip the second leg (config 4, cells sharded over the GPUs)")
+    ap.add_argument("--quick", action="store_true", help="main leg and e2e only (kernel development)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -94,6 +94,10 @@ int scs_estep(scs_ctx* ctx);
 int scs_mstep(scs_ctx* ctx);
 /* iterations done, converged flag (iterations < max_iter, scSplit:162) and last LL (lP_c_m) per restart */
 int scs_em_status(scs_ctx* ctx, int32_t* iters, int32_t* converged, double* ll);
+/* how the E-step sums of the current EM state run: out[0] = lanes per fixed-point table row (4 or 8; 0 = the fp64 kernels do
+ * the E-step), out[1] = fraction bits F of the fixed-point tables, out[2] = table tiles, out[3] = restarts whose table
+ * currently does not fit the fixed-point format (their E-step runs in fp64).  scSplit:175-178; DESIGN.md section 4. */
+int scs_em_info(scs_ctx* ctx, int64_t out[4]);
 int scs_em_get(scs_ctx* ctx, int restart, int what, double* out);
 int scs_em_set(scs_ctx* ctx, int restart, int what, const double* in);
 int scs_em_end(scs_ctx* ctx);
@@ -135,13 +139,15 @@ int scs_csv_free(scs_csv* csv);
 int scs_launch_count(scs_ctx* ctx, int64_t* out);
 /* average device time in microseconds of the E-step SpMM and M-step SpMM launches recorded with CUDA events
  * on the context's stream since the last reset; pass reset=1 to clear. out[0]=E us, out[1]=M us,
- * out[2]=#E-steps timed, out[3]=#M-steps timed.  scs_set_timing(ctx, n): n = 0 off, n >= 1 times every n-th E-step and
+ * out[2]=#E-steps timed, out[3]=#M-steps timed, out[4]=us of statistics all-reduce per timed M-step (cells sharded over
+ * ranks; the pieces overlap the M-step kernels), out[5]=#all-reduce pieces timed.  scs_set_timing(ctx, n): n = 0 off, n >= 1 times every n-th E-step and
  * every n-th M-step of the EM loop (the event records cost ~11 us per timed iteration at config 3, so a loop that is
  * itself being timed samples, e.g. n = 8); step-level calls outside the loop are always timed while n >= 1. */
 int scs_set_timing(scs_ctx* ctx, int enable);
-int scs_kernel_times(scs_ctx* ctx, double out[4], int reset);
-/* select kernel variant: 0 = auto (tiled shared-memory SpMM; sparse M-step once posteriors saturate), 1 = v1 (warp per row,
- * gathers from L1/L2; for A/B tests), 2 = tiled SpMM for both half-steps (sparse M-step off) */
+int scs_kernel_times(scs_ctx* ctx, double out[6], int reset);
+/* select kernel variant (before scs_em_begin): 0 = auto (fixed-point E-step where the pool fits the format, sparse M-step
+ * once posteriors saturate), 1 = v1 (warp per row, gathers from L1/L2; for A/B tests), 2 = tiled fp64 SpMM for both
+ * half-steps (sparse M-step off), 3 = tiled fp64 E-step + sparse M-step (the fixed-point E-step off) */
 int scs_set_variant(scs_ctx* ctx, int variant);
 /* self-test of the device 2^x used by the Bayes step (scSplit:184, 188 evaluate `2 ** x` in numpy): y[i] = 2^x[i] for n host
  * doubles, computed on the context's device with the kernel's own routine */

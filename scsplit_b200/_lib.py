@@ -34,6 +34,7 @@ SIGNATURES = {
     "scs_estep": (c_int, [c_void_p]),
     "scs_mstep": (c_int, [c_void_p]),
     "scs_em_status": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+    "scs_em_info": (c_int, [c_void_p, POINTER(c_int64)]),
     "scs_em_get": (c_int, [c_void_p, c_int, c_int, c_void_p]),
     "scs_em_set": (c_int, [c_void_p, c_int, c_int, c_void_p]),
     "scs_em_end": (c_int, [c_void_p]),

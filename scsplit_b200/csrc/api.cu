@@ -94,13 +94,17 @@ int scs_destroy(scs_ctx* ctx) {
     if (!ctx) return 0;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->comm_stream) cudaStreamSynchronize(ctx->comm_stream);
     em_free(ctx);
     comm_destroy(ctx);
     free_stream(ctx, ctx->E);
     free_stream(ctx, ctx->M);
     dev_free(ctx, ctx->m_order);
+    dev_free(ctx, ctx->m_order_chunks);
     free_tiled(ctx, ctx->TE);
     free_tiled(ctx, ctx->TM);
+    free_tiled(ctx, ctx->QE);
+    dev_free(ctx, ctx->qpart);
     dev_free(ctx, ctx->part);
     dev_free(ctx, ctx->sum_alt);
     dev_free(ctx, ctx->sum_ref);
@@ -151,15 +155,16 @@ int scs_set_timing(scs_ctx* ctx, int enable) {
 
 int scs_set_variant(scs_ctx* ctx, int variant) {
     SCS_CHECK(ctx, "null context");
-    SCS_CHECK(variant >= 0 && variant <= 2, "variant must be 0, 1 or 2");
+    SCS_CHECK(variant >= 0 && variant <= 3, "variant must be 0, 1, 2 or 3");
     ctx->variant = variant;
     return 0;
 }
 
-int scs_kernel_times(scs_ctx* ctx, double out[4], int reset) {
+int scs_kernel_times(scs_ctx* ctx, double out[6], int reset) {
     SCS_CHECK(ctx && out, "null argument");
     SCS_CUDA(cudaSetDevice(ctx->device));
     SCS_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (ctx->comm_stream) SCS_CUDA(cudaStreamSynchronize(ctx->comm_stream));
     for (auto& p : ctx->ev_pending) {
         float ms = 0.f;
         SCS_CUDA(cudaEventElapsedTime(&ms, p.second.first, p.second.second));
@@ -174,8 +179,11 @@ int scs_kernel_times(scs_ctx* ctx, double out[4], int reset) {
     out[1] = ctx->m_samples ? (ctx->t_sum[1] + ctx->t_sum[2]) / (double)ctx->m_samples : 0.0;
     out[2] = (double)ctx->t_cnt[0];
     out[3] = (double)ctx->m_samples;
+    // the all-reduce of a step is issued in pieces: their durations are summed per sampled M-step
+    out[4] = ctx->m_samples ? ctx->t_sum[3] / (double)ctx->m_samples : 0.0;
+    out[5] = (double)ctx->t_cnt[3];
     if (reset) {
-        for (int i = 0; i < 3; ++i) { ctx->t_sum[i] = 0.0; ctx->t_cnt[i] = 0; }
+        for (int i = 0; i < 4; ++i) { ctx->t_sum[i] = 0.0; ctx->t_cnt[i] = 0; }
         ctx->m_samples = 0;
     }
     return 0;

@@ -21,6 +21,8 @@ struct NcclApi {
     int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
     int (*CommDestroy)(ncclComm_t) = nullptr;
     int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
 };
 
@@ -39,7 +41,10 @@ static int load_nccl() {
     g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))dlsym(g_nccl.lib, "ncclCommDestroy");
     g_nccl.AllReduce = (decltype(g_nccl.AllReduce))dlsym(g_nccl.lib, "ncclAllReduce");
     g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))dlsym(g_nccl.lib, "ncclGetErrorString");
-    SCS_CHECK(g_nccl.GetUniqueId && g_nccl.CommInitRank && g_nccl.CommDestroy && g_nccl.AllReduce, "libnccl lacks required symbols");
+    g_nccl.GroupStart = (decltype(g_nccl.GroupStart))dlsym(g_nccl.lib, "ncclGroupStart");
+    g_nccl.GroupEnd = (decltype(g_nccl.GroupEnd))dlsym(g_nccl.lib, "ncclGroupEnd");
+    SCS_CHECK(g_nccl.GetUniqueId && g_nccl.CommInitRank && g_nccl.CommDestroy && g_nccl.AllReduce && g_nccl.GroupStart && g_nccl.GroupEnd,
+              "libnccl lacks required symbols");
     return 0;
 }
 
@@ -58,6 +63,25 @@ int comm_allreduce_f64(scs_ctx* ctx, double* buf, int64_t count) {
     return 0;
 }
 
+// Sum over ranks of `nseg` segments send[i * stride .. + count) -> recv[i * stride .. + count) (i = 0 .. nseg-1, segments
+// whose skip[i] is set are left out), issued as one NCCL group on `stream`.  Out of place: what a rank sends is never
+// overwritten, so a segment nobody recomputes (a restart that has stopped) keeps giving the same sum.
+int comm_allreduce_segments(scs_ctx* ctx, const double* send, double* recv, int64_t stride, int64_t count, int nseg, const int32_t* skip,
+                            cudaStream_t stream) {
+    if (ctx->world <= 1) return 0;
+    SCS_NCCL(g_nccl.GroupStart());
+    int rc = 0;
+    for (int i = 0; i < nseg && !rc; ++i) {
+        if (skip && skip[i]) continue;
+        rc = g_nccl.AllReduce(send + (int64_t)i * stride, recv + (int64_t)i * stride, (size_t)count, ncclFloat64_, ncclSum_, (ncclComm_t)ctx->comm,
+                              stream);
+    }
+    const int rc2 = g_nccl.GroupEnd();
+    SCS_NCCL(rc);
+    SCS_NCCL(rc2);
+    return 0;
+}
+
 int comm_allreduce_i64(scs_ctx* ctx, int64_t* buf, int64_t count) {
     if (ctx->world <= 1) return 0;
     SCS_NCCL(g_nccl.AllReduce(buf, buf, (size_t)count, ncclInt64_, ncclSum_, (ncclComm_t)ctx->comm, ctx->stream));
@@ -66,6 +90,9 @@ int comm_allreduce_i64(scs_ctx* ctx, int64_t* buf, int64_t count) {
 
 int comm_destroy(scs_ctx* ctx) {
     if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)ctx->comm);
+    if (ctx->comm_stream) cudaStreamDestroy(ctx->comm_stream);
+    ctx->comm_stream = nullptr;
+    for (auto& e : ctx->ev_comm) { if (e) cudaEventDestroy(e); e = nullptr; }
     ctx->comm = nullptr;
     ctx->world = 1;
     ctx->rank = 0;
@@ -103,6 +130,12 @@ int scs_comm_init(scs_ctx* ctx, const uint8_t id[128], int rank, int world) {
     ctx->comm = comm;
     ctx->rank = rank;
     ctx->world = world;
+    {   // the statistics all-reduce runs on its own high-priority stream so that it overlaps the M-step kernels (em.cu: run_m)
+        int lo = 0, hi = 0;
+        SCS_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        SCS_CUDA(cudaStreamCreateWithPriority(&ctx->comm_stream, cudaStreamNonBlocking, hi));
+        for (auto& e : ctx->ev_comm) SCS_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
     // k_alt is a function of the GLOBAL per-SNV sums (scSplit:101-103): reduce the integer sums once
     SCS_TRY(comm_allreduce_i64(ctx, ctx->sum_alt, ctx->V));
     SCS_TRY(comm_allreduce_i64(ctx, ctx->sum_ref, ctx->V));

@@ -96,8 +96,12 @@ struct EmState {
     double* L = nullptr;        // [R][N][KP]
     double* W = nullptr;        // [R][N][KP]
     double* stats = nullptr;    // [R][2V*KP + KP + 2]: S (alt/ref posterior-weighted sums), colsum[KP], LL, pad
+    double* gstats = nullptr;   // the same summed over ranks (cells sharded over GPUs); nullptr on a single GPU
     double* lps = nullptr;      // [R][KP]
     double* partial = nullptr;  // [R][nblk][KP+2] per-block column mass, LL, dense-path cell count (fixed-order reduction)
+    uint64_t* Tq = nullptr;     // [R][2V][2 * q_lanes] fixed-point copy of T (estep_q.cuh); nullptr = the E-step runs in fp64
+    int32_t* qbad = nullptr;    // [R] the restart's table does not fit the fixed-point format: its E-step runs in fp64
+    int q_lanes = 0, q_F = 0;
     int32_t* sat = nullptr;     // [R] latched: the restart's dense-row count has been at or below the saturation threshold
     uint32_t* hq = nullptr;     // [R][h_stride] packed (state, 1 - weight) of a saturated posterior row, or SPARSE_DENSE
     int64_t h_stride = 0;       // N rounded up to 4 (16-byte multiples for the bulk copy)
@@ -122,6 +126,11 @@ struct scs_ctx {
     scs::Stream E;   // cell-major
     scs::Stream M;   // SNV-major (2V pseudo-rows)
     scs::TiledStream TE, TM;   // tile-major copies for the current KP
+    scs::TiledStream QE;       // tile-major cell-major stream of the fixed-point E-step (estep_q.cuh): KP field = lanes per row
+    int q_state[2] = {0, 0};   // per row width (4 / 8 lanes): 0 = not tried, 1 = built, -1 = the pool does not fit the format
+    int q_F = 0;               // fraction bits of the fixed-point tables of this pool
+    uint64_t* qpart = nullptr; // per-(unit, lane) integer sums of the fixed-point E-step
+    int64_t qpart_words = 0;
     double* part = nullptr;    // per-(tile,row) partial sums of the tiled SpMM
     int64_t part_doubles = 0;
     uint32_t smem_attr_set[3] = {0, 0, 0};  // bit KP/2: this device already has the large-shared-memory attribute of k_spmm_tiled<KP> / k_mstep_sparse<KP> / k_spmm_tiled<KP, packed>
@@ -133,6 +142,10 @@ struct scs_ctx {
     // multi-GPU
     void* comm = nullptr;        // ncclComm_t
     int rank = 0, world = 1;
+    cudaStream_t comm_stream = nullptr;       // high-priority stream of the statistics all-reduce (cells sharded over ranks)
+    cudaEvent_t ev_comm[10] = {};             // [0..7] M-step chunk done (main stream), [8] posterior tail ready, [9] all-reduce done (comm stream)
+    int32_t* m_order_chunks = nullptr;        // [2V] job order of the sparse M-step inside each of the M_CHUNKS row ranges
+    std::vector<int32_t> h_done;              // done flags as of the last poll (which restarts the collectives may leave out)
     // instrumentation
     int64_t launches = 0;
     int timing = 0;              // 0 = off, n = time every n-th E-step and every n-th M-step
@@ -144,8 +157,8 @@ struct scs_ctx {
     std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> ev_pending;  // (kind, (start, stop))
     cudaEvent_t ev_iter[2] = {nullptr, nullptr};   // brackets the launches of the last scs_em_iterate
     double last_iter_ms = 0.0;
-    double t_sum[3] = {0, 0, 0};      // E SpMM, M tiled SpMM, M sparse kernel
-    int64_t t_cnt[3] = {0, 0, 0};
+    double t_sum[4] = {0, 0, 0, 0};   // E SpMM, M tiled SpMM, M sparse kernel, statistics all-reduce pieces
+    int64_t t_cnt[4] = {0, 0, 0, 0};
 };
 
 namespace scs {
@@ -202,7 +215,10 @@ int build_layout(scs_ctx* ctx, const int64_t* ref_indptr, const int32_t* ref_ind
 void free_stream(scs_ctx* ctx, Stream& s);
 void free_tiled(scs_ctx* ctx, TiledStream& t);
 int build_tiled(scs_ctx* ctx, const Stream& s, TiledStream& t, int KP, int TR, int pad, int ncta, int ngroups, int order_gpw = 0);
-int build_row_order(scs_ctx* ctx, const Stream& s, int32_t** order);   // rows by descending light-entry count, ties by index
+// rows by descending light-entry count, ties by index; with nchunks > 1 that order inside each of nchunks equal row ranges
+int build_row_order(scs_ctx* ctx, const Stream& s, int32_t** order, int nchunks = 1);
+// tile-major stream of the fixed-point E-step; *ok = 0 when the pool's cells are too deep for a useful fraction (F < 40)
+int build_qtiled(scs_ctx* ctx, const Stream& s, TiledStream& t, int lanes, int TR, int ncta, int ngroups, int* F, int* ok);
 
 // em.cu
 int launch_spmm(scs_ctx* ctx, int kind /*0=E,1=M*/, int KP, int R, const double* X, int64_t x_stride, double* Y,
@@ -215,6 +231,8 @@ int download_pitched(scs_ctx* ctx, double* host, const double* src_dev, int64_t 
 // comm.cu
 int comm_allreduce_f64(scs_ctx* ctx, double* buf_dev, int64_t count);
 int comm_allreduce_i64(scs_ctx* ctx, int64_t* buf_dev, int64_t count);
+int comm_allreduce_segments(scs_ctx* ctx, const double* send, double* recv, int64_t stride, int64_t count, int nseg, const int32_t* skip,
+                            cudaStream_t stream);
 int comm_destroy(scs_ctx* ctx);
 
 }  // namespace scs

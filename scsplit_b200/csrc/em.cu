@@ -62,14 +62,14 @@ int launch_spmm(scs_ctx* ctx, int kind, int KP, int R, const double* X, int64_t 
     cudaEvent_t ea, eb;
     SCS_TRY(timing_begin(ctx, &ea, &eb));
     int variant = ctx->variant;
-    if (variant == 0) variant = tiled_supported(ctx, kind, KP) ? 2 : 1;
+    if (variant == 0 || variant == 3) variant = tiled_supported(ctx, kind, KP) ? 2 : 1;
     if (variant == 2) {
         SCS_TRY(launch_spmm_tiled(ctx, kind, KP, R, X, x_stride, Y, y_stride, done, gate));
     } else {
         const int WPB = 8;
         dim3 grid((unsigned)((s.nrows + WPB - 1) / WPB), (unsigned)R);
         SCS_DISPATCH_KP(KP, (k_spmm_rows<KPc><<<grid, WPB * 32, 0, ctx->stream>>>(s.nrows, s.lptr, s.lcode, s.hptr, s.hcode, s.hcnt, X,
-                                                                                  x_stride, Y, y_stride, done)));
+                                                                                  x_stride, Y, y_stride, done, nullptr)));
         ctx->launches++;
     }
     SCS_TRY(timing_end(ctx, kind, ea, eb));
@@ -125,8 +125,67 @@ int launch_spmm_tiled(scs_ctx* ctx, int kind, int KP, int R, const double* X, in
     return 0;
 }
 
+// Fixed-point E-step (estep_q.cuh): tile-major stream with inline counts, built on first use per row width.
+// Returns the lanes per row (4 / 8) when this pool and K can use it, else 0.
+static int q_prepare(scs_ctx* ctx, int K) {
+    if (ctx->variant != 0 || std::getenv("SCS_NO_Q")) return 0;
+    const int lanes = q_lanes_for(K);
+    if (!lanes) return 0;
+    const int idx = lanes == 4 ? 0 : 1;
+    if (ctx->q_state[idx] < 0) return 0;
+    const int ctas = ctx->sm_count > 0 ? ctx->sm_count : 148;
+    const int ngroups = (TILED_THREADS / 32) * (32 / lanes);
+    const int TR = q_tile_rows(lanes, ctx->E.xrows);
+    if (ctx->QE.KP != lanes || ctx->QE.TR != TR || ctx->QE.ncta != ctas || ctx->QE.ngroups != ngroups || !ctx->QE.tcode) {
+        int ok = 0, F = 0;
+        if (build_qtiled(ctx, ctx->E, ctx->QE, lanes, TR, ctas, ngroups, &F, &ok)) return -1;
+        ctx->q_state[idx] = ok ? 1 : -1;
+        if (!ok) return 0;
+        ctx->q_F = F;
+    }
+    return lanes;
+}
+
+static int launch_estep_q(scs_ctx* ctx, const int32_t* done) {
+    EmState& em = ctx->em;
+    TiledStream& t = ctx->QE;
+    const int lanes = em.q_lanes;
+    const int64_t part_stride = t.nunits * lanes * 3;
+    if (ctx->qpart_words < part_stride * em.R) {
+        dev_free(ctx, ctx->qpart);
+        SCS_TRY(dev_alloc(ctx, &ctx->qpart, part_stride * em.R));
+        ctx->qpart_words = part_stride * em.R;
+    }
+    const size_t smem = ((((size_t)(t.TR + 1) * lanes * 16) + 127) & ~(size_t)127) + 16;
+    const int64_t xq_stride = 2 * ctx->V * 2 * lanes;
+    dim3 grid((unsigned)t.ncta, (unsigned)em.R);
+    dim3 cgrid((unsigned)((ctx->N * lanes + 63) / 64), (unsigned)em.R);       // 256 threads = 64 (cell, lane) pairs x 4 tile classes
+    const double scale_inv = ldexp(1.0, -em.q_F);
+    if (!(ctx->smem_attr_set[2] >> (16 + lanes) & 1u)) {
+        if (lanes == 4) SCS_CUDA(cudaFuncSetAttribute(k_estep_q<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_BYTES + 1024));
+        else SCS_CUDA(cudaFuncSetAttribute(k_estep_q<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_BYTES + 1024));
+        ctx->smem_attr_set[2] |= 1u << (16 + lanes);
+    }
+    if (lanes == 4) {
+        k_estep_q<4><<<grid, TILED_THREADS, smem, ctx->stream>>>(t.TR, ctx->E.xrows, t.tptr, reinterpret_cast<const uint32_t*>(t.tcode), t.seg_ptr,
+                                                                 t.seg_tile, t.gb, em.Tq, xq_stride, ctx->qpart, part_stride, done, em.qbad);
+        k_combine_q<4><<<cgrid, 256, 0, ctx->stream>>>(ctx->N, em.K, em.KP, t.ntiles, ctx->qpart, part_stride, scale_inv, ctx->E.hptr, ctx->E.hcode,
+                                                       ctx->E.hcnt, em.T, 2 * ctx->V * em.KP, em.L, ctx->N * em.KP, done, em.qbad);
+    } else {
+        k_estep_q<8><<<grid, TILED_THREADS, smem, ctx->stream>>>(t.TR, ctx->E.xrows, t.tptr, reinterpret_cast<const uint32_t*>(t.tcode), t.seg_ptr,
+                                                                 t.seg_tile, t.gb, em.Tq, xq_stride, ctx->qpart, part_stride, done, em.qbad);
+        k_combine_q<8><<<cgrid, 256, 0, ctx->stream>>>(ctx->N, em.K, em.KP, t.ntiles, ctx->qpart, part_stride, scale_inv, ctx->E.hptr, ctx->E.hcode,
+                                                       ctx->E.hcnt, em.T, 2 * ctx->V * em.KP, em.L, ctx->N * em.KP, done, em.qbad);
+    }
+    ctx->launches += 2;
+    SCS_CUDA(cudaGetLastError());
+    return 0;
+}
+
 int em_free(scs_ctx* ctx) {
     EmState& em = ctx->em;
+    dev_free(ctx, em.Tq); dev_free(ctx, em.qbad); dev_free(ctx, em.gstats);
+    ctx->h_done.clear();
     dev_free(ctx, em.T); dev_free(ctx, em.P); dev_free(ctx, em.L); dev_free(ctx, em.W); dev_free(ctx, em.stats); dev_free(ctx, em.lps);
     dev_free(ctx, em.hq); dev_free(ctx, em.sched); dev_free(ctx, em.sat);
     dev_free(ctx, em.partial); dev_free(ctx, em.hist); dev_free(ctx, em.ll_prev); dev_free(ctx, em.iters); dev_free(ctx, em.done);
@@ -185,11 +244,27 @@ int download_pitched(scs_ctx* ctx, double* host, const double* src, int64_t rows
     return 0;
 }
 
+static TableOut table_out(scs_ctx* ctx, int r0) {
+    EmState& em = ctx->em;
+    TableOut t;
+    t.T = em.T + (int64_t)r0 * 2 * ctx->V * em.KP;
+    if (em.Tq) {
+        t.Tq = em.Tq + (int64_t)r0 * 2 * ctx->V * 2 * em.q_lanes;
+        t.qlanes = em.q_lanes;
+        t.qscale = ldexp(1.0, em.q_F);
+        t.qbad = em.qbad + r0;
+        t.qbad_next = em.qbad + em.R + r0;
+    }
+    return t;
+}
+
 static int tables_from_P(scs_ctx* ctx, int r0, int nr) {
     EmState& em = ctx->em;
-    dim3 grid((unsigned)((ctx->V * em.KP + 255) / 256), (unsigned)nr);
-    k_tables_from_P<<<grid, 256, 0, ctx->stream>>>(ctx->V, em.K, em.KP, em.P + (int64_t)r0 * ctx->V * em.KP,
-                                                   em.T + (int64_t)r0 * 2 * ctx->V * em.KP);
+    const int rpb = finalize_rows_per_block(em.KP);
+    dim3 grid((unsigned)((ctx->V + rpb - 1) / rpb), (unsigned)nr);
+    if (em.qbad) SCS_CUDA(cudaMemsetAsync(em.qbad + r0, 0, (size_t)nr * 4, ctx->stream));
+    k_finalize<<<grid, FIN_THREADS, 0, ctx->stream>>>(ctx->V, em.K, em.KP, nullptr, 0, nullptr, em.P + (int64_t)r0 * ctx->V * em.KP, nullptr,
+                                                      table_out(ctx, r0), nullptr, PriorArgs{});
     ctx->launches++;
     SCS_CUDA(cudaGetLastError());
     return 0;
@@ -200,7 +275,21 @@ static int run_e(scs_ctx* ctx, const int32_t* done) {
     EmState& em = ctx->em;
     PhaseSample sample(ctx, 0);
     const int64_t V = ctx->V, N = ctx->N;
-    SCS_TRY(launch_spmm(ctx, 0, em.KP, em.R, em.T, 2 * V * em.KP, em.L, N * em.KP, done));
+    if (em.Tq) {
+        // fixed-point sums for every restart whose table fits the format; the (rare) others -- flagged by k_finalize -- take the
+        // fp64 row kernel, which needs no tile-major stream of its own
+        cudaEvent_t ea, eb;
+        SCS_TRY(timing_begin(ctx, &ea, &eb));
+        SCS_TRY(launch_estep_q(ctx, done));
+        const int WPB = 8;
+        dim3 rgrid((unsigned)std::min<int64_t>((N + WPB - 1) / WPB, (int64_t)(ctx->sm_count > 0 ? ctx->sm_count : 148) * 8), (unsigned)em.R);
+        SCS_DISPATCH_KP(em.KP, (k_spmm_rows<KPc><<<rgrid, WPB * 32, 0, ctx->stream>>>(N, ctx->E.lptr, ctx->E.lcode, ctx->E.hptr, ctx->E.hcode, ctx->E.hcnt,
+                                                                                     em.T, 2 * V * em.KP, em.L, N * em.KP, done, em.qbad)));
+        ctx->launches++;
+        SCS_TRY(timing_end(ctx, 0, ea, eb));
+    } else {
+        SCS_TRY(launch_spmm(ctx, 0, em.KP, em.R, em.T, 2 * V * em.KP, em.L, N * em.KP, done));
+    }
     dim3 grid((unsigned)em.nblk, (unsigned)em.R);
     SCS_DISPATCH_KP(em.KP, (k_bayes<KPc><<<grid, 1024, 0, ctx->stream>>>(N, em.K, em.L, em.W, em.lps, em.partial, em.nblk, em.hq,
                                                                               em.h_stride, done, em.stats + 2 * V * em.KP,
@@ -211,13 +300,39 @@ static int run_e(scs_ctx* ctx, const int32_t* done) {
     return 0;
 }
 
+constexpr int M_CHUNKS = 4;   // row ranges of the M-step sums whose all-reduce overlaps the next range's kernel (cells sharded over ranks)
+
+// One sum all-reduce of a piece of the statistics of every live restart, stats -> gstats, on the communication stream, after
+// `after` (an event of the main stream) has fired.  Timed (kind 3) when the step is sampled.
+static int reduce_piece(scs_ctx* ctx, int64_t off, int64_t count, cudaEvent_t after) {
+    EmState& em = ctx->em;
+    SCS_CUDA(cudaEventRecord(after, ctx->stream));
+    SCS_CUDA(cudaStreamWaitEvent(ctx->comm_stream, after, 0));
+    cudaEvent_t ea = nullptr, eb = nullptr;
+    if (ctx->timing && ctx->sample_on && ctx->ev_pending.size() < 8192) {
+        for (cudaEvent_t* e : {&ea, &eb}) {
+            if (!ctx->ev_pool.empty()) { *e = ctx->ev_pool.back(); ctx->ev_pool.pop_back(); }
+            else SCS_CUDA(cudaEventCreate(e));
+        }
+        SCS_CUDA(cudaEventRecord(ea, ctx->comm_stream));
+    }
+    const int32_t* skip = (int)ctx->h_done.size() == em.R ? ctx->h_done.data() : nullptr;
+    SCS_TRY(comm_allreduce_segments(ctx, em.stats + off, em.gstats + off, em.stats_stride, count, em.R, skip, ctx->comm_stream));
+    if (ea) {
+        SCS_CUDA(cudaEventRecord(eb, ctx->comm_stream));
+        ctx->ev_pending.push_back({3, {ea, eb}});
+    }
+    return 0;
+}
+
 static int run_m(scs_ctx* ctx, const int32_t* done, int track, int check_conv) {
     EmState& em = ctx->em;
     PhaseSample sample(ctx, 1);
     const int64_t V = ctx->V, N = ctx->N;
+    const bool multi = ctx->world > 1;
     // M-step sums: the sparse kernel when (nearly) all posterior rows are saturated, else the tiled SpMM; both are launched
     // and the dense-path cell count in the statistics tail (written by the last block of k_bayes, or by k_reduce_stats on the step-level path) gates which one does the work
-    const int sparse_threads = ctx->variant == 0 ? sparse_threads_for(N, em.KP) : 0;
+    const int sparse_threads = (ctx->variant == 0 || ctx->variant == 3) ? sparse_threads_for(N, em.KP) : 0;
     const bool sparse = sparse_threads > 0;
     Gate gate;
     // N/32: measured at config 3 (tools/soft_phase_probe.py) -- the run's second iteration still has 14 % unsaturated cells,
@@ -228,36 +343,56 @@ static int run_m(scs_ctx* ctx, const int32_t* done, int track, int check_conv) {
         gate.thr = (double)std::max<int64_t>(16, N / 32);
         gate.sat = em.sat;
     }
-    if (sparse) {
-        cudaEvent_t ea = nullptr, eb = nullptr;
-        SCS_TRY(timing_begin(ctx, &ea, &eb));
-        if (!ctx->m_order) SCS_TRY(build_row_order(ctx, ctx->M, &ctx->m_order));
-        const size_t smem = sparse_smem_bytes(em.h_stride, em.KP, sparse_threads);
-        dim3 grid((unsigned)(ctx->sm_count > 0 ? ctx->sm_count : 148), (unsigned)em.R);
-        SCS_DISPATCH_KP(em.KP, {
-            if (!(ctx->smem_attr_set[1] >> (KPc / 2) & 1u)) {
-                SCS_CUDA(cudaFuncSetAttribute(k_mstep_sparse<KPc>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_BYTES + 1024));
-                ctx->smem_attr_set[1] |= 1u << (KPc / 2);
-            }
-            k_mstep_sparse<KPc><<<grid, sparse_threads, smem, ctx->stream>>>(ctx->M.nrows, N, em.K, ctx->m_order, ctx->M.lptr, ctx->M.lcode, ctx->M.hptr,
-                                                                           ctx->M.hcode, ctx->M.hcnt, em.hq, em.h_stride, em.W, em.stats,
-                                                                           em.stats_stride, gate, done, em.sched);
-        });
-        ctx->launches++;
-        SCS_TRY(timing_end(ctx, 2, ea, eb));
-    }
+    // Cells sharded over ranks: the sums of every rank are added by NCCL, piece by piece on a second stream, while the next
+    // piece is still being computed -- first the posterior tail (column mass, LL; ready since k_bayes), then M_CHUNKS row
+    // ranges of S, each as soon as its kernel has finished.  k_finalize waits for the last piece.
+    const int64_t tail_off = 2 * V * em.KP;
+    if (multi) SCS_TRY(reduce_piece(ctx, tail_off, em.KP + 2, ctx->ev_comm[8]));
     // (the sparse kernel is correct for ANY number of unsaturated cells, only slower; once a poll has seen the latch of every
     // live restart set, the tiled pair -- which those restarts can no longer take -- is not launched at all)
     if (!(sparse && em.sparse_only))
         SCS_TRY(launch_spmm(ctx, 1, em.KP, em.R, em.W, N * em.KP, em.stats, em.stats_stride, done, gate));
-    if (ctx->world > 1) SCS_TRY(comm_allreduce_f64(ctx, em.stats, (int64_t)em.R * em.stats_stride));
-    dim3 grid((unsigned)((V * em.KP + 255) / 256), (unsigned)em.R);
+    if (sparse) {
+        cudaEvent_t ea = nullptr, eb = nullptr;
+        SCS_TRY(timing_begin(ctx, &ea, &eb));
+        const int nchunks = multi ? M_CHUNKS : 1;
+        int32_t*& order = multi ? ctx->m_order_chunks : ctx->m_order;
+        if (!order) SCS_TRY(build_row_order(ctx, ctx->M, &order, nchunks));
+        const size_t smem = sparse_smem_bytes(em.h_stride, em.KP, sparse_threads);
+        dim3 grid((unsigned)(ctx->sm_count > 0 ? ctx->sm_count : 148), (unsigned)em.R);
+        const int64_t nrows = ctx->M.nrows;
+        for (int c = 0; c < nchunks; ++c) {
+            // rows [lo, hi) of chunk c: the keys of build_row_order put row i into chunk i * nchunks / nrows
+            const int64_t lo = (c * nrows + nchunks - 1) / nchunks, hi = ((c + 1) * nrows + nchunks - 1) / nchunks;
+            SCS_DISPATCH_KP(em.KP, {
+                if (!(ctx->smem_attr_set[1] >> (KPc / 2) & 1u)) {
+                    SCS_CUDA(cudaFuncSetAttribute(k_mstep_sparse<KPc>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_BYTES + 1024));
+                    ctx->smem_attr_set[1] |= 1u << (KPc / 2);
+                }
+                k_mstep_sparse<KPc><<<grid, sparse_threads, smem, ctx->stream>>>(nrows, hi - lo, N, em.K, order + lo, ctx->M.lptr, ctx->M.lcode,
+                                                                               ctx->M.hptr, ctx->M.hcode, ctx->M.hcnt, em.hq, em.h_stride, em.W,
+                                                                               em.stats, em.stats_stride, gate, done, em.sched);
+            });
+            ctx->launches++;
+            if (multi) SCS_TRY(reduce_piece(ctx, lo * em.KP, (hi - lo) * em.KP, ctx->ev_comm[c]));
+        }
+        SCS_TRY(timing_end(ctx, 2, ea, eb));
+    } else if (multi) {
+        SCS_TRY(reduce_piece(ctx, 0, tail_off, ctx->ev_comm[0]));
+    }
+    if (multi) {
+        SCS_CUDA(cudaEventRecord(ctx->ev_comm[9], ctx->comm_stream));
+        SCS_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_comm[9], 0));
+    }
+    const double* S = multi ? em.gstats : em.stats;
+    const int rpb = finalize_rows_per_block(em.KP);
+    dim3 grid((unsigned)((V + rpb - 1) / rpb), (unsigned)em.R);
     PriorArgs prior;
-    prior.tail_off = 2 * V * em.KP;
+    prior.tail_off = tail_off;
     prior.lps = em.lps; prior.hist = em.hist; prior.max_iter = em.max_iter; prior.ll_prev = em.ll_prev;
     prior.iters = em.iters; prior.done = em.done; prior.count = em.sched + 2 * em.R;
     prior.track = track; prior.check_conv = check_conv;
-    k_finalize<<<grid, 256, 0, ctx->stream>>>(V, em.K, em.KP, em.stats, em.stats_stride, ctx->kalt, em.P, em.T, done, prior);
+    k_finalize<<<grid, FIN_THREADS, 0, ctx->stream>>>(V, em.K, em.KP, S, em.stats_stride, ctx->kalt, nullptr, em.P, table_out(ctx, 0), done, prior);
     ctx->launches += 1;
     SCS_CUDA(cudaGetLastError());
     return 0;
@@ -319,11 +454,26 @@ int scs_em_begin(scs_ctx* ctx, int R, int K, const double* P0, int max_iter) {
         }
         em.nblk = (int)best;
     }
+    {
+        const int lanes = q_prepare(ctx, K);
+        if (lanes < 0) return 1;
+        if (lanes) {
+            em.q_lanes = lanes;
+            em.q_F = ctx->q_F;
+            SCS_TRY(dev_alloc(ctx, &em.Tq, (int64_t)R * 2 * V * 2 * lanes));
+            SCS_TRY(dev_alloc(ctx, &em.qbad, 2 * R));   // [R] flags, [R] their staging inside k_finalize
+            SCS_CUDA(cudaMemsetAsync(em.qbad, 0, (size_t)R * 8, ctx->stream));
+        }
+    }
     SCS_TRY(dev_alloc(ctx, &em.T, (int64_t)R * 2 * V * KP));
     SCS_TRY(dev_alloc(ctx, &em.P, (int64_t)R * V * KP));
     SCS_TRY(dev_alloc(ctx, &em.L, (int64_t)R * N * KP));
     SCS_TRY(dev_alloc(ctx, &em.W, (int64_t)R * N * KP));
     SCS_TRY(dev_alloc(ctx, &em.stats, (int64_t)R * em.stats_stride));
+    if (ctx->world > 1) {
+        SCS_TRY(dev_alloc(ctx, &em.gstats, (int64_t)R * em.stats_stride));
+        SCS_CUDA(cudaMemsetAsync(em.gstats, 0, (size_t)R * em.stats_stride * 8, ctx->stream));
+    }
     SCS_TRY(dev_alloc(ctx, &em.lps, (int64_t)R * KP));
     SCS_TRY(dev_alloc(ctx, &em.partial, (int64_t)R * em.nblk * (KP + 2)));
     em.h_stride = (N + 3) / 4 * 4;
@@ -388,6 +538,7 @@ int scs_em_iterate(scs_ctx* ctx, int n_iter, int check_conv) {
     const int32_t* done = check_conv ? em.done : nullptr;
     std::vector<int32_t> h_done((size_t)em.R);
     std::vector<int32_t> h_sat((size_t)em.R);
+    if (!check_conv) ctx->h_done.clear();     // every restart takes part in the collectives of a fixed-length run
     const int POLL = 8;   // iterations between host polls of the device-side convergence flags and saturation counts
     if (!ctx->ev_iter[0]) { SCS_CUDA(cudaEventCreate(&ctx->ev_iter[0])); SCS_CUDA(cudaEventCreate(&ctx->ev_iter[1])); }
     SCS_CUDA(cudaEventRecord(ctx->ev_iter[0], ctx->stream));
@@ -404,6 +555,7 @@ int scs_em_iterate(scs_ctx* ctx, int n_iter, int check_conv) {
                 if (!(check_conv && h_done[r])) saturated = saturated && h_sat[r];
             }
             em.sparse_only = saturated ? 1 : 0;
+            if (check_conv) ctx->h_done = h_done; // (identical on every rank: the flags are functions of all-reduced sums)
             if (check_conv && all) break;
         }
     }
@@ -442,6 +594,24 @@ int scs_em_status(scs_ctx* ctx, int32_t* iters, int32_t* converged, double* ll) 
     return 0;
 }
 
+int scs_em_info(scs_ctx* ctx, int64_t out[4]) {
+    SCS_CHECK(ctx && ctx->em.R, "EM state not initialised (call scs_em_begin)");
+    SCS_CHECK(out, "null output");
+    SCS_CUDA(cudaSetDevice(ctx->device));
+    EmState& em = ctx->em;
+    out[0] = em.Tq ? em.q_lanes : 0;
+    out[1] = em.Tq ? em.q_F : 0;
+    out[2] = em.Tq ? ctx->QE.ntiles : ctx->TE.ntiles;
+    out[3] = 0;
+    if (em.Tq) {
+        std::vector<int32_t> bad((size_t)em.R);
+        SCS_CUDA(cudaMemcpyAsync(bad.data(), em.qbad, (size_t)em.R * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        SCS_CUDA(cudaStreamSynchronize(ctx->stream));
+        for (int r = 0; r < em.R; ++r) out[3] += bad[r] != 0;
+    }
+    return 0;
+}
+
 int scs_em_get(scs_ctx* ctx, int restart, int what, double* out) {
     SCS_CHECK(ctx && ctx->em.R, "EM state not initialised (call scs_em_begin)");
     EmState& em = ctx->em;
@@ -457,7 +627,7 @@ int scs_em_get(scs_ctx* ctx, int restart, int what, double* out) {
         case SCS_L: SCS_TRY(download_pitched(ctx, out, em.L + (int64_t)restart * N * KP, N, K, KP)); break;
         case SCS_LPS: SCS_CUDA(cudaMemcpyAsync(out, em.lps + (int64_t)restart * KP, (size_t)K * 8, cudaMemcpyDeviceToHost, ctx->stream)); break;
         case SCS_LLHIST: SCS_CUDA(cudaMemcpyAsync(out, em.hist + (int64_t)restart * em.max_iter, (size_t)em.max_iter * 8, cudaMemcpyDeviceToHost, ctx->stream)); break;
-        case SCS_STATS: SCS_CUDA(cudaMemcpyAsync(out, em.stats + (int64_t)restart * em.stats_stride, (size_t)em.stats_stride * 8, cudaMemcpyDeviceToHost, ctx->stream)); break;
+        case SCS_STATS: SCS_CUDA(cudaMemcpyAsync(out, (em.gstats ? em.gstats : em.stats) + (int64_t)restart * em.stats_stride, (size_t)em.stats_stride * 8, cudaMemcpyDeviceToHost, ctx->stream)); break;
         default: SCS_CHECK(false, "unknown array id %d", what);
     }
     SCS_CUDA(cudaStreamSynchronize(ctx->stream));

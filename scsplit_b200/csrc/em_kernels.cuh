@@ -12,6 +12,7 @@
 //   (k_mstep_sparse, the M-step for saturated posteriors, lives in mstep_sparse.cuh)
 #pragma once
 #include "common.cuh"
+#include "estep_q.cuh"
 
 namespace scs {
 
@@ -29,60 +30,62 @@ __global__ void __launch_bounds__(256) k_spmm_rows(int64_t nrows, const int64_t*
                                                    const uint32_t* __restrict__ lcode, const int64_t* __restrict__ hptr,
                                                    const uint32_t* __restrict__ hcode, const int32_t* __restrict__ hcnt,
                                                    const double* __restrict__ X, int64_t x_stride, double* __restrict__ Y,
-                                                   int64_t y_stride, const int32_t* __restrict__ done) {
+                                                   int64_t y_stride, const int32_t* __restrict__ done, const int32_t* __restrict__ only) {
     const int r = blockIdx.y;
     if (done && done[r]) return;
+    if (only && !only[r]) return;      // fp64 stand-in of the fixed-point E-step: only the restarts whose table did not fit
     const int lane = threadIdx.x & 31;
-    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (row >= nrows) return;
     X += (int64_t)r * x_stride;
     Y += (int64_t)r * y_stride;
-    double acc[KP];
+    // (grid-stride over the rows: the grid may be smaller than the row count, e.g. when this kernel only stands by)
+    for (int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < nrows; row += (int64_t)gridDim.x * (blockDim.x >> 5)) {
+        double acc[KP];
 #pragma unroll
-    for (int k = 0; k < KP; ++k) acc[k] = 0.0;
+        for (int k = 0; k < KP; ++k) acc[k] = 0.0;
 
-    const int64_t lb = lptr[row], le = lptr[row + 1];
-    int64_t e = lb + lane;
-    for (; e + 32 < le; e += 64) {  // two independent gathers in flight per lane
-        const uint32_t c0 = __ldg(lcode + e), c1 = __ldg(lcode + e + 32);
-        const double* x0 = X + (int64_t)(c0 >> 1) * KP;
-        const double* x1 = X + (int64_t)(c1 >> 1) * KP;
-        double2 t0[KP / 2], t1[KP / 2];
+        const int64_t lb = lptr[row], le = lptr[row + 1];
+        int64_t e = lb + lane;
+        for (; e + 32 < le; e += 64) {  // two independent gathers in flight per lane
+            const uint32_t c0 = __ldg(lcode + e), c1 = __ldg(lcode + e + 32);
+            const double* x0 = X + (int64_t)(c0 >> 1) * KP;
+            const double* x1 = X + (int64_t)(c1 >> 1) * KP;
+            double2 t0[KP / 2], t1[KP / 2];
 #pragma unroll
-        for (int j = 0; j < KP / 2; ++j) { t0[j] = ldg2(x0 + 2 * j); t1[j] = ldg2(x1 + 2 * j); }
+            for (int j = 0; j < KP / 2; ++j) { t0[j] = ldg2(x0 + 2 * j); t1[j] = ldg2(x1 + 2 * j); }
 #pragma unroll
-        for (int j = 0; j < KP / 2; ++j) {
-            acc[2 * j] += t0[j].x; acc[2 * j + 1] += t0[j].y;
-            acc[2 * j] += t1[j].x; acc[2 * j + 1] += t1[j].y;
+            for (int j = 0; j < KP / 2; ++j) {
+                acc[2 * j] += t0[j].x; acc[2 * j + 1] += t0[j].y;
+                acc[2 * j] += t1[j].x; acc[2 * j + 1] += t1[j].y;
+            }
         }
-    }
-    if (e < le) {
-        const uint32_t c0 = __ldg(lcode + e);
-        const double* x0 = X + (int64_t)(c0 >> 1) * KP;
+        if (e < le) {
+            const uint32_t c0 = __ldg(lcode + e);
+            const double* x0 = X + (int64_t)(c0 >> 1) * KP;
 #pragma unroll
-        for (int j = 0; j < KP / 2; ++j) { double2 t = ldg2(x0 + 2 * j); acc[2 * j] += t.x; acc[2 * j + 1] += t.y; }
-    }
-    const int64_t hb = hptr[row], he = hptr[row + 1];
-    for (int64_t h = hb + lane; h < he; h += 32) {
-        const uint32_t c0 = __ldg(hcode + h);
-        const double cnt = (double)__ldg(hcnt + h);
-        const double* x0 = X + (int64_t)(c0 >> 1) * KP;
-#pragma unroll
-        for (int j = 0; j < KP / 2; ++j) {
-            double2 t = ldg2(x0 + 2 * j);
-            acc[2 * j] += cnt * t.x;       // contracted to one DFMA (count is an exact small integer)
-            acc[2 * j + 1] += cnt * t.y;
+            for (int j = 0; j < KP / 2; ++j) { double2 t = ldg2(x0 + 2 * j); acc[2 * j] += t.x; acc[2 * j + 1] += t.y; }
         }
+        const int64_t hb = hptr[row], he = hptr[row + 1];
+        for (int64_t h = hb + lane; h < he; h += 32) {
+            const uint32_t c0 = __ldg(hcode + h);
+            const double cnt = (double)__ldg(hcnt + h);
+            const double* x0 = X + (int64_t)(c0 >> 1) * KP;
+#pragma unroll
+            for (int j = 0; j < KP / 2; ++j) {
+                double2 t = ldg2(x0 + 2 * j);
+                acc[2 * j] += cnt * t.x;       // contracted to one DFMA (count is an exact small integer)
+                acc[2 * j + 1] += cnt * t.y;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < KP; ++k) {
+#pragma unroll
+            for (int o = 16; o; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+        }
+        double* y = Y + row * KP;
+#pragma unroll
+        for (int j = 0; j < KP / 2; ++j)
+            if (lane == j) *reinterpret_cast<double2*>(y + 2 * j) = make_double2(acc[2 * j], acc[2 * j + 1]);
     }
-#pragma unroll
-    for (int k = 0; k < KP; ++k) {
-#pragma unroll
-        for (int o = 16; o; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
-    }
-    double* y = Y + row * KP;
-#pragma unroll
-    for (int j = 0; j < KP / 2; ++j)
-        if (lane == j) *reinterpret_cast<double2*>(y + 2 * j) = make_double2(acc[2 * j], acc[2 * j + 1]);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -372,63 +375,88 @@ __device__ __forceinline__ void update_prior(int r, int K, int KP, const double*
     }
 }
 
-// P = (altW + k_alt) / ((altW + refW) + 1);  T[v] = log2 P, T[V+v] = log2(1 - P)   (scSplit:196, 176-177)
-__device__ __forceinline__ void finalize_rows(int64_t V, int K, int KP, const double* __restrict__ stats, int64_t stats_stride,
-                                              const double* __restrict__ kalt, double* __restrict__ P, double* __restrict__ T, int r) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= V * KP) return;   // (the caller's block still takes part in the block count)
-    const int64_t v = i / KP;
-    const int k = (int)(i - v * KP);
-    const double* S = stats + (int64_t)r * stats_stride;
-    double p = 0.0, lp = 0.0, lq = 0.0;
-    if (k < K) {
-        const double a = S[v * KP + k], rf = S[(V + v) * KP + k];
-        p = (a + kalt[v]) / ((a + rf) + 1.0);
-        lp = log2(p);
-        lq = log2(1.0 - p);
-    }
-    P[((int64_t)r * V + v) * KP + k] = p;
-    if (T) {
-        T[((int64_t)r * 2 * V + v) * KP + k] = lp;
-        T[((int64_t)r * 2 * V + V + v) * KP + k] = lq;
-    }
-}
+// What k_finalize writes besides P: the fp64 log table T and (when the E-step runs in fixed point, estep_q.cuh) its
+// quantised copy Tq with the per-restart "does not fit" flag.
+struct TableOut {
+    double* T = nullptr;          // [R][2V][KP]
+    uint64_t* Tq = nullptr;       // [R][2V][2 * qlanes]
+    int qlanes = 0;
+    double qscale = 0.0;          // 2^F
+    int32_t* qbad = nullptr;      // [R] the table of restart r does not fit the format
+    int32_t* qbad_next = nullptr; // [R] staging of the flag while the blocks of an EM-loop launch are still writing the table
+};
 
-// With `prior` (the EM loop) the LAST block of a restart to finish also runs update_prior (block counter in prior->count,
+constexpr int FIN_THREADS = 256;
+inline int finalize_rows_per_block(int KP) { return FIN_THREADS / KP; }
+
+// P = (altW + k_alt) / ((altW + refW) + 1);  T[v] = log2 P, T[V+v] = log2(1 - P)   (scSplit:196, 176-177)
+// A block owns FIN_THREADS / KP whole SNVs (thread = one (SNV, state)), so that the packed fixed-point rows -- which mix the
+// states of a row into 16-byte lanes -- can be put together from shared memory.  With Pin the probabilities are taken as
+// given (EM start, scs_em_set(SCS_P), post-EM scores) instead of computed from the statistics.
+// With `prior` (the EM loop) the LAST block of a restart to finish also runs update_prior (block counter in prior.count,
 // left at zero again): by then every block has read the stop flag, so a restart that stops NOW still gets this
 // iteration's P (scSplit:155-162: E, M, then the test); `done` skips the restarts that had stopped before this iteration.
-static __global__ void __launch_bounds__(256) k_finalize(int64_t V, int K, int KP, const double* __restrict__ stats, int64_t stats_stride,
-                                                  const double* __restrict__ kalt, double* __restrict__ P, double* __restrict__ T,
-                                                  const int32_t* __restrict__ done, const PriorArgs prior) {
+static __global__ void __launch_bounds__(FIN_THREADS) k_finalize(int64_t V, int K, int KP, const double* __restrict__ stats, int64_t stats_stride,
+                                                          const double* __restrict__ kalt, const double* __restrict__ Pin,
+                                                          double* __restrict__ P, const TableOut out,
+                                                          const int32_t* __restrict__ done, const PriorArgs prior) {
+    __shared__ double s_l[2][FIN_THREADS];
     const int r = blockIdx.y;
     if (done && done[r]) return;
-    finalize_rows(V, K, KP, stats, stats_stride, kalt, P, T, r);
+    const int rpb = FIN_THREADS / KP;
+    const int64_t v0 = (int64_t)blockIdx.x * rpb;
+    const int rl = threadIdx.x / KP, k = threadIdx.x - rl * KP;
+    const int64_t v = v0 + rl;
+    double lp = 0.0, lq = 0.0;
+    if (rl < rpb && v < V) {
+        double p = 0.0;
+        if (k < K) {
+            if (Pin) {
+                p = Pin[((int64_t)r * V + v) * KP + k];
+            } else {
+                const double* S = stats + (int64_t)r * stats_stride;
+                const double a = S[v * KP + k], rf = S[(V + v) * KP + k];
+                p = (a + kalt[v]) / ((a + rf) + 1.0);
+            }
+            lp = log2(p);
+            lq = log2(1.0 - p);
+        }
+        if (P) P[((int64_t)r * V + v) * KP + k] = p;
+        if (out.T) {
+            out.T[((int64_t)r * 2 * V + v) * KP + k] = lp;
+            out.T[((int64_t)r * 2 * V + V + v) * KP + k] = lq;
+        }
+    }
+    if (out.Tq) {                                        // (uniform over the grid)
+        if (threadIdx.x < rpb * KP) { s_l[0][threadIdx.x] = lp; s_l[1][threadIdx.x] = lq; }
+        __syncthreads();
+        const int QL = out.qlanes;
+        bool bad = false;
+        for (int o = threadIdx.x; o < rpb * 2 * QL; o += FIN_THREADS) {
+            const int row = o / (2 * QL), rem = o - row * 2 * QL, sel = rem / QL, j = rem - sel * QL;
+            if (v0 + row >= V) continue;
+            const double* l = s_l[sel] + row * KP;
+            const int ka = 2 * j, kb = 2 * j + 1, kx = 2 * QL;
+            const uint64_t a = ka < K ? q_quant(l[ka], out.qscale, &bad) : 0ull;
+            const uint64_t b = kb < K ? q_quant(l[kb], out.qscale, &bad) : 0ull;
+            const uint64_t x = (kx < K && j < 4) ? q_quant(l[kx], out.qscale, &bad) : 0ull;
+            uint4* dst = reinterpret_cast<uint4*>(out.Tq + (((int64_t)r * 2 + sel) * V + v0 + row) * (2 * QL)) + j;
+            *dst = q_pack_lane(a, b, x, j);
+        }
+        if (bad) (prior.lps ? out.qbad_next : out.qbad)[r] = 1;
+    }
     if (prior.lps) {
         __threadfence();
         __syncthreads();
         if (threadIdx.x == 0 && atomicAdd(prior.count + r, 1) == (int)gridDim.x - 1) {
             prior.count[r] = 0;
+            if (out.Tq) {                                // every block has written its part of the table: publish its flag
+                out.qbad[r] = *reinterpret_cast<volatile int32_t*>(out.qbad_next + r);
+                out.qbad_next[r] = 0;
+            }
             update_prior(r, K, KP, stats, stats_stride, prior);
         }
     }
-}
-
-
-// log tables from a given P (EM start, scs_em_set(SCS_P), post-EM scores)
-static __global__ void __launch_bounds__(256) k_tables_from_P(int64_t V, int K, int KP, const double* __restrict__ P, double* __restrict__ T) {
-    const int r = blockIdx.y;
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= V * KP) return;
-    const int64_t v = i / KP;
-    const int k = (int)(i - v * KP);
-    double lp = 0.0, lq = 0.0;
-    if (k < K) {
-        const double p = P[((int64_t)r * V + v) * KP + k];
-        lp = log2(p);
-        lq = log2(1.0 - p);
-    }
-    T[((int64_t)r * 2 * V + v) * KP + k] = lp;
-    T[((int64_t)r * 2 * V + V + v) * KP + k] = lq;
 }
 
 }  // namespace scs

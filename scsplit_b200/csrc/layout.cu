@@ -12,6 +12,7 @@
 #include <cstdlib>
 
 #include "common.cuh"
+#include "estep_q.cuh"
 
 namespace scs {
 
@@ -178,14 +179,20 @@ static int stable_sort_by_cell(scs_ctx* ctx, const uint32_t* kin, uint32_t* kout
 }
 
 // ---- job order of the sparse M-step: pseudo-rows by descending length (stable, so ties keep their index order)
-static __global__ void k_row_len_keys(int64_t nrows, const int64_t* __restrict__ lptr, uint32_t* __restrict__ key, int32_t* __restrict__ val) {
+static __global__ void k_row_len_keys(int64_t nrows, int nchunks, const int64_t* __restrict__ lptr, uint32_t* __restrict__ key,
+                                      int32_t* __restrict__ val) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nrows) return;
-    key[i] = 0xffffffffu - (uint32_t)min((int64_t)0xffffffffLL, lptr[i + 1] - lptr[i]);
+    if (nchunks <= 1) {
+        key[i] = 0xffffffffu - (uint32_t)min((int64_t)0xffffffffLL, lptr[i + 1] - lptr[i]);
+    } else {          // chunk in the top 4 bits, inverted length below: rows of a chunk stay together, longest first
+        const uint32_t chunk = (uint32_t)(i * nchunks / nrows);
+        key[i] = (chunk << 28) | (0x0fffffffu - (uint32_t)min((int64_t)0x0fffffffLL, lptr[i + 1] - lptr[i]));
+    }
     val[i] = (int32_t)i;
 }
 
-int build_row_order(scs_ctx* ctx, const Stream& s, int32_t** order) {
+int build_row_order(scs_ctx* ctx, const Stream& s, int32_t** order, int nchunks) {
     const int64_t n = s.nrows;
     uint32_t *kin = nullptr, *kout = nullptr;
     int32_t *vin = nullptr, *vout = nullptr;
@@ -195,7 +202,7 @@ int build_row_order(scs_ctx* ctx, const Stream& s, int32_t** order) {
         SCS_TRY(dev_alloc(ctx, &kout, n));
         SCS_TRY(dev_alloc(ctx, &vin, n));
         SCS_TRY(dev_alloc(ctx, &vout, n));
-        k_row_len_keys<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(n, s.lptr, kin, vin);
+        k_row_len_keys<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(n, nchunks, s.lptr, kin, vin);
         size_t tb = 0;
         SCS_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, kin, kout, vin, vout, n, 0, 32, ctx->stream));
         SCS_CUDA(cudaMallocAsync(&tmp, tb ? tb : 1, ctx->stream));
@@ -481,6 +488,192 @@ int build_tiled(scs_ctx* ctx, const Stream& s, TiledStream& t, int KP, int TR, i
         ctx->launches += 2;
     }
     SCS_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ---- tile-major stream of the fixed-point E-step (estep_q.cuh) --------------------------------------------------
+// unit u = tile * nrows + row holds one 16-bit code (the in-tile row) per read of the row's entries inside the tile --
+// an entry of count c <= Q_REP_MAX is written c times, larger counts are left to the combine kernel -- padded to a
+// multiple of Q_UNIT_PAD codes.  Integer sums: the order inside a unit is free.  The codes are packed into the kernel's 32-bit words
+// of two (QCode) as the last step.
+
+__device__ __forceinline__ int64_t q_codes_of(int64_t c) { return c <= Q_REP_MAX ? c : 0; }
+
+// one thread per unit: padded code count, where the unit's light / heavy entries start inside the row
+__global__ void k_qunit_counts(int64_t nrows, int ntiles, int TR, const int64_t* __restrict__ lptr, const uint32_t* __restrict__ lcode,
+                               const int64_t* __restrict__ hptr, const uint32_t* __restrict__ hcode, const int32_t* __restrict__ hcnt,
+                               int64_t* __restrict__ cnt, int32_t* __restrict__ ulo, int32_t* __restrict__ uho) {
+    const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= nrows * ntiles) return;
+    const int64_t t = u / nrows, row = u - t * nrows;
+    const int64_t b = lptr[row], e = lptr[row + 1], hb = hptr[row], he = hptr[row + 1];
+    const int64_t lo = row_lower_bound(lcode, b, e, t * TR), hi = row_lower_bound(lcode, b, e, (t + 1) * (int64_t)TR);
+    const int64_t hlo = row_lower_bound(hcode, hb, he, t * TR), hhi = row_lower_bound(hcode, hb, he, (t + 1) * (int64_t)TR);
+    int64_t n = hi - lo;
+    for (int64_t h = hlo; h < hhi; ++h) n += q_codes_of(hcnt[h]);
+    cnt[u] = (n + Q_UNIT_PAD - 1) / Q_UNIT_PAD * Q_UNIT_PAD;
+    ulo[u] = (int32_t)(lo - b);
+    uho[u] = (int32_t)(hlo - hb);
+}
+// one thread per row: total reads of the row (a cell's depth bounds its whole sum)
+__global__ void k_qrow_depth(int64_t nrows, const int64_t* __restrict__ lptr, const int64_t* __restrict__ hptr, const int32_t* __restrict__ hcnt,
+                             unsigned long long* __restrict__ maxdepth) {
+    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= nrows) return;
+    int64_t d = lptr[row + 1] - lptr[row];
+    for (int64_t h = hptr[row]; h < hptr[row + 1]; ++h) d += hcnt[h];
+    if ((unsigned long long)d > *maxdepth) atomicMax(maxdepth, (unsigned long long)d);
+}
+// one warp per row: light entries by the warp, then lane = tile for the repeated codes of the heavy entries and the padding
+__global__ void k_qtile_scatter(int64_t nrows, int ntiles, int TR, const int64_t* __restrict__ lptr, const uint32_t* __restrict__ lcode,
+                                const int64_t* __restrict__ hptr, const uint32_t* __restrict__ hcode, const int32_t* __restrict__ hcnt,
+                                const int64_t* __restrict__ tptr, const int32_t* __restrict__ ulo, const int32_t* __restrict__ uho,
+                                uint16_t* __restrict__ tcode) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= nrows) return;
+    const int64_t b = lptr[row], e = lptr[row + 1], hb = hptr[row], he = hptr[row + 1];
+    for (int64_t i = b + lane; i < e; i += 32) {
+        const int64_t g = (int64_t)(lcode[i] >> 1);
+        const int64_t t = g / TR;
+        const int64_t u = t * nrows + row;
+        tcode[tptr[u] + (i - b - ulo[u])] = (uint16_t)(g - t * TR);
+    }
+    for (int64_t t = lane; t < ntiles; t += 32) {
+        const int64_t u = t * nrows + row, end = tptr[u + 1];
+        const bool last = t + 1 >= ntiles;
+        int64_t pos = tptr[u] + ((last ? e - b : (int64_t)ulo[u + nrows]) - ulo[u]);
+        const int64_t h1 = hb + (last ? he - hb : (int64_t)uho[u + nrows]);
+        for (int64_t h = hb + uho[u]; h < h1; ++h) {
+            const uint16_t rowt = (uint16_t)((int64_t)(hcode[h] >> 1) - t * TR);
+            for (int64_t c = q_codes_of(hcnt[h]); c > 0; --c) tcode[pos++] = rowt;
+        }
+        for (; pos < end; ++pos) tcode[pos] = (uint16_t)TR;
+    }
+}
+// Order inside the units for 64-byte rows: two row groups share a quarter-warp wavefront, conflict-free when their rows lie
+// in different halves of the 128 bytes, i.e. differ in parity.  Position p of a unit whose phase is ph gets, wherever the
+// unit has one, a row of parity (ph + p) & 1 -- neighbouring groups have opposite phases.  One lane orders one unit, staged
+// in shared memory like k_order_units.
+__global__ void __launch_bounds__(ORDER_WARPS * 32) k_qorder_units(const int64_t* __restrict__ tptr, uint16_t* __restrict__ tcode,
+                                                                  const uint8_t* __restrict__ phase, int64_t nunits, int upw) {
+    __shared__ __align__(16) uint16_t s_in[ORDER_WARPS][ORDER_CAP], s_out[ORDER_WARPS][ORDER_CAP];
+    const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
+    const int64_t U0 = ((int64_t)blockIdx.x * ORDER_WARPS + wl) * upw;
+    if (U0 >= nunits) return;
+    const int64_t Uend = min(U0 + upw, nunits);
+    const int64_t Ul = min(U0 + lane, Uend - 1);
+    const int64_t e0 = tptr[U0], e1 = tptr[Uend];
+    const int len = (int)min(e1 - e0, (int64_t)ORDER_CAP + 1);
+    if (len < 2 || len > ORDER_CAP) return;                           // (over-long ranges keep their natural order)
+    const int ua = (int)(tptr[Ul] - e0), n = (U0 + lane < Uend) ? (int)(tptr[Ul + 1] - tptr[Ul]) : 0;
+    const int ph = phase[Ul] & 1;
+    uint16_t* in = s_in[wl];
+    uint16_t* out = s_out[wl];
+    for (int i = lane; i < len / 2; i += 32)
+        reinterpret_cast<uint32_t*>(in)[i] = reinterpret_cast<const uint32_t*>(tcode + e0)[i];
+    __syncwarp();
+    int i0 = 0, i1 = 0;                                               // next unread code of parity 0 / 1
+    for (int p = 0; p < n; ++p) {
+        while (i0 < n && (in[ua + i0] & 1u) != 0u) ++i0;
+        while (i1 < n && (in[ua + i1] & 1u) != 1u) ++i1;
+        const int want = (ph + p) & 1;
+        int src;
+        if (want == 0) { if (i0 < n) src = i0++; else src = i1++; }
+        else           { if (i1 < n) src = i1++; else src = i0++; }
+        out[ua + p] = in[ua + src];
+    }
+    __syncwarp();
+    for (int i = lane; i < len / 2; i += 32)
+        reinterpret_cast<uint32_t*>(tcode + e0)[i] = reinterpret_cast<const uint32_t*>(out)[i];
+}
+// codes (pairs of 16-bit rows) -> stream words, in place
+template <int LANES>
+__global__ void k_qpack_words(int64_t nwords, uint32_t* __restrict__ w) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nwords) return;
+    const uint32_t x = w[i];
+    w[i] = QCode<LANES>::word(x & 0xffffu, x >> 16);
+}
+
+int build_qtiled(scs_ctx* ctx, const Stream& s, TiledStream& t, int lanes, int TR, int ncta, int ngroups, int* F, int* ok) {
+    free_tiled(ctx, t);
+    *ok = 0;
+    SCS_CHECK(ncta >= 1 && ncta <= 1024, "work plan supports 1..1024 CTAs (got %d)", ncta);
+    cudaStream_t st = ctx->stream;
+    const int ntiles = (int)((s.xrows + TR - 1) / TR);
+    const int64_t nunits = (int64_t)ntiles * s.nrows;
+    Scratch tmps(st);
+    int32_t *d_ulo = nullptr, *d_uho = nullptr;
+    unsigned long long* d_max = nullptr;
+    int64_t* tptr = nullptr;
+    SCS_TRY(tmps.get(&d_ulo, nunits));
+    SCS_TRY(tmps.get(&d_uho, nunits));
+    SCS_TRY(tmps.get(&d_max, 1));
+    SCS_CUDA(cudaMemsetAsync(d_max, 0, 8, st));
+    SCS_TRY(dev_alloc(ctx, &tptr, nunits + 1));
+    t.tptr = tptr;                                       // (free_tiled releases it on every path from here)
+    SCS_CUDA(cudaMemsetAsync(tptr, 0, sizeof(int64_t), st));
+    k_qunit_counts<<<(unsigned)((nunits + 255) / 256), 256, 0, st>>>(s.nrows, ntiles, TR, s.lptr, s.lcode, s.hptr, s.hcode, s.hcnt, tptr + 1,
+                                                                      d_ulo, d_uho);
+    k_qrow_depth<<<(unsigned)((s.nrows + 255) / 256), 256, 0, st>>>(s.nrows, s.lptr, s.hptr, s.hcnt, d_max);
+    ctx->launches += 2;
+    unsigned long long h_max = 0;
+    SCS_CUDA(cudaMemcpyAsync(&h_max, d_max, 8, cudaMemcpyDeviceToHost, st));
+    SCS_CUDA(cudaStreamSynchronize(st));
+    *F = h_max < (1ull << 40) ? q_frac_bits((int64_t)h_max) : 0;
+    if (*F < Q_MIN_F) {                                  // cells too deep for a useful fraction: fp64 keeps the E-step
+        free_tiled(ctx, t);
+        return 0;
+    }
+    size_t tb = 0;
+    SCS_CUDA(cub::DeviceScan::InclusiveSum(nullptr, tb, tptr + 1, tptr + 1, nunits, st));
+    void* tmp = nullptr;
+    SCS_TRY(tmps.get_bytes(&tmp, tb));
+    SCS_CUDA(cub::DeviceScan::InclusiveSum(tmp, tb, tptr + 1, tptr + 1, nunits, st));
+    ctx->launches += 2;
+    int64_t total = 0;
+    SCS_CUDA(cudaMemcpyAsync(&total, tptr + nunits, 8, cudaMemcpyDeviceToHost, st));
+    SCS_CUDA(cudaStreamSynchronize(st));
+    t.KP = lanes;
+    t.TR = TR;
+    t.ntiles = ntiles;
+    t.nunits = nunits;
+    SCS_TRY(dev_alloc(ctx, &t.tcode, total + 64));
+    k_qtile_scatter<<<(unsigned)((s.nrows + 7) / 8), 256, 0, st>>>(s.nrows, ntiles, TR, s.lptr, s.lcode, s.hptr, s.hcode, s.hcnt, tptr, d_ulo, d_uho,
+                                                                    t.tcode);
+    ctx->launches++;
+    t.ncta = ncta;
+    t.ngroups = ngroups;
+    t.nseg = ncta + ntiles;
+    int64_t *d_cu = nullptr, *d_lo = nullptr, *d_hi = nullptr;
+    SCS_TRY(tmps.get(&d_cu, ncta + 1));
+    SCS_TRY(tmps.get(&d_lo, t.nseg));
+    SCS_TRY(tmps.get(&d_hi, t.nseg));
+    SCS_TRY(dev_alloc(ctx, &t.seg_ptr, ncta + 1));
+    SCS_TRY(dev_alloc(ctx, &t.seg_tile, t.nseg));
+    SCS_TRY(dev_alloc(ctx, &t.gb, (int64_t)t.nseg * (ngroups + 1)));
+    k_plan_ctas<<<(ncta + 1 + 127) / 128, 128, 0, st>>>(tptr, nunits, ncta, d_cu);
+    k_plan_segments<<<1, 1024, 0, st>>>(d_cu, ncta, s.nrows, t.nseg, t.seg_ptr, t.seg_tile, d_lo, d_hi);
+    k_plan_groups<<<t.nseg, 256, 0, st>>>(tptr, d_lo, d_hi, ngroups, t.gb);
+    ctx->launches += 3;
+    if (lanes == 4 && !std::getenv("SCS_Q_NO_ORDER")) {
+        uint8_t* d_phase = nullptr;
+        SCS_TRY(tmps.get(&d_phase, nunits));
+        SCS_CUDA(cudaMemsetAsync(d_phase, 0, (size_t)nunits, st));
+        const int64_t runs = (int64_t)t.nseg * ngroups;
+        k_unit_phase<<<(unsigned)((runs + 255) / 256), 256, 0, st>>>(tptr, t.gb, ngroups, 32 / lanes, t.nseg, d_phase);
+        const int64_t avg = std::max<int64_t>(2, (total + nunits) / std::max<int64_t>(nunits, 1));
+        const int upw = (int)std::min<int64_t>(32, std::max<int64_t>(1, (int64_t)ORDER_CAP * 2 / 3 / avg));
+        const int64_t owarps = (nunits + upw - 1) / upw;
+        k_qorder_units<<<(unsigned)((owarps + ORDER_WARPS - 1) / ORDER_WARPS), ORDER_WARPS * 32, 0, st>>>(tptr, t.tcode, d_phase, nunits, upw);
+        ctx->launches += 2;
+    }
+    if (lanes == 4) k_qpack_words<4><<<(unsigned)((total / 2 + 255) / 256), 256, 0, st>>>(total / 2, reinterpret_cast<uint32_t*>(t.tcode));
+    else k_qpack_words<8><<<(unsigned)((total / 2 + 255) / 256), 256, 0, st>>>(total / 2, reinterpret_cast<uint32_t*>(t.tcode));
+    ctx->launches++;
+    SCS_CUDA(cudaGetLastError());
+    *ok = 1;
     return 0;
 }
 

@@ -95,7 +95,7 @@ __device__ __forceinline__ void dense_add(uint32_t acc_base, int K, int64_t cell
 // Which warp sums a row never changes the order inside the row, so the result is the same bits on every run.
 template <int KP>
 __global__ void __launch_bounds__(SPARSE_THREADS, 1)
-k_mstep_sparse(int64_t nrows, int64_t N, int K, const int32_t* __restrict__ order, const int64_t* __restrict__ lptr,
+k_mstep_sparse(int64_t nrows, int64_t njobs, int64_t N, int K, const int32_t* __restrict__ order, const int64_t* __restrict__ lptr,
                const uint32_t* __restrict__ lcode,
                const int64_t* __restrict__ hptr, const uint32_t* __restrict__ hcode, const int32_t* __restrict__ hcnt,
                const uint32_t* __restrict__ hq, int64_t h_stride, const double* __restrict__ W, double* __restrict__ S,
@@ -135,7 +135,7 @@ k_mstep_sparse(int64_t nrows, int64_t N, int K, const int32_t* __restrict__ orde
 #define SCS_SPARSE_UV 2
 #endif
     constexpr int UV = SCS_SPARSE_UV;
-    const int npairs = (int)((nrows + GPW - 1) / GPW);
+    const int npairs = (int)((njobs + GPW - 1) / GPW);    // `order` lists the njobs pseudo-rows of this launch
     const uint32_t nop_code = (uint32_t)h_stride << 1;               // code whose table word is SPARSE_NOP
     // A row (pair) is a short job (a few hundred entries), so the chain ticket -> row bounds -> first codes is software-
     // pipelined across rows: the ticket is drawn two rows ahead, the bounds are loaded one row ahead, and the first code
@@ -151,7 +151,7 @@ k_mstep_sparse(int64_t nrows, int64_t N, int K, const int32_t* __restrict__ orde
         // lengths, so the groups of a warp finish together) and the longest rows are drawn first
         RowJob j;
         const int64_t idx = (int64_t)ticket * GPW + g;
-        j.row = (ticket < npairs && idx < nrows) ? (int64_t)__ldg(order + idx) : nrows;
+        j.row = (ticket < npairs && idx < njobs) ? (int64_t)__ldg(order + idx) : nrows;
         const bool act = j.row < nrows;
         j.lb = act ? __ldg(lptr + j.row) : 0;
         j.n = act ? (int)(__ldg(lptr + j.row + 1) - j.lb) : 0;

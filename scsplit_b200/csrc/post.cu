@@ -186,8 +186,9 @@ int scs_seed_af(scs_ctx* ctx, int R, int K, const int32_t* labels, double* P0_ou
     ctx->launches++;
     SCS_TRY(launch_spmm(ctx, 1, KP, R, d_W, N * KP, d_S, stride, nullptr));
     if (ctx->world > 1) SCS_TRY(comm_allreduce_f64(ctx, d_S, (int64_t)R * stride));
-    dim3 grid((unsigned)((V * KP + 255) / 256), (unsigned)R);
-    k_finalize<<<grid, 256, 0, st>>>(V, K, KP, d_S, stride, ctx->kalt, d_P, nullptr, nullptr, PriorArgs{});
+    const int rpb = finalize_rows_per_block(KP);
+    dim3 grid((unsigned)((V + rpb - 1) / rpb), (unsigned)R);
+    k_finalize<<<grid, FIN_THREADS, 0, st>>>(V, K, KP, d_S, stride, ctx->kalt, nullptr, d_P, TableOut{}, nullptr, PriorArgs{});
     ctx->launches++;
     SCS_TRY(download_pitched(ctx, P0_out, d_P, (int64_t)R * V, K, KP));
     SCS_CUDA(cudaStreamSynchronize(st));
@@ -243,8 +244,11 @@ int scs_doublet_scores(scs_ctx* ctx, int K, const double* P, const uint8_t* mask
     SCS_TRY(s.get(&d_mask, N));
     SCS_TRY(upload_pitched(ctx, d_P, P, V, K, KP));
     SCS_CUDA(cudaMemcpyAsync(d_mask, mask, (size_t)N, cudaMemcpyHostToDevice, st));
-    dim3 grid((unsigned)((V * KP + 255) / 256), 1);
-    k_tables_from_P<<<grid, 256, 0, st>>>(V, K, KP, d_P, d_T);
+    const int rpb = finalize_rows_per_block(KP);
+    dim3 grid((unsigned)((V + rpb - 1) / rpb), 1);
+    TableOut tab;
+    tab.T = d_T;
+    k_finalize<<<grid, FIN_THREADS, 0, st>>>(V, K, KP, nullptr, 0, nullptr, d_P, nullptr, tab, nullptr, PriorArgs{});
     ctx->launches++;
     SCS_TRY(launch_spmm(ctx, 0, KP, 1, d_T, 2 * V * KP, d_L, N * KP, nullptr));
     SCS_DISPATCH_KP2(KP, (k_masked_colsum<KPc><<<nblk, CELL_BLOCK, 0, st>>>(N, d_L, d_mask, d_part)));

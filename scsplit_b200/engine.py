@@ -152,6 +152,12 @@ class Engine:
         check(self.lib.scs_em_status(self.h, _ptr(it), _ptr(cv), _ptr(ll)))
         return it, cv, ll
 
+    def em_info(self):
+        """How the E-step of the current EM state runs (fixed-point row lanes, fraction bits, tiles, restarts on the fp64 stand-in)."""
+        out = (ctypes.c_int64 * 4)()
+        check(self.lib.scs_em_info(self.h, out))
+        return dict(q_lanes=int(out[0]), q_frac_bits=int(out[1]), tiles=int(out[2]), q_unfit_restarts=int(out[3]))
+
     def _shape(self, what):
         return {SCS_P: (self.V, self.K), SCS_W: (self.N, self.K), SCS_L: (self.N, self.K), SCS_LPS: (self.K,),
                 SCS_LLHIST: (self.max_iter,)}[what]
@@ -225,9 +231,9 @@ class Engine:
         check(self.lib.scs_set_timing(self.h, int(every) if on else 0))
 
     def kernel_times(self, reset=False):
-        out = (ctypes.c_double * 4)()
+        out = (ctypes.c_double * 6)()
         check(self.lib.scs_kernel_times(self.h, out, 1 if reset else 0))
-        return dict(e_us=out[0], m_us=out[1], e_n=int(out[2]), m_n=int(out[3]))
+        return dict(e_us=out[0], m_us=out[1], e_n=int(out[2]), m_n=int(out[3]), allreduce_us=out[4], allreduce_n=int(out[5]))
 
     def set_variant(self, v):
         check(self.lib.scs_set_variant(self.h, int(v)))

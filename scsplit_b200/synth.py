@@ -64,49 +64,67 @@ def make_genotypes(V, samples, seed):
     return rng.choice(np.array([0.01, 0.5, 0.99]), size=(V, samples), p=[0.5, 0.3, 0.2])
 
 
+def _gen_block(args):
+    """Non-zero depths of one BLOCK of cells: (SNV rows, local cell columns, alt, ref, truth, truth2, doublet flags, index range)."""
+    b, V, N, samples, doublet_frac, lam, seed, cell_lo, cell_hi = args
+    G = make_genotypes(V, samples, seed)
+    rho = 1.0 - np.exp(-lam)
+    lo, hi = b * BLOCK, min((b + 1) * BLOCK, N)
+    nb = hi - lo
+    rng = np.random.default_rng([seed, b])
+    s1 = rng.integers(0, samples, nb)
+    s2 = (s1 + 1 + rng.integers(0, max(samples - 1, 1), nb)) % samples
+    dbl = rng.random(nb) < doublet_frac
+    # iid Bernoulli(rho) over the nb*V linearised (cell-major) positions via geometric gaps
+    total = nb * V
+    m = int(total * rho + 8 * np.sqrt(total * rho) + 64)
+    pos = np.cumsum(rng.geometric(rho, m)) - 1
+    while pos[-1] < total:
+        extra = np.cumsum(rng.geometric(rho, m)) + pos[-1]
+        pos = np.concatenate([pos, extra])
+    pos = pos[pos < total]
+    c_loc = pos // V
+    v = pos - c_loc * V
+    depth = _truncated_poisson(rng, lam, pos.size)
+    p = G[v, s1[c_loc]]
+    pd2 = 0.5 * (G[v, s1[c_loc]] + G[v, s2[c_loc]])
+    p = np.where(dbl[c_loc], pd2, p)
+    a = rng.binomial(depth, p)
+    r = depth - a
+    keep = (lo + c_loc >= cell_lo) & (lo + c_loc < cell_hi)
+    sel = (np.arange(lo, hi) >= cell_lo) & (np.arange(lo, hi) < cell_hi)
+    idx = np.arange(lo, hi)[sel] - cell_lo
+    return (v[keep].astype(np.int32), (lo + c_loc[keep] - cell_lo).astype(np.int32), a[keep].astype(np.int16), r[keep].astype(np.int16),
+            s1[sel], s2[sel], dbl[sel], idx)
+
+
 def make_pool(V, N, samples, doublet_frac=0.05, lam=0.05, seed=0, cell_lo=0, cell_hi=None,
-              dtype=np.int16):
-    """Return a Pool for cells [cell_lo, cell_hi) of a V x N experiment (SNV-major CSR, V x n)."""
+              dtype=np.int16, workers=1):
+    """Return a Pool for cells [cell_lo, cell_hi) of a V x N experiment (SNV-major CSR, V x n).
+
+    workers > 1 samples the blocks of cells in that many threads (every block has its own seed, so the result is the same)."""
     cell_hi = N if cell_hi is None else cell_hi
     assert 0 <= cell_lo <= cell_hi <= N
     G = make_genotypes(V, samples, seed)
-    rho = 1.0 - np.exp(-lam)
     rows_l, cols_l, alt_l, ref_l = [], [], [], []
     truth = np.zeros(cell_hi - cell_lo, dtype=np.int32)
     truth2 = np.zeros(cell_hi - cell_lo, dtype=np.int32)
     isdbl = np.zeros(cell_hi - cell_lo, dtype=bool)
     b0, b1 = cell_lo // BLOCK, (max(cell_hi, 1) - 1) // BLOCK
-    for b in range(b0, b1 + 1):
-        lo, hi = b * BLOCK, min((b + 1) * BLOCK, N)
-        nb = hi - lo
-        rng = np.random.default_rng([seed, b])
-        s1 = rng.integers(0, samples, nb)
-        s2 = (s1 + 1 + rng.integers(0, max(samples - 1, 1), nb)) % samples
-        dbl = rng.random(nb) < doublet_frac
-        # iid Bernoulli(rho) over the nb*V linearised (cell-major) positions via geometric gaps
-        total = nb * V
-        m = int(total * rho + 8 * np.sqrt(total * rho) + 64)
-        pos = np.cumsum(rng.geometric(rho, m)) - 1
-        while pos[-1] < total:
-            extra = np.cumsum(rng.geometric(rho, m)) + pos[-1]
-            pos = np.concatenate([pos, extra])
-        pos = pos[pos < total]
-        c_loc = pos // V
-        v = pos - c_loc * V
-        depth = _truncated_poisson(rng, lam, pos.size)
-        p = G[v, s1[c_loc]]
-        pd2 = 0.5 * (G[v, s1[c_loc]] + G[v, s2[c_loc]])
-        p = np.where(dbl[c_loc], pd2, p)
-        a = rng.binomial(depth, p)
-        r = depth - a
-        keep = (lo + c_loc >= cell_lo) & (lo + c_loc < cell_hi)
-        rows_l.append(v[keep])
-        cols_l.append(lo + c_loc[keep] - cell_lo)
-        alt_l.append(a[keep])
-        ref_l.append(r[keep])
-        sel = (np.arange(lo, hi) >= cell_lo) & (np.arange(lo, hi) < cell_hi)
-        idx = np.arange(lo, hi)[sel] - cell_lo
-        truth[idx], truth2[idx], isdbl[idx] = s1[sel], s2[sel], dbl[sel]
+    jobs = [(b, V, N, samples, doublet_frac, lam, seed, cell_lo, cell_hi) for b in range(b0, b1 + 1)]
+    if workers > 1 and len(jobs) > 1:
+        # threads, not processes: the numpy samplers release the GIL on these array sizes, and the caller may hold a CUDA context
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(min(workers, len(jobs))) as pool:
+            blocks = list(pool.map(_gen_block, jobs))
+    else:
+        blocks = map(_gen_block, jobs)
+    for v, c, a, r, s1, s2, dbl, idx in blocks:
+        rows_l.append(v)
+        cols_l.append(c)
+        alt_l.append(a)
+        ref_l.append(r)
+        truth[idx], truth2[idx], isdbl[idx] = s1, s2, dbl
     rows = np.concatenate(rows_l)
     cols = np.concatenate(cols_l)
     a = np.concatenate(alt_l)
@@ -125,14 +143,14 @@ def make_pool(V, N, samples, doublet_frac=0.05, lam=0.05, seed=0, cell_lo=0, cel
     return Pool(to_csr(r), to_csr(a), snv_ids(V), barcodes(cell_lo, cell_hi), truth, isdbl, G)
 
 
-def make_config(name, lam=0.05, cell_lo=0, cell_hi=None, V=None, N=None):
+def make_config(name, lam=0.05, cell_lo=0, cell_hi=None, V=None, N=None, workers=1):
     cfg = dict(CONFIGS[name])
     if V is not None:
         cfg["V"] = V
     if N is not None:
         cfg["N"] = N
     return make_pool(cfg["V"], cfg["N"], cfg["samples"], cfg["doublet_frac"], lam, cfg["seed"],
-                     cell_lo, cell_hi)
+                     cell_lo, cell_hi, workers=workers)
 
 
 def union_nnz(ref, alt):

@@ -1,0 +1,193 @@
+"""GPU tests of the fixed-point E-step (csrc/estep_q.cuh) through the C-ABI.
+
+The E-step sums L[c,k] = sum_v A[v,c] log2 P[v,k] + R[v,c] log2(1-P[v,k]) (scSplit:175-178) run, by default, on a
+55-bit fixed-point copy of the log table with exact integer accumulation.  These tests pin that path against
+  * the fp64 kernels of the same library (variant 3) and the numpy oracle, at the north-star tolerance (1e-9 relative),
+  * sums of the same table values in extended precision (np.longdouble), to show that the fixed-point path is at least as
+    close to the exact sums as fp64 accumulation is,
+and exercise its edges: counts above 1 (repeated codes up to 8, fp64 leftovers beyond), every row width (K <= 9: 64-byte rows, K <= 17: 128-byte rows,
+K > 17: fp64), tables that do not fit the format (NaN / -inf: per-restart fp64 stand-in), pools the format cannot hold.
+"""
+import numpy as np
+import pytest
+
+from conftest import assert_close, load_golden
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-9
+
+
+@pytest.fixture(scope="module")
+def E():
+    from scsplit_b200 import _lib
+    if _lib.device_count() < 1:
+        pytest.fail("no CUDA device visible: the gpu-marked tests must run on the B200 box")
+    from scsplit_b200.engine import Engine
+    return Engine
+
+
+def _random_P(V, K, seed):
+    rng = np.random.default_rng(seed)
+    P = rng.choice([0.01, 0.5, 0.99, 1e-5, 0.3], size=(V, K), p=[0.3, 0.3, 0.2, 0.05, 0.15])
+    return P * rng.uniform(0.9, 1.0, size=(V, K))
+
+
+def _estep(E, pool, P, variant):
+    from scsplit_b200._lib import SCS_L, SCS_W
+    with E(pool.ref, pool.alt) as eng:
+        eng.set_variant(variant)
+        eng.em_begin(P)
+        info = eng.em_info()
+        eng.estep()
+        return eng.get(SCS_L), eng.get(SCS_W), eng.stats()["ll"], info
+
+
+@pytest.mark.parametrize("K", [1, 2, 5, 8, 9, 10, 16, 17, 18])
+def test_fixed_point_estep_matches_fp64_and_oracle(K, E):
+    from oracle import em_oracle as O
+    from scsplit_b200 import synth
+    pool = synth.make_pool(3000, 700, max(K - 1, 1), 0.05 if K > 2 else 0.0, 0.08, seed=300 + K)
+    P = _random_P(3000, K, K)
+    Lq, Wq, llq, info = _estep(E, pool, P, 0)
+    Lf, Wf, llf, info_f = _estep(E, pool, P, 3)
+    assert info_f["q_lanes"] == 0
+    assert info["q_lanes"] == (4 if K <= 9 else 8 if K <= 17 else 0), info
+    if info["q_lanes"]:
+        assert 40 <= info["q_frac_bits"] <= 49, info
+    L_o = O.loglik_matrix(pool.ref, pool.alt, P)
+    assert_close(Lq, L_o, RTOL, "L fixed point vs oracle K=%d" % K)
+    assert_close(Lq, Lf, 1e-12, "L fixed point vs fp64 kernels K=%d" % K)
+    assert_close(llq, llf, 1e-11, "LL K=%d" % K)
+    assert np.array_equal(Wq >= 0.99, Wf >= 0.99)
+
+
+def test_fixed_point_sums_are_closer_to_exact_than_fp64(E):
+    """Extended-precision sums of the table values are the yardstick: the fixed-point path may be off by at most
+    depth * 2^-(F+1) per cell (its only error is the table quantisation), and must not be worse than fp64 accumulation."""
+    from scsplit_b200 import synth
+    V, N, K = 6000, 400, 9
+    pool = synth.make_pool(V, N, 8, 0.05, 0.25, seed=77)           # ~1500 reads per cell
+    P = _random_P(V, K, 5)
+    Lq, _, _, info = _estep(E, pool, P, 0)
+    Lf, _, _, _ = _estep(E, pool, P, 3)
+    F = info["q_frac_bits"]
+    lp, lq = np.log2(P).astype(np.longdouble), np.log2(1 - P).astype(np.longdouble)
+    A, R = pool.alt.tocsc(), pool.ref.tocsc()
+    err_q = err_f = 0.0
+    for c in range(0, N, 7):
+        a, r = A.getcol(c).tocoo(), R.getcol(c).tocoo()
+        exact = (a.data.astype(np.longdouble)[:, None] * lp[a.row]).sum(axis=0) + (r.data.astype(np.longdouble)[:, None] * lq[r.row]).sum(axis=0)
+        depth = float(a.data.sum() + r.data.sum())
+        eq = np.abs(Lq[c].astype(np.longdouble) - exact).max()
+        ef = np.abs(Lf[c].astype(np.longdouble) - exact).max()
+        bound = depth * 2.0 ** -(F + 1) + 2.0 ** -52 * float(np.abs(exact).max())    # quantisation + the final int -> double rounding
+        assert eq <= bound, (c, float(eq), bound)
+        err_q, err_f = max(err_q, float(eq)), max(err_f, float(ef))
+    print("max |L - exact|: fixed point %.3e, fp64 kernels %.3e (F = %d)" % (err_q, err_f, F))
+    assert err_q <= 4 * max(err_f, 1e-13)
+
+
+@pytest.mark.parametrize("K", [4, 9, 17])
+def test_fixed_point_heavy_counts(K, E):
+    """Counts up to 8 are repeated codes, larger ones are added by the combine kernel in fp64."""
+    from scipy.sparse import csr_matrix
+    rng = np.random.default_rng(K)
+    V, N = 900, 130
+    dense_a = (rng.random((V, N)) < 0.06) * rng.choice([1, 2, 3, 15, 16, 17, 31, 45, 200, 3000], size=(V, N))
+    dense_r = (rng.random((V, N)) < 0.09) * rng.choice([1, 1, 1, 2, 14, 15, 16, 30, 46, 999], size=(V, N))
+    dense_r[:, 3] = 0
+    dense_a[:, 3] = 0                                     # an empty cell
+    dense_a[5, :] = 0
+    dense_r[5, :] = 0                                     # an empty SNV
+    ref, alt = csr_matrix(dense_r.astype(np.int32)), csr_matrix(dense_a.astype(np.int32))
+
+    class Pool:
+        pass
+    pool = Pool()
+    pool.ref, pool.alt = ref, alt
+    P = _random_P(V, K, 11)
+    Lq, Wq, llq, info = _estep(E, pool, P, 0)
+    assert info["q_lanes"] in (4, 8)
+    Lf, Wf, llf, _ = _estep(E, pool, P, 3)
+    L_o = dense_a.T.astype(np.float64) @ np.log2(P) + dense_r.T.astype(np.float64) @ np.log2(1 - P)
+    assert_close(Lq, L_o, RTOL, "L heavy counts")
+    assert_close(Lq, Lf, 1e-12, "L heavy counts vs fp64")
+    assert np.all(Lq[3] == 0.0) and not np.signbit(Lq[3]).any()
+
+
+def test_unfit_table_takes_fp64_per_restart(E):
+    """A restart whose table holds NaN / -inf (dying cluster, scSplit:198 -> 184) runs its E-step in fp64; the restart
+    batched next to it keeps the fixed-point path; both give what they give alone."""
+    from scsplit_b200 import synth
+    from scsplit_b200._lib import SCS_L, SCS_W
+    V, N, K = 2500, 300, 5
+    pool = synth.make_pool(V, N, 4, 0.05, 0.1, seed=9)
+    P_ok = _random_P(V, K, 1)
+    P_bad = P_ok.copy()
+    P_bad[:, 2] = np.nan
+    P_bad[7, 0] = 1.0                                      # log2(1 - P) = -inf
+    P_far = P_ok.copy()
+    P_far[11, 1] = 1e-25                                   # log2 = -83: outside the format, still finite
+    single = {}
+    for name, P in (("ok", P_ok), ("bad", P_bad), ("far", P_far)):
+        with E(pool.ref, pool.alt) as eng:
+            eng.set_variant(3)
+            eng.em_begin(P)
+            eng.em_iterate(3, check_conv=False)
+            single[name] = (eng.get(SCS_L), eng.get(SCS_W), eng.em_status()[2][0])
+    with E(pool.ref, pool.alt) as eng:
+        eng.em_begin(np.stack([P_ok, P_bad, P_far]))
+        info = eng.em_info()
+        assert info["q_lanes"] == 4 and info["q_unfit_restarts"] == 2, info
+        eng.em_iterate(3, check_conv=False)
+        for r, name in enumerate(("ok", "bad", "far")):
+            L, W, ll = eng.get(SCS_L, r), eng.get(SCS_W, r), eng.em_status()[2][r]
+            assert_close(L, single[name][0], 1e-10, "L restart %s" % name)
+            assert np.array_equal(np.isnan(W), np.isnan(single[name][1]))
+            assert_close(ll, single[name][2], 1e-10, "LL restart %s" % name)
+        # the far-away value is gone after one M-step, so that restart is back on the fixed-point path
+        assert eng.em_info()["q_unfit_restarts"] == 1
+
+
+def test_pool_too_deep_for_the_format_keeps_fp64(E):
+    """A cell so deep (2^21 reads) that the fixed-point fraction would drop below 40 bits: the context keeps the fp64
+    E-step as a whole and still matches the oracle."""
+    from scipy.sparse import csr_matrix
+    rng = np.random.default_rng(3)
+    V, N, K = 400, 60, 3
+    a = (rng.random((V, N)) < 0.1) * rng.integers(1, 4, size=(V, N))
+    r = (rng.random((V, N)) < 0.1) * rng.integers(1, 4, size=(V, N))
+    a[10, 0] = 1 << 21
+    ref, alt = csr_matrix(r.astype(np.int32)), csr_matrix(a.astype(np.int32))
+    P = _random_P(V, K, 2)
+    from scsplit_b200._lib import SCS_L
+    with E(ref, alt) as eng:
+        eng.em_begin(P)
+        assert eng.em_info()["q_lanes"] == 0
+        eng.estep()
+        L = eng.get(SCS_L)
+    L_o = a.T.astype(np.float64) @ np.log2(P) + r.T.astype(np.float64) @ np.log2(1 - P)
+    assert_close(L, L_o, RTOL, "L deep pool")
+
+
+@pytest.mark.parametrize("name", ["k5_nan_a", "k5_nan_b", "k6_dead"])
+def test_dead_cluster_runs_match_fp64_variant(name, E):
+    """Whole runs through a dying cluster (lP_s -> -inf -> NaN, pandas skipna LL = 0.0): the default path (fixed point with
+    the per-restart fp64 stand-in) against the all-fp64 variant: same NaN pattern, same assignments, same stop."""
+    from scsplit_b200._lib import SCS_P, SCS_W
+    g = load_golden(name)
+    out = {}
+    for variant in (0, 3):
+        with E(g["ref"], g["alt"]) as eng:
+            eng.set_variant(variant)
+            eng.em_begin(g["P0"])
+            eng.em_iterate(int(g["iters"]) + 2, check_conv=False)
+            out[variant] = (eng.get(SCS_W), eng.get(SCS_P), eng.em_status()[2][0])
+    W0, P0, ll0 = out[0]
+    W3, P3, ll3 = out[3]
+    assert np.array_equal(np.isnan(W0), np.isnan(W3))
+    with np.errstate(invalid="ignore"):
+        assert np.array_equal(W0 >= 0.99, W3 >= 0.99)
+    assert_close(P0, P3, 1e-9, "P %s" % name)
+    assert_close(ll0, ll3, 1e-9, "LL %s" % name)
