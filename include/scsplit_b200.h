@@ -79,6 +79,10 @@ int scs_pattern_counts(scs_ctx* ctx, const uint8_t* keep_rows, const uint8_t* ke
 
 /* ---- EM over R batched restarts (run_EM, scSplit:148-162; restart driver scSplit:470-484) ---- */
 
+/* Device memory one batched restart of K states needs (out[0], bytes: tables, posteriors, statistics, per-unit partial sums
+ * of both SpMM orientations, seeding temporaries) and what the device can still give (out[1], bytes: free memory plus the
+ * unused part of the context's pool).  The restart driver sizes its batches with it (scSplit:470-490 runs restarts serially). */
+int scs_em_footprint(scs_ctx* ctx, int K, int64_t out[2]);
 /* Allocate EM state for R restarts of K states, upload P0 (double[R][V][K]); lP_s = log2(1/K), scSplit:91. */
 int scs_em_begin(scs_ctx* ctx, int R, int K, const double* P0, int max_iter);
 /* Run up to n_iter more iterations on every unconverged restart. check_conv=1 applies the reference's

@@ -27,6 +27,7 @@ SIGNATURES = {
     "scs_kalt": (c_int, [c_void_p, c_void_p]),
     "scs_seed_af": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "scs_pattern_counts": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "scs_em_footprint": (c_int, [c_void_p, c_int, POINTER(c_int64)]),
     "scs_em_begin": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int]),
     "scs_em_iterate": (c_int, [c_void_p, c_int, c_int]),
     "scs_em_last_ms": (c_int, [c_void_p, POINTER(c_double)]),

@@ -56,6 +56,15 @@ def load_counts(ref_path, alt_path):
     return [ref_s, alt_s, ref_index, ref_columns]
 
 
+def _preload_sklearn():
+    try:
+        from sklearn.cluster import KMeans            # noqa: F401
+        from sklearn.decomposition import PCA         # noqa: F401
+        from sklearn.preprocessing import StandardScaler  # noqa: F401
+    except Exception:
+        pass                                          # (the initialiser imports them itself and reports any real error)
+
+
 def elbow(points):
     """Elbow of the LL curve, including the reference's quirk that `m` is never updated (scSplit:493-501)."""
     points = [-x for x in points]
@@ -103,25 +112,50 @@ def run(argv):
 
     if not os.path.exists(args.out):
         raise ValueError('Specified output directory does not exist')
+    # launched by torchrun (one process per GPU): the restarts are sharded over the ranks (models.core_batched) and rank 0
+    # alone post-processes and writes the outputs
+    rank, world, own_group = 0, int(os.environ.get('WORLD_SIZE', '1')), False
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        args.device = int(os.environ.get('LOCAL_RANK', '0'))
+        torch.cuda.set_device(args.device)
+        if not dist.is_initialized():
+            dist.init_process_group('nccl', device_id=torch.device('cuda', args.device))
+            own_group = True
+        rank = dist.get_rank()
     doublets = float(args.dbl) if args.dbl is not None else -1
     num = args.num if doublets == 0 else args.num + 1          # additional doublet state, scSplit:535-538
+    # The initialiser's PCA / KMeans are scikit-learn's (scSplit:14-16 imports them at start-up; ~1 s of module loading):
+    # load them while the CSV parser's threads and the device upload run, instead of in the first restart.
+    import threading
+    threading.Thread(target=_preload_sklearn, daemon=True).start()
 
-    _log(args.out, '\n' + ' '.join(['scSplit', 'run'] + list(argv)) + '\n')
-    _log(args.out, 'Loading allele count matrices: ' + str(datetime.datetime.now()) + '\n')
+    if rank == 0:
+        _log(args.out, '\n' + ' '.join(['scSplit', 'run'] + list(argv)) + '\n')
+        _log(args.out, 'Loading allele count matrices: ' + str(datetime.datetime.now()) + '\n')
     base_calls_mtx = load_counts(args.ref, args.alt)
-    _log(args.out, 'Allele counts matrices loaded: ' + str(datetime.datetime.now()) + '\n')
+    if rank == 0:
+        _log(args.out, 'Allele counts matrices loaded: ' + str(datetime.datetime.now()) + '\n')
 
     if args.num == 0:                                            # autodetect sweep, scSplit:550-558
         all_models, LL = [], []
         for sub in range(2, args.sub + 1):
             model, _ = M.core_batched(base_calls_mtx, sub, args.out, args.ems, device=args.device)
             all_models.append(model)
-            LL.append(model.lP_c_s.max(axis=1).sum())
-        elb = elbow(LL)
-        model = all_models[elb]
-        num = elb + 2
+            if rank == 0:
+                LL.append(model.lP_c_s.max(axis=1).sum())
+        if rank == 0:
+            elb = elbow(LL)
+            model = all_models[elb]
+            num = elb + 2
     else:
         model, _ = M.core_batched(base_calls_mtx, num, args.out, args.ems, device=args.device)
+    if rank != 0:                                                 # the other ranks have done their share of the restarts
+        M.release_engines()
+        if own_group:
+            dist.destroy_process_group()
+        return None
 
     model.define_doublet()
     model.refine_doublets(doublets)
@@ -141,6 +175,8 @@ def run(argv):
     model.distinguishing_alleles(pos)
     write_outputs(model, num, doublets, args.out)
     M.release_engines()
+    if own_group:
+        dist.destroy_process_group()
     return model
 
 

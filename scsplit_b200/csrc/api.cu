@@ -113,6 +113,7 @@ int scs_destroy(scs_ctx* ctx) {
     for (auto& p : ctx->ev_pending) { cudaEventDestroy(p.second.first); cudaEventDestroy(p.second.second); }
     for (auto e : ctx->ev_pool) cudaEventDestroy(e);
     for (auto e : ctx->ev_iter) if (e) cudaEventDestroy(e);
+    if (ctx->h_poll) cudaFreeHost(ctx->h_poll);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return 0;

@@ -140,6 +140,18 @@ int scs_comm_init(scs_ctx* ctx, const uint8_t id[128], int rank, int world) {
     SCS_TRY(comm_allreduce_i64(ctx, ctx->sum_alt, ctx->V));
     SCS_TRY(comm_allreduce_i64(ctx, ctx->sum_ref, ctx->V));
     SCS_TRY(recompute_kalt(ctx));
+    {   // entries of the whole pool: decisions every rank must take alike (how many pieces the all-reduce is cut into) use this
+        int64_t* d = nullptr;
+        int64_t h = ctx->M.n_light + ctx->M.n_heavy;
+        SCS_CUDA(cudaMallocAsync((void**)&d, 8, ctx->stream));
+        SCS_CUDA(cudaMemcpyAsync(d, &h, 8, cudaMemcpyHostToDevice, ctx->stream));
+        int rc = comm_allreduce_i64(ctx, d, 1);
+        if (!rc) rc = cudaMemcpyAsync(&h, d, 8, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess;
+        if (!rc) rc = cudaStreamSynchronize(ctx->stream) != cudaSuccess;
+        cudaFreeAsync(d, ctx->stream);
+        SCS_CHECK(!rc, "all-reduce of the entry count failed");
+        ctx->entries_global = h;
+    }
     SCS_CUDA(cudaStreamSynchronize(ctx->stream));
     return 0;
 }

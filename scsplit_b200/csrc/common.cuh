@@ -112,6 +112,11 @@ struct EmState {
     int32_t* iters = nullptr;   // [R]
     int32_t* done = nullptr;    // [R]
     int nblk = 0;
+    // One EM iteration (E-step + M-step launches) captured as a CUDA graph, per launch set: [check_conv][sparse_only].  A set is
+    // captured the second time it is needed (the first pass does the lazy builds and attribute calls a capture cannot hold).
+    cudaGraphExec_t graph[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+    bool graph_warm[2][2] = {{false, false}, {false, false}};
+    int graph_launches[2][2] = {{0, 0}, {0, 0}};   // kernels inside each captured iteration
 };
 
 }  // namespace scs
@@ -142,6 +147,7 @@ struct scs_ctx {
     // multi-GPU
     void* comm = nullptr;        // ncclComm_t
     int rank = 0, world = 1;
+    int64_t entries_global = 0;               // stored entries of the whole pool (all ranks)
     cudaStream_t comm_stream = nullptr;       // high-priority stream of the statistics all-reduce (cells sharded over ranks)
     cudaEvent_t ev_comm[10] = {};             // [0..7] M-step chunk done (main stream), [8] posterior tail ready, [9] all-reduce done (comm stream)
     int32_t* m_order_chunks = nullptr;        // [2V] job order of the sparse M-step inside each of the M_CHUNKS row ranges
@@ -153,6 +159,9 @@ struct scs_ctx {
     bool sample_on = true;       // whether the launches issued right now belong to a sampled step
     int64_t m_samples = 0;       // sampled M-steps (an M-step is up to three launches)
     int variant = 0;
+    int use_graphs = 1;          // replay one EM iteration as a CUDA graph (single GPU, kernel timing off)
+    int32_t* h_poll = nullptr;   // pinned [2 * R]: stop flags and saturation latches as of the last poll
+    int h_poll_cap = 0;
     std::vector<cudaEvent_t> ev_pool;
     std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> ev_pending;  // (kind, (start, stop))
     cudaEvent_t ev_iter[2] = {nullptr, nullptr};   // brackets the launches of the last scs_em_iterate

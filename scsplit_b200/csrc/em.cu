@@ -184,10 +184,13 @@ static int launch_estep_q(scs_ctx* ctx, const int32_t* done) {
 
 int em_free(scs_ctx* ctx) {
     EmState& em = ctx->em;
+    for (auto& row : em.graph)
+        for (auto& g : row)
+            if (g) { cudaGraphExecDestroy(g); g = nullptr; }
     dev_free(ctx, em.Tq); dev_free(ctx, em.qbad); dev_free(ctx, em.gstats);
     ctx->h_done.clear();
     dev_free(ctx, em.T); dev_free(ctx, em.P); dev_free(ctx, em.L); dev_free(ctx, em.W); dev_free(ctx, em.stats); dev_free(ctx, em.lps);
-    dev_free(ctx, em.hq); dev_free(ctx, em.sched); dev_free(ctx, em.sat);
+    dev_free(ctx, em.hq); dev_free(ctx, em.sched);
     dev_free(ctx, em.partial); dev_free(ctx, em.hist); dev_free(ctx, em.ll_prev); dev_free(ctx, em.iters); dev_free(ctx, em.done);
     em = EmState();
     return 0;
@@ -352,18 +355,21 @@ static int run_m(scs_ctx* ctx, const int32_t* done, int track, int check_conv) {
     // live restart set, the tiled pair -- which those restarts can no longer take -- is not launched at all)
     if (!(sparse && em.sparse_only))
         SCS_TRY(launch_spmm(ctx, 1, em.KP, em.R, em.W, N * em.KP, em.stats, em.stats_stride, done, gate));
+    // (a piece of the sums is worth its own launch from ~16 M entries per rank on: below that the launches cost more than the
+    // overlap hides; decided from the pool's global size so that every rank issues the same collectives)
+    const int nchunks = multi ? (int)std::min<int64_t>(M_CHUNKS, std::max<int64_t>(1, ctx->entries_global / ctx->world / (16 << 20))) : 1;
+    const int64_t nrows = ctx->M.nrows;
+    // rows [lo, hi) of chunk c: the keys of build_row_order put row i into chunk i * nchunks / nrows
+    auto chunk_lo = [&](int c) { return ((int64_t)c * nrows + nchunks - 1) / nchunks; };
     if (sparse) {
         cudaEvent_t ea = nullptr, eb = nullptr;
         SCS_TRY(timing_begin(ctx, &ea, &eb));
-        const int nchunks = multi ? M_CHUNKS : 1;
-        int32_t*& order = multi ? ctx->m_order_chunks : ctx->m_order;
+        int32_t*& order = nchunks > 1 ? ctx->m_order_chunks : ctx->m_order;
         if (!order) SCS_TRY(build_row_order(ctx, ctx->M, &order, nchunks));
         const size_t smem = sparse_smem_bytes(em.h_stride, em.KP, sparse_threads);
         dim3 grid((unsigned)(ctx->sm_count > 0 ? ctx->sm_count : 148), (unsigned)em.R);
-        const int64_t nrows = ctx->M.nrows;
         for (int c = 0; c < nchunks; ++c) {
-            // rows [lo, hi) of chunk c: the keys of build_row_order put row i into chunk i * nchunks / nrows
-            const int64_t lo = (c * nrows + nchunks - 1) / nchunks, hi = ((c + 1) * nrows + nchunks - 1) / nchunks;
+            const int64_t lo = chunk_lo(c), hi = chunk_lo(c + 1);
             SCS_DISPATCH_KP(em.KP, {
                 if (!(ctx->smem_attr_set[1] >> (KPc / 2) & 1u)) {
                     SCS_CUDA(cudaFuncSetAttribute(k_mstep_sparse<KPc>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_BYTES + 1024));
@@ -377,8 +383,8 @@ static int run_m(scs_ctx* ctx, const int32_t* done, int track, int check_conv) {
             if (multi) SCS_TRY(reduce_piece(ctx, lo * em.KP, (hi - lo) * em.KP, ctx->ev_comm[c]));
         }
         SCS_TRY(timing_end(ctx, 2, ea, eb));
-    } else if (multi) {
-        SCS_TRY(reduce_piece(ctx, 0, tail_off, ctx->ev_comm[0]));
+    } else if (multi) {                                  // (same pieces as a rank whose shard takes the sparse kernel)
+        for (int c = 0; c < nchunks; ++c) SCS_TRY(reduce_piece(ctx, chunk_lo(c) * em.KP, (chunk_lo(c + 1) - chunk_lo(c)) * em.KP, ctx->ev_comm[c]));
     }
     if (multi) {
         SCS_CUDA(cudaEventRecord(ctx->ev_comm[9], ctx->comm_stream));
@@ -426,6 +432,37 @@ int scs_em_end(scs_ctx* ctx) {
     SCS_CHECK(ctx, "null context");
     SCS_CUDA(cudaSetDevice(ctx->device));
     return em_free(ctx);
+}
+
+int scs_em_footprint(scs_ctx* ctx, int K, int64_t out[2]) {
+    SCS_CHECK(ctx && out, "null argument");
+    SCS_CHECK(K >= 1 && K <= SCS_MAX_K, "K must be in [1, %d] (got %d)", SCS_MAX_K, K);
+    SCS_CUDA(cudaSetDevice(ctx->device));
+    const int64_t V = ctx->V, N = ctx->N, KP = round_even(K);
+    int64_t b = 0;
+    b += 2 * V * KP * 8 + V * KP * 8 + 2 * N * KP * 8;                     // T, P, L, W
+    b += (2 * V * KP + KP + 2) * 8 * (ctx->world > 1 ? 2 : 1);              // statistics (and their sum over ranks)
+    b += 4 * N + SCS_MAX_ITER * 8 + 64 * (KP + 2) * 8 * 8;                  // packed posteriors, LL history, block partials
+    const int lanes = q_lanes_for(K);
+    if (lanes) {
+        const int64_t ntq = (2 * V + q_tile_rows(lanes, 2 * V) - 1) / q_tile_rows(lanes, 2 * V);
+        b += 2 * V * 2 * lanes * 8 + ntq * N * lanes * 24;                  // fixed-point table, its per-unit sums
+    }
+    const int64_t nte = (2 * V + tile_rows_for((int)KP, 2 * V) - 1) / tile_rows_for((int)KP, 2 * V);
+    const int64_t ntm = (N + tile_rows_for((int)KP, N) - 1) / tile_rows_for((int)KP, N);
+    b += std::max(lanes ? (int64_t)0 : nte * N, ntm * 2 * V) * KP * 8;      // per-unit sums of the fp64 tiled SpMM (one buffer for both)
+    b += (N + 3 * V) * KP * 8 + 4 * N;                                      // seeding: one-hot W, S, P, labels
+    out[0] = b;
+    size_t free_b = 0, total_b = 0;
+    SCS_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    uint64_t reserved = 0, used = 0;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, ctx->device) == cudaSuccess &&
+        cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved) == cudaSuccess &&
+        cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used) == cudaSuccess && reserved > used)
+        free_b += (size_t)(reserved - used);
+    out[1] = (int64_t)free_b;
+    return 0;
 }
 
 int scs_em_begin(scs_ctx* ctx, int R, int K, const double* P0, int max_iter) {
@@ -480,21 +517,20 @@ int scs_em_begin(scs_ctx* ctx, int R, int K, const double* P0, int max_iter) {
     SCS_TRY(dev_alloc(ctx, &em.hq, (int64_t)R * em.h_stride));
     k_fill_u32<<<(unsigned)((R * em.h_stride + 255) / 256), 256, 0, ctx->stream>>>(em.hq, R * em.h_stride, SPARSE_DENSE);
     ctx->launches++;
-    SCS_TRY(dev_alloc(ctx, &em.sat, R));
-    SCS_CUDA(cudaMemsetAsync(em.sat, 0, (size_t)R * 4, ctx->stream));
+    SCS_TRY(dev_alloc(ctx, &em.done, 2 * R));      // [R] stop flags, [R] saturation latches: one copy per poll
+    em.sat = em.done + R;
+    SCS_CUDA(cudaMemsetAsync(em.done, 0, (size_t)R * 8, ctx->stream));
     SCS_TRY(dev_alloc(ctx, &em.sched, 4 * R));   // [R][2] sparse M-step tickets, [R] k_finalize and [R] k_bayes block counts
     SCS_CUDA(cudaMemsetAsync(em.sched, 0, (size_t)R * 16, ctx->stream));
     SCS_TRY(dev_alloc(ctx, &em.hist, (int64_t)R * max_iter));
     SCS_TRY(dev_alloc(ctx, &em.ll_prev, R));
     SCS_TRY(dev_alloc(ctx, &em.iters, R));
-    SCS_TRY(dev_alloc(ctx, &em.done, R));
     cudaStream_t st = ctx->stream;
     SCS_CUDA(cudaMemsetAsync(em.W, 0, (size_t)R * N * KP * 8, st));
     SCS_CUDA(cudaMemsetAsync(em.L, 0, (size_t)R * N * KP * 8, st));
     SCS_CUDA(cudaMemsetAsync(em.stats, 0, (size_t)R * em.stats_stride * 8, st));
     SCS_CUDA(cudaMemsetAsync(em.hist, 0, (size_t)R * max_iter * 8, st));
     SCS_CUDA(cudaMemsetAsync(em.iters, 0, (size_t)R * 4, st));
-    SCS_CUDA(cudaMemsetAsync(em.done, 0, (size_t)R * 4, st));
     SCS_TRY(upload_pitched(ctx, em.P, P0, (int64_t)R * V, K, KP));
     // lP_s = [log2(1/K)] * K (scSplit:91); sum_log_likelihood = [1, 2] (scSplit:155) -> previous LL = 2
     std::vector<double> h_lps((size_t)R * KP, 0.0), h_prev((size_t)R, 2.0);
@@ -531,23 +567,70 @@ int scs_mstep(scs_ctx* ctx) {
     return 0;
 }
 
+// One iteration: the launches of run_e + run_m, replayed from a CUDA graph where one exists for the current launch set.
+static int em_one_iteration(scs_ctx* ctx, const int32_t* done, int check_conv) {
+    EmState& em = ctx->em;
+    const bool graphs = ctx->use_graphs && ctx->world == 1 && !ctx->timing && !std::getenv("SCS_NO_GRAPH");
+    const int a = check_conv ? 1 : 0, b = em.sparse_only ? 1 : 0;
+    if (graphs && em.graph[a][b]) {
+        SCS_CUDA(cudaGraphLaunch(em.graph[a][b], ctx->stream));
+        ctx->launches += em.graph_launches[a][b];
+        return 0;
+    }
+    if (graphs && em.graph_warm[a][b]) {
+        const int64_t l0 = ctx->launches;
+        cudaGraph_t g = nullptr;
+        SCS_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+        int rc = run_e(ctx, done);
+        if (!rc) rc = run_m(ctx, done, 1, check_conv);
+        const cudaError_t e = cudaStreamEndCapture(ctx->stream, &g);
+        if (rc || e != cudaSuccess || !g) {
+            if (g) cudaGraphDestroy(g);
+            cudaGetLastError();
+            ctx->use_graphs = 0;                         // fall back to plain launches for the rest of this context
+            ctx->launches = l0;
+            if (rc) return rc;
+        } else {
+            cudaGraphExec_t x = nullptr;
+            const cudaError_t e2 = cudaGraphInstantiate(&x, g, 0);
+            cudaGraphDestroy(g);
+            if (e2 == cudaSuccess && x) {
+                em.graph[a][b] = x;
+                em.graph_launches[a][b] = (int)(ctx->launches - l0);
+                ctx->launches = l0;
+                return em_one_iteration(ctx, done, check_conv);
+            }
+            cudaGetLastError();
+            ctx->use_graphs = 0;
+            ctx->launches = l0;
+        }
+    }
+    SCS_TRY(run_e(ctx, done));
+    SCS_TRY(run_m(ctx, done, 1, check_conv));
+    em.graph_warm[a][b] = true;
+    return 0;
+}
+
 int scs_em_iterate(scs_ctx* ctx, int n_iter, int check_conv) {
     SCS_CHECK(ctx && ctx->em.R, "EM state not initialised (call scs_em_begin)");
     SCS_CUDA(cudaSetDevice(ctx->device));
     EmState& em = ctx->em;
     const int32_t* done = check_conv ? em.done : nullptr;
-    std::vector<int32_t> h_done((size_t)em.R);
-    std::vector<int32_t> h_sat((size_t)em.R);
+    if (ctx->h_poll_cap < 2 * em.R) {
+        if (ctx->h_poll) cudaFreeHost(ctx->h_poll);
+        ctx->h_poll = nullptr;
+        SCS_CUDA(cudaMallocHost((void**)&ctx->h_poll, (size_t)2 * em.R * 4));
+        ctx->h_poll_cap = 2 * em.R;
+    }
+    const int32_t *h_done = ctx->h_poll, *h_sat = ctx->h_poll + em.R;
     if (!check_conv) ctx->h_done.clear();     // every restart takes part in the collectives of a fixed-length run
-    const int POLL = 8;   // iterations between host polls of the device-side convergence flags and saturation counts
+    const int POLL = 8;   // iterations between host polls of the device-side convergence flags and saturation latches
     if (!ctx->ev_iter[0]) { SCS_CUDA(cudaEventCreate(&ctx->ev_iter[0])); SCS_CUDA(cudaEventCreate(&ctx->ev_iter[1])); }
     SCS_CUDA(cudaEventRecord(ctx->ev_iter[0], ctx->stream));
     for (int i = 0; i < n_iter; ++i) {
-        SCS_TRY(run_e(ctx, done));
-        SCS_TRY(run_m(ctx, done, 1, check_conv));
+        SCS_TRY(em_one_iteration(ctx, done, check_conv));
         if ((i + 1) % POLL == 0 || (check_conv && i + 1 == n_iter)) {
-            SCS_CUDA(cudaMemcpyAsync(h_done.data(), em.done, (size_t)em.R * 4, cudaMemcpyDeviceToHost, ctx->stream));
-            SCS_CUDA(cudaMemcpyAsync(h_sat.data(), em.sat, (size_t)em.R * 4, cudaMemcpyDeviceToHost, ctx->stream));
+            SCS_CUDA(cudaMemcpyAsync(ctx->h_poll, em.done, (size_t)em.R * 8, cudaMemcpyDeviceToHost, ctx->stream));
             SCS_CUDA(cudaStreamSynchronize(ctx->stream));
             bool all = true, saturated = true;
             for (int r = 0; r < em.R; ++r) {
@@ -555,7 +638,7 @@ int scs_em_iterate(scs_ctx* ctx, int n_iter, int check_conv) {
                 if (!(check_conv && h_done[r])) saturated = saturated && h_sat[r];
             }
             em.sparse_only = saturated ? 1 : 0;
-            if (check_conv) ctx->h_done = h_done; // (identical on every rank: the flags are functions of all-reduced sums)
+            if (check_conv) ctx->h_done.assign(h_done, h_done + em.R);   // (identical on every rank: functions of all-reduced sums)
             if (check_conv && all) break;
         }
     }

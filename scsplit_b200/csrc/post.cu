@@ -60,10 +60,15 @@ __global__ void __launch_bounds__(CELL_BLOCK) k_masked_colsum(int64_t N, const d
 // one warp per SNV: union-pattern entries whose cell is kept
 __global__ void __launch_bounds__(256) k_row_pattern_counts(int64_t V, const int64_t* __restrict__ lptr, const uint32_t* __restrict__ lcode,
                                                             const int64_t* __restrict__ hptr, const uint32_t* __restrict__ hcode,
-                                                            const uint8_t* __restrict__ keep_cols, int64_t* __restrict__ out) {
+                                                            const uint8_t* __restrict__ keep_rows, const uint8_t* __restrict__ keep_cols,
+                                                            int64_t* __restrict__ out) {
     const int lane = threadIdx.x & 31;
     const int64_t v = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (v >= V) return;
+    if (keep_rows && !keep_rows[v]) {   // a dropped SNV: nobody reads its count, and the later passes of the trimming loop keep
+        if (lane == 0) out[v] = 0;      // only a few per cent of the rows, so skipping them is what makes those passes cheap
+        return;
+    }
     int64_t n = 0;
     for (int sel = 0; sel < 2; ++sel) {
         const int64_t pr = (int64_t)sel * V + v;
@@ -83,10 +88,15 @@ __global__ void __launch_bounds__(256) k_row_pattern_counts(int64_t V, const int
 // one warp per cell: union-pattern entries whose SNV is kept
 __global__ void __launch_bounds__(256) k_col_pattern_counts(int64_t N, int64_t V, const int64_t* __restrict__ lptr, const uint32_t* __restrict__ lcode,
                                                             const int64_t* __restrict__ hptr, const uint32_t* __restrict__ hcode,
-                                                            const uint8_t* __restrict__ keep_rows, int64_t* __restrict__ out) {
+                                                            const uint8_t* __restrict__ keep_rows, const uint8_t* __restrict__ keep_cols,
+                                                            int64_t* __restrict__ out) {
     const int lane = threadIdx.x & 31;
     const int64_t c = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (c >= N) return;
+    if (keep_cols && !keep_cols[c]) {
+        if (lane == 0) out[c] = 0;
+        return;
+    }
     int64_t n = 0;
     for (int64_t e = lptr[c] + lane; e < lptr[c + 1]; e += 32) {
         const uint32_t code = lcode[e];
@@ -209,13 +219,13 @@ int scs_pattern_counts(scs_ctx* ctx, const uint8_t* keep_rows, const uint8_t* ke
     if (keep_rows) { SCS_TRY(s.get(&d_kr, V)); SCS_CUDA(cudaMemcpyAsync(d_kr, keep_rows, (size_t)V, cudaMemcpyHostToDevice, st)); }
     if (keep_cols) { SCS_TRY(s.get(&d_kc, N)); SCS_CUDA(cudaMemcpyAsync(d_kc, keep_cols, (size_t)N, cudaMemcpyHostToDevice, st)); }
     if (row_cnt) {
-        k_row_pattern_counts<<<(unsigned)((V + 7) / 8), 256, 0, st>>>(V, ctx->M.lptr, ctx->M.lcode, ctx->M.hptr, ctx->M.hcode, d_kc, d_rc);
+        k_row_pattern_counts<<<(unsigned)((V + 7) / 8), 256, 0, st>>>(V, ctx->M.lptr, ctx->M.lcode, ctx->M.hptr, ctx->M.hcode, d_kr, d_kc, d_rc);
         ctx->launches++;
         if (ctx->world > 1) SCS_TRY(comm_allreduce_i64(ctx, d_rc, V));
         SCS_CUDA(cudaMemcpyAsync(row_cnt, d_rc, (size_t)V * 8, cudaMemcpyDeviceToHost, st));
     }
     if (col_cnt) {
-        k_col_pattern_counts<<<(unsigned)((N + 7) / 8), 256, 0, st>>>(N, V, ctx->E.lptr, ctx->E.lcode, ctx->E.hptr, ctx->E.hcode, d_kr, d_cc);
+        k_col_pattern_counts<<<(unsigned)((N + 7) / 8), 256, 0, st>>>(N, V, ctx->E.lptr, ctx->E.lcode, ctx->E.hptr, ctx->E.hcode, d_kr, d_kc, d_cc);
         ctx->launches++;
         SCS_CUDA(cudaMemcpyAsync(col_cnt, d_cc, (size_t)N * 8, cudaMemcpyDeviceToHost, st));
     }

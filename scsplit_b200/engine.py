@@ -117,6 +117,12 @@ class Engine:
         return rc, cc
 
     # -- EM
+    def em_footprint(self, K):
+        """(device bytes one batched restart of K states needs, device bytes still available)."""
+        out = (ctypes.c_int64 * 2)()
+        check(self.lib.scs_em_footprint(self.h, int(K), out))
+        return int(out[0]), int(out[1])
+
     def em_begin(self, P0, max_iter=_lib.SCS_MAX_ITER):
         P0 = np.ascontiguousarray(P0, dtype=np.float64)
         if P0.ndim == 2:

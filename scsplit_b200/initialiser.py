@@ -18,7 +18,8 @@ import numpy as np
 def _positions_to_drop(rng, n):
     """scSplit:113-114: sorted unique int(beta(1,10) * n) positions, int(0.1*n + 0.5) draws."""
     draws = rng.beta(1, 10, int(0.1 * n + 0.5)) * n
-    return np.unique(draws.astype(np.int64))      # int() truncation of non-negative floats; np.unique returns sorted values
+    pos = np.sort(draws.astype(np.int64))         # int() truncation of non-negative floats; sorted unique values (= np.unique)
+    return pos[np.concatenate(([True], pos[1:] != pos[:-1]))] if pos.size else pos
 
 
 def trim_subset(count_fn, V, N, K, rng=np.random):

@@ -309,65 +309,164 @@ def select_distinguishing(alt_or_ref, num, ncols):
     return dist_variants
 
 
+def _assign_lists(W, barcodes):
+    """assign_cells on a bare posterior matrix (scSplit:201-207)."""
+    bc = np.asarray(barcodes, dtype=object)
+    with np.errstate(invalid='ignore'):
+        hit = W >= 0.99
+    return [sorted(bc[hit[:, n]].tolist()) for n in range(W.shape[1])]
+
+
+def _initialise(engine, base_calls_mtx, barcodes, num, output):
+    """The initialisation part of models.__init__ (scSplit:105-142) without the model's frames: (labels or None, initial lists)."""
+    irows, icols, nrows, ncols = initialiser.trim_subset(engine.pattern_counts, base_calls_mtx[0].shape[0], len(barcodes), num)
+    labels = initialiser.initial_labels(base_calls_mtx[0], base_calls_mtx[1], irows, icols, nrows, ncols, num)
+    if labels is None:
+        _log(output, 'Not enough informative cells to support model initialization. \n')
+        return None, None
+    return labels, [[barcodes[col] for col in icols[labels[icols] == n]] for n in range(num)]
+
+
+def _world():
+    """(rank, world) of a torchrun launch whose process group is up, else (0, 1)."""
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_rank(), dist.get_world_size()
+    except Exception:
+        pass
+    return 0, 1
+
+
+def _bcast(arr, src, device):
+    """Broadcast a numpy array from rank `src` (shape and dtype known on every rank)."""
+    import torch
+    import torch.distributed as dist
+    t = torch.from_numpy(np.ascontiguousarray(arr))
+    if dist.get_backend() == 'nccl':
+        t = t.cuda(device)
+    dist.broadcast(t, src)
+    return t.cpu().numpy()
+
+
 def core_batched(base_calls_mtx, num, output, ems, device=0, chunk=64):
     """Restart driver (run.core, scSplit:470-490): `ems` restarts, first strictly greatest LL wins.
 
     The R initialisations are generated serially on the host first -- they share one `np.random` stream and never read
-    EM results (hard part 6) -- then the R EM runs execute as one batch on the GPU.
+    EM results (hard part 6) -- then the EM runs execute in batches on the GPU; a batch holds as many
+    restarts as the device has memory for (`scs_em_footprint`), at most `chunk`.  Only the LAST restart is a full `models`
+    object (the reference returns that object with four attributes of the best restart grafted on, scSplit:488); the
+    others are kept as labels + results.
+
+    Under torchrun (an initialised torch.distributed process group) the restarts are sharded over the ranks, one GPU
+    each: rank 0 draws all initialisations (one `np.random` stream, as above) and broadcasts the labels, rank r runs
+    restarts r, r + world, ... (dist.shard_restarts), the log-likelihoods are gathered and the reference's selection rule is
+    applied to them in restart order on every rank, and the winner's arrays travel to rank 0, the only rank that returns a
+    populated model (the others return (None, best)).
     Returns (model, chosen_index); raises ValueError like scSplit:486 when no restart could be initialised.
     """
-    max_likelihood = -1e50
-    built = []
-    for i in range(ems):
-        _log(output, 'Repeat ' + str(i + 1) + ' of ' + str(ems) + ' in demultiplexing ' + str(num) +
-             ' subpopulations (including doublets if expected)' + '\n')
-        _log(output, 'Building model... \n')
-        built.append(models(base_calls_mtx, num, output, device=device, _defer_seed=True))
-    model = built[-1]
-    eng = model.engine
-    live = [i for i, m in enumerate(built) if m._labels is not None]
-    best = None
+    from . import dist as D
+    rank, world = _world()
+    barcodes = base_calls_mtx[3].tolist()
+    N, V = len(barcodes), base_calls_mtx[0].shape[0]
+    eng = get_engine(base_calls_mtx, device)
+    model, labels, initial = None, [None] * ems, [None] * ems
+    if rank == 0:
+        for i in range(ems):
+            _log(output, 'Repeat ' + str(i + 1) + ' of ' + str(ems) + ' in demultiplexing ' + str(num) +
+                 ' subpopulations (including doublets if expected)' + '\n')
+            _log(output, 'Building model... \n')
+            if i == ems - 1:
+                model = models(base_calls_mtx, num, output, device=device, _defer_seed=True)
+                labels[i], initial[i] = model._labels, getattr(model, 'initial', None)
+            else:
+                labels[i], initial[i] = _initialise(eng, base_calls_mtx, barcodes, num, output)
+    if world > 1:
+        lab = np.full((ems, N), -2, dtype=np.int32)          # -2 rows: restarts whose initialisation failed
+        if rank == 0:
+            for i in range(ems):
+                if labels[i] is not None:
+                    lab[i] = labels[i]
+        lab = _bcast(lab, 0, device)
+        labels = [None if (lab[i] == -2).all() else lab[i] for i in range(ems)]
+    mine = D.shard_restarts(ems, world)[rank]
+    live = [i for i in mine if labels[i] is not None]
+    per, free = eng.em_footprint(num)
+    chunk = int(max(1, min(chunk, (0.7 * free) // max(per, 1))))
+    ll_all = np.full(ems, np.nan)
+    iters_all = np.zeros(ems, dtype=np.int64)
+    best_local, best_ll, keep, last = None, -1e50, None, None
     for c0 in range(0, len(live), chunk):
         part = live[c0:c0 + chunk]
-        labels = np.stack([built[i]._labels for i in part])
-        P0 = eng.seed_af(labels, num)
+        P0 = eng.seed_af(np.stack([labels[i] for i in part]), num)
         if P0.ndim == 2:
             P0 = P0[None]
-        keep = [r for r in range(len(part)) if P0[r].sum() > 0]           # scSplit:478 gate
-        if not keep:
+        ok = [r for r in range(len(part)) if P0[r].sum() > 0]             # scSplit:478 gate
+        if not ok:
             continue
-        eng.em_begin(np.ascontiguousarray(P0[keep]))
+        eng.em_begin(np.ascontiguousarray(P0[ok]))
         eng.em_run()
         it, conv, ll = eng.em_status()
-        for r, pr in enumerate(keep):
+        for r, pr in enumerate(ok):
             i = part[pr]
-            m = built[i]
-            m._set_af(P0[pr])
-            iterations = int(it[r])
-            now = str(datetime.datetime.now())
-            _log(output, ''.join('E-M Iteration ' + str(t + 1) + '   ' + now + '\n' for t in range(iterations)))
-            m.lP_c_m = float(ll[r])
-            m.convergence = int(iterations < 300)
-            _log(output, 'Model Log-Likelihood = ' + str(m.lP_c_m) + '\n')
-            if i == ems - 1:
-                # the reference returns the LAST model object and later reads ITS lP_c_s (autodetect, scSplit:555 with 488)
-                m.lP_c_s = pd.DataFrame(eng.get(SCS_L, r), index=m.barcodes, columns=range(num))
-            if m.lP_c_m > max_likelihood:
-                max_likelihood = m.lP_c_m
-                hist = eng.get(4, r)[:iterations]
-                m.sum_log_likelihood = [1, 2] + hist.tolist()
-                m.lP_c_s = pd.DataFrame(eng.get(SCS_L, r), index=m.barcodes, columns=range(num))
-                m.P_s_c = pd.DataFrame(eng.get(SCS_W, r), index=m.barcodes, columns=range(num))
-                m._set_af(eng.get(SCS_P, r))
-                m.lP_s = pd.Series(eng.get(SCS_LPS, r), index=range(num))
-                m.assign_cells()
-                best = i
-    if max_likelihood == -1e50:
+            ll_all[i], iters_all[i] = float(ll[r]), int(it[r])
+            if i == ems - 1:       # the reference returns the LAST model object and later reads ITS lP_c_s (autodetect, scSplit:555 with 488)
+                last = dict(L=eng.get(SCS_L, r), P0=P0[pr])
+            if float(ll[r]) > best_ll:                                      # first strictly greater within this rank's order
+                best_local, best_ll = i, float(ll[r])
+                keep = dict(W=eng.get(SCS_W, r), P=eng.get(SCS_P, r), L=eng.get(SCS_L, r), lps=eng.get(SCS_LPS, r),
+                            hist=eng.get(4, r)[:int(it[r])], iters=int(it[r]))
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        pack = np.stack([np.nan_to_num(ll_all, nan=-np.inf), iters_all.astype(np.float64)])
+        t = torch.from_numpy(pack)
+        t = t.cuda(device) if dist.get_backend() == 'nccl' else t
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)                            # every restart ran on exactly one rank
+        pack = t.cpu().numpy()
+        ll_all = np.where(np.isinf(pack[0]), np.nan, pack[0])
+        iters_all = pack[1].astype(np.int64)
+    best = D.select_best([None if np.isnan(x) else float(x) for x in ll_all])
+    if rank == 0:
+        now = str(datetime.datetime.now())
+        for i in range(ems):
+            if not np.isnan(ll_all[i]):
+                _log(output, ''.join('E-M Iteration ' + str(t + 1) + '   ' + now + '\n' for t in range(int(iters_all[i]))))
+                _log(output, 'Model Log-Likelihood = ' + str(float(ll_all[i])) + '\n')
+    if best is None:
         raise ValueError('Model not converged, please allow more repeats!')
-    chosen = built[best]
-    # the reference grafts four attributes of the best restart onto the LAST model object (scSplit:488)
-    model.assigned, model.initial, model.model_af, model.P_s_c = chosen.assigned, chosen.initial, chosen.model_af, chosen.P_s_c
-    if model is not chosen and not hasattr(model, 'lP_c_m'):
-        model.lP_c_m = chosen.lP_c_m
+    if world > 1:
+        owner = best % world                                                # dist.shard_restarts deals round robin
+        K = num
+        shapes = dict(W=(N, K), P=(V, K), L=(N, K), lps=(K,), hist=(int(iters_all[best]),))
+        got = {}
+        for name, shp in shapes.items():
+            src = keep[name] if (rank == owner and best_local == best) else np.zeros(shp)
+            got[name] = _bcast(np.asarray(src, dtype=np.float64).reshape(shp), owner, device)
+        keep = dict(got, iters=int(iters_all[best]))
+        lastL = np.zeros((N, K))
+        last_owner = (ems - 1) % world
+        have_last = not np.isnan(ll_all[ems - 1])
+        if have_last:
+            lastL = _bcast(last["L"] if rank == last_owner else lastL, last_owner, device)
+            lastP0 = _bcast(last["P0"] if rank == last_owner else np.zeros((V, K)), last_owner, device)
+            last = dict(L=lastL, P0=lastP0)
+        if rank != 0:
+            return None, best
+    # ---- rank 0 (or the only process): the LAST model object with the best restart grafted on (scSplit:488)
+    if not np.isnan(ll_all[ems - 1]):
+        model._set_af(last["P0"])
+        model.lP_c_m = float(ll_all[ems - 1])
+        model.convergence = int(iters_all[ems - 1] < 300)
+        model.lP_c_s = pd.DataFrame(last["L"], index=model.barcodes, columns=range(num))
+    if best == ems - 1:
+        model.sum_log_likelihood = [1, 2] + np.asarray(keep["hist"]).tolist()
+        model.lP_s = pd.Series(keep["lps"], index=range(num))
+    model.P_s_c = pd.DataFrame(keep["W"], index=model.barcodes, columns=range(num))
+    model._set_af(keep["P"])
+    model.assigned = _assign_lists(keep["W"], barcodes)
+    model.initial = initial[best]
+    if not hasattr(model, 'lP_c_m'):
+        model.lP_c_m = float(ll_all[best])
     print('Repeat ' + str(best + 1) + ' was chosen.')
     return model, best
