@@ -156,14 +156,14 @@ static int launch_estep_q(scs_ctx* ctx, const int32_t* done) {
         SCS_TRY(dev_alloc(ctx, &ctx->qpart, part_stride * em.R));
         ctx->qpart_words = part_stride * em.R;
     }
-    const size_t smem = ((((size_t)(t.TR + 1) * lanes * 16) + 127) & ~(size_t)127) + 16;
+    const size_t smem = ((((size_t)(t.TR + 2) * lanes * 16) + 127) & ~(size_t)127) + 16;
     const int64_t xq_stride = 2 * ctx->V * 2 * lanes;
     dim3 grid((unsigned)t.ncta, (unsigned)em.R);
     dim3 cgrid((unsigned)((ctx->N * lanes + 63) / 64), (unsigned)em.R);       // 256 threads = 64 (cell, lane) pairs x 4 tile classes
     const double scale_inv = ldexp(1.0, -em.q_F);
     if (!(ctx->smem_attr_set[2] >> (16 + lanes) & 1u)) {
-        if (lanes == 4) SCS_CUDA(cudaFuncSetAttribute(k_estep_q<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_BYTES + 1024));
-        else SCS_CUDA(cudaFuncSetAttribute(k_estep_q<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_BYTES + 1024));
+        if (lanes == 4) SCS_CUDA(cudaFuncSetAttribute(k_estep_q<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, Q_SMEM_BYTES));
+        else SCS_CUDA(cudaFuncSetAttribute(k_estep_q<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, Q_SMEM_BYTES));
         ctx->smem_attr_set[2] |= 1u << (16 + lanes);
     }
     if (lanes == 4) {

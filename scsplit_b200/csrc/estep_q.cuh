@@ -23,7 +23,8 @@
 // count c <= Q_REP_MAX is c codes, larger counts (rare in droplet data) are added in fp64 by the combine kernel.
 //
 // Stream: 32-bit words of two codes, word = rowA << SA | rowB << (SA + 14), SA = log2(row bytes): the first row's byte
-// offset is one AND away, the second's a shift and an AND.  Padding codes point at the all-zero row TR.
+// offset is one AND away, the second's a shift and an AND.  Padding codes point at one of the two all-zero rows TR, TR + 1
+// (one of each parity: a padding code never costs a bank conflict, see k_qorder_units).
 #pragma once
 #include "common.cuh"
 #include "spmm_tiled.cuh"
@@ -37,9 +38,11 @@ constexpr int Q_MIN_F = 40;
 constexpr int Q_UNIT_PAD = 8;        // units hold a multiple of this many codes (the kernel looks for a unit's end once per 8 codes)          // pools whose deepest cell would push F below this keep the fp64 E-step
 
 inline int q_lanes_for(int K) { return K <= 9 ? 4 : K <= 17 ? 8 : 0; }
+// shared memory of k_estep_q: table tile (TR + 2 rows) | mbarrier
+constexpr int Q_SMEM_BYTES = 227 * 1024;
 inline int q_tile_rows(int lanes, int64_t xrows) {
-    int64_t tr = TILE_BYTES / (lanes * 16) - 1;      // + the zero row
-    const int64_t cap = lanes == 4 ? 4094 : 2046;    // 12 / 11 bits of in-tile row per code, row TR is the zero row
+    int64_t tr = (Q_SMEM_BYTES - 256) / (lanes * 16) - 2;      // + the two zero rows
+    const int64_t cap = lanes == 4 ? 4094 : 2046;    // 12 / 11 bits of in-tile row per code; rows TR and TR + 1 are all zeros
     if (tr > cap) tr = cap;
     if (tr > xrows) tr = xrows;
     return (int)(tr < 1 ? 1 : tr);
@@ -107,9 +110,9 @@ k_estep_q(int TR, int64_t xrows, const int64_t* __restrict__ tptr, const uint32_
           const uint64_t* __restrict__ Xq, int64_t xq_stride, uint64_t* __restrict__ part, int64_t part_stride,
           const int32_t* __restrict__ done, const int32_t* __restrict__ qbad) {
     using QC = QCode<LANES>;
-    constexpr int ROWB = LANES * 16, GPW = 32 / LANES, BE = 4 * LANES;   // codes per batch of one group
+    constexpr int ROWB = LANES * 16, GPW = 32 / LANES, BE = 4 * LANES;   // BE: codes per batch of one group
     extern __shared__ __align__(128) unsigned char smem[];
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + (((size_t)(TR + 1) * ROWB + 127) & ~(size_t)127));
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + (((size_t)(TR + 2) * ROWB + 127) & ~(size_t)127));
 
     const int r = blockIdx.y;
     if (done && done[r]) return;
@@ -122,10 +125,11 @@ k_estep_q(int TR, int64_t xrows, const int64_t* __restrict__ tptr, const uint32_
     const int G = warp * GPW + g;
     const uint32_t smem_base = smem_u32(smem);
     const uint32_t lane_off = (uint32_t)li * 16u;     // ORed into the row's byte offset (rows are ROWB-aligned)
-    const uint32_t zero_word = QC::word((uint32_t)TR, (uint32_t)TR);
+    // padding for positions beyond a group's run: zero rows of the parities this group's positions want (G + p) & 1
+    const uint32_t zero_word = QC::word((uint32_t)(TR + ((TR ^ G) & 1)), (uint32_t)(TR + ((TR ^ G ^ 1) & 1)));
 
     if (tid == 0) mbar_init(bar, 1);
-    for (int k = tid; k < ROWB / 8; k += blockDim.x) reinterpret_cast<uint64_t*>(smem + (size_t)TR * ROWB)[k] = 0ull;
+    for (int k = tid; k < 2 * ROWB / 8; k += blockDim.x) reinterpret_cast<uint64_t*>(smem + (size_t)TR * ROWB)[k] = 0ull;
     __syncthreads();
     uint32_t phase = 0;
     int loaded_tile = -1;
@@ -177,7 +181,8 @@ k_estep_q(int TR, int64_t xrows, const int64_t* __restrict__ tptr, const uint32_
         if (b1 <= 0) flush(0);                           // empty units at the head of the run
         int pos = 0;
         // every lane holds two stream words (four codes) of the current batch: LDG.64, so that a warp's stream loads touch
-        // each 32-byte sector once per 16 codes of a group
+        // each 32-byte sector once per 16 codes of a group.  (Staging the words in shared memory instead of shuffling them
+        // measured no better: a 16-byte broadcast read still costs one wavefront per quarter-warp.)
         const uint2 zero2 = make_uint2(zero_word, zero_word);
         uint2 word = (4 * li < run) ? __ldcs(reinterpret_cast<const uint2*>(words) + li) : zero2;
         while (__any_sync(0xffffffffu, u < uend)) {

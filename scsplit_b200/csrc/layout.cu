@@ -553,10 +553,12 @@ __global__ void k_qtile_scatter(int64_t nrows, int ntiles, int TR, const int64_t
 }
 // Order inside the units for 64-byte rows: two row groups share a quarter-warp wavefront, conflict-free when their rows lie
 // in different halves of the 128 bytes, i.e. differ in parity.  Position p of a unit whose phase is ph gets, wherever the
-// unit has one, a row of parity (ph + p) & 1 -- neighbouring groups have opposite phases.  One lane orders one unit, staged
-// in shared memory like k_order_units.
+// unit has one, a row of parity (ph + p) & 1 -- neighbouring groups have opposite phases.  The unit's padding codes are
+// wildcards: there is a zero row of either parity (TR, TR + 1), so they fill slots whose parity has run out of entries
+// before any entry has to take a slot of the wrong parity.  One lane orders one unit, staged in shared memory like
+// k_order_units.
 __global__ void __launch_bounds__(ORDER_WARPS * 32) k_qorder_units(const int64_t* __restrict__ tptr, uint16_t* __restrict__ tcode,
-                                                                  const uint8_t* __restrict__ phase, int64_t nunits, int upw) {
+                                                                  const uint8_t* __restrict__ phase, int64_t nunits, int upw, int TR) {
     __shared__ __align__(16) uint16_t s_in[ORDER_WARPS][ORDER_CAP], s_out[ORDER_WARPS][ORDER_CAP];
     const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
     const int64_t U0 = ((int64_t)blockIdx.x * ORDER_WARPS + wl) * upw;
@@ -573,15 +575,22 @@ __global__ void __launch_bounds__(ORDER_WARPS * 32) k_qorder_units(const int64_t
     for (int i = lane; i < len / 2; i += 32)
         reinterpret_cast<uint32_t*>(in)[i] = reinterpret_cast<const uint32_t*>(tcode + e0)[i];
     __syncwarp();
-    int i0 = 0, i1 = 0;                                               // next unread code of parity 0 / 1
+    int npad = 0;                                                     // padding codes sit at the end of the unit
+    while (npad < n && in[ua + n - 1 - npad] == (uint16_t)TR) ++npad;
+    const int ne = n - npad;                                          // real entries: in[ua .. ua + ne)
+    const uint16_t zrow[2] = {(uint16_t)(TR + (TR & 1)), (uint16_t)(TR + ((TR & 1) ^ 1))};   // zero row of parity 0 / 1
+    int i0 = 0, i1 = 0;                                               // next unread entry of parity 0 / 1
     for (int p = 0; p < n; ++p) {
-        while (i0 < n && (in[ua + i0] & 1u) != 0u) ++i0;
-        while (i1 < n && (in[ua + i1] & 1u) != 1u) ++i1;
+        while (i0 < ne && (in[ua + i0] & 1u) != 0u) ++i0;
+        while (i1 < ne && (in[ua + i1] & 1u) != 1u) ++i1;
         const int want = (ph + p) & 1;
-        int src;
-        if (want == 0) { if (i0 < n) src = i0++; else src = i1++; }
-        else           { if (i1 < n) src = i1++; else src = i0++; }
-        out[ua + p] = in[ua + src];
+        int& iw = want ? i1 : i0;
+        int& io = want ? i0 : i1;
+        uint16_t c;
+        if (iw < ne) c = in[ua + iw++];
+        else if (npad > 0) { c = zrow[want]; --npad; }
+        else c = in[ua + io++];
+        out[ua + p] = c;
     }
     __syncwarp();
     for (int i = lane; i < len / 2; i += 32)
@@ -666,7 +675,7 @@ int build_qtiled(scs_ctx* ctx, const Stream& s, TiledStream& t, int lanes, int T
         const int64_t avg = std::max<int64_t>(2, (total + nunits) / std::max<int64_t>(nunits, 1));
         const int upw = (int)std::min<int64_t>(32, std::max<int64_t>(1, (int64_t)ORDER_CAP * 2 / 3 / avg));
         const int64_t owarps = (nunits + upw - 1) / upw;
-        k_qorder_units<<<(unsigned)((owarps + ORDER_WARPS - 1) / ORDER_WARPS), ORDER_WARPS * 32, 0, st>>>(tptr, t.tcode, d_phase, nunits, upw);
+        k_qorder_units<<<(unsigned)((owarps + ORDER_WARPS - 1) / ORDER_WARPS), ORDER_WARPS * 32, 0, st>>>(tptr, t.tcode, d_phase, nunits, upw, TR);
         ctx->launches += 2;
     }
     if (lanes == 4) k_qpack_words<4><<<(unsigned)((total / 2 + 255) / 256), 256, 0, st>>>(total / 2, reinterpret_cast<uint32_t*>(t.tcode));
