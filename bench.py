@@ -526,7 +526,11 @@ def run_cuda_arm(args):
                      "achieved": dom_bytes / (dom_us * 1e-6) / 1e9,
                      "peak": peak, "unit": "GB/s", "frac": dom_bytes / (dom_us * 1e-6) / 1e9 / peak, "traffic": traffic, "traffic_source": traffic_src,
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": int(dom_bytes), "avg_launch_us": dom_us,
-                     "e_step": {"us": kt["e_us"], "bytes": int(eb), "GBps": eb / max(kt["e_us"], 1e-9) / 1e3, "launches_timed": kt["e_n"]},
+                     "e_step": {"us": kt["e_us"], "bytes": int(eb), "GBps": eb / max(kt["e_us"], 1e-9) / 1e3, "launches_timed": kt["e_n"],
+                                "what": "all launches that produce L: k_estep_q (per-(tile, cell) integer sums) + k_combine_q (fold over the tiles)" if einfo["q_lanes"] else "k_spmm_tiled + k_spmm_combine",
+                                "bayes_us": kt["bayes_us"],
+                                "with_bayes": {"us": kt["e_us"] + kt["bayes_us"], "frac": eb / max(kt["e_us"] + kt["bayes_us"], 1e-9) / 1e3 / peak,
+                                               "what": "the whole E-step (scSplit:165-188): sums + k_bayes (posteriors, LL, column mass)"}},
                      "m_step": {"us": kt["m_us"], "bytes": int(mb), "GBps": mb / max(kt["m_us"], 1e-9) / 1e3, "launches_timed": kt["m_n"]},
                      "iteration_frac": (eb + mb) / (dev_s / args.steps) / 1e9 / peak},
     }

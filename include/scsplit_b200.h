@@ -144,11 +144,12 @@ int scs_launch_count(scs_ctx* ctx, int64_t* out);
 /* average device time in microseconds of the E-step SpMM and M-step SpMM launches recorded with CUDA events
  * on the context's stream since the last reset; pass reset=1 to clear. out[0]=E us, out[1]=M us,
  * out[2]=#E-steps timed, out[3]=#M-steps timed, out[4]=us of statistics all-reduce per timed M-step (cells sharded over
- * ranks; the pieces overlap the M-step kernels), out[5]=#all-reduce pieces timed.  scs_set_timing(ctx, n): n = 0 off, n >= 1 times every n-th E-step and
+ * ranks; the pieces overlap the M-step kernels), out[5]=#all-reduce pieces timed, out[6]=us of the Bayes kernel (posteriors, LL, statistics),
+ * out[7]=#launches of it timed.  scs_set_timing(ctx, n): n = 0 off, n >= 1 times every n-th E-step and
  * every n-th M-step of the EM loop (the event records cost ~11 us per timed iteration at config 3, so a loop that is
  * itself being timed samples, e.g. n = 8); step-level calls outside the loop are always timed while n >= 1. */
 int scs_set_timing(scs_ctx* ctx, int enable);
-int scs_kernel_times(scs_ctx* ctx, double out[6], int reset);
+int scs_kernel_times(scs_ctx* ctx, double out[8], int reset);
 /* select kernel variant (before scs_em_begin): 0 = auto (fixed-point E-step where the pool fits the format, sparse M-step
  * once posteriors saturate), 1 = v1 (warp per row, gathers from L1/L2; for A/B tests), 2 = tiled fp64 SpMM for both
  * half-steps (sparse M-step off), 3 = tiled fp64 E-step + sparse M-step (the fixed-point E-step off) */

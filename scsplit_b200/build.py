@@ -26,19 +26,24 @@ def _stale(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    """Compile every .cu for sm_100a and link the shared library. Returns the library path."""
+def build(force=False, verbose=False, bounds=False):
+    """Compile every .cu for sm_100a and link the shared library. Returns the library path.
+
+    bounds=True builds libscsplit_b200_bounds.so with the device-side index checks (SCS_ASSERT) compiled in; point
+    SCSPLIT_B200_LIB at it to run the test-suite against it."""
     nvcc = _nvcc()
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     headers.append(os.path.join(os.path.dirname(HERE), "include", "scsplit_b200.h"))
-    objdir = os.path.join(HERE, "build")
+    objdir = os.path.join(HERE, "build_bounds" if bounds else "build")
+    lib = os.path.join(HERE, "libscsplit_b200_bounds.so") if bounds else LIB
+    flags = NVCC_FLAGS + (["-DSCS_BOUNDS_CHECK"] if bounds else ["-DNDEBUG"])
     os.makedirs(objdir, exist_ok=True)
     jobs = []
     for src in SOURCES:
         s = os.path.join(CSRC, src)
         o = os.path.join(objdir, src.replace(".cu", ".o"))
         if force or _stale(o, [s] + headers):
-            jobs.append([nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o])
+            jobs.append([nvcc] + flags + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o])
 
     def run(cmd):
         p = subprocess.run(cmd, capture_output=True, text=True)
@@ -52,10 +57,10 @@ def build(force=False, verbose=False):
         for l in logs:
             sys.stderr.write(l)
     objs = [os.path.join(objdir, s.replace(".cu", ".o")) for s in SOURCES]
-    if force or jobs or _stale(LIB, objs):
-        run([nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-ldl", "-lpthread"])
-    return LIB
+    if force or jobs or _stale(lib, objs):
+        run([nvcc, "-shared", "-o", lib] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-ldl", "-lpthread"])
+    return lib
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, bounds="--bounds" in sys.argv))

@@ -161,7 +161,7 @@ int scs_set_variant(scs_ctx* ctx, int variant) {
     return 0;
 }
 
-int scs_kernel_times(scs_ctx* ctx, double out[6], int reset) {
+int scs_kernel_times(scs_ctx* ctx, double out[8], int reset) {
     SCS_CHECK(ctx && out, "null argument");
     SCS_CUDA(cudaSetDevice(ctx->device));
     SCS_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -183,8 +183,10 @@ int scs_kernel_times(scs_ctx* ctx, double out[6], int reset) {
     // the all-reduce of a step is issued in pieces: their durations are summed per sampled M-step
     out[4] = ctx->m_samples ? ctx->t_sum[3] / (double)ctx->m_samples : 0.0;
     out[5] = (double)ctx->t_cnt[3];
+    out[6] = ctx->t_cnt[4] ? ctx->t_sum[4] / (double)ctx->t_cnt[4] : 0.0;
+    out[7] = (double)ctx->t_cnt[4];
     if (reset) {
-        for (int i = 0; i < 4; ++i) { ctx->t_sum[i] = 0.0; ctx->t_cnt[i] = 0; }
+        for (int i = 0; i < 5; ++i) { ctx->t_sum[i] = 0.0; ctx->t_cnt[i] = 0; }
         ctx->m_samples = 0;
     }
     return 0;

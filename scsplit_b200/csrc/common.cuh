@@ -29,6 +29,16 @@ void set_error(const char* fmt, ...);
         }                                 \
     } while (0)
 
+// Device-side bounds checks of the gather / scatter indices (compute-sanitizer is not available on the pool's boxes): compiled
+// in with -DSCS_BOUNDS_CHECK (python -m scsplit_b200.build --bounds -> libscsplit_b200_bounds.so, selected with
+// SCSPLIT_B200_LIB); a violated check traps the kernel, which the next CUDA call reports.
+#ifdef SCS_BOUNDS_CHECK
+#include <assert.h>
+#define SCS_ASSERT(cond) assert(cond)
+#else
+#define SCS_ASSERT(cond) ((void)0)
+#endif
+
 #define SCS_TRY(expr)        \
     do {                     \
         int _r = (expr);     \
@@ -166,8 +176,8 @@ struct scs_ctx {
     std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> ev_pending;  // (kind, (start, stop))
     cudaEvent_t ev_iter[2] = {nullptr, nullptr};   // brackets the launches of the last scs_em_iterate
     double last_iter_ms = 0.0;
-    double t_sum[4] = {0, 0, 0, 0};   // E SpMM, M tiled SpMM, M sparse kernel, statistics all-reduce pieces
-    int64_t t_cnt[4] = {0, 0, 0, 0};
+    double t_sum[5] = {0, 0, 0, 0, 0};   // E-step sums (all launches), M tiled SpMM, M sparse kernel, statistics all-reduce pieces, k_bayes
+    int64_t t_cnt[5] = {0, 0, 0, 0, 0};
 };
 
 namespace scs {

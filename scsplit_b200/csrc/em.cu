@@ -278,32 +278,46 @@ static int run_e(scs_ctx* ctx, const int32_t* done) {
     EmState& em = ctx->em;
     PhaseSample sample(ctx, 0);
     const int64_t V = ctx->V, N = ctx->N;
+    LSource src;
     if (em.Tq) {
-        // fixed-point sums for every restart whose table fits the format; the (rare) others -- flagged by k_finalize -- take the
-        // fp64 row kernel, which needs no tile-major stream of its own
+        // fixed-point sums (k_estep_q, folded over the tiles into L by k_combine_q) for every restart whose table fits the format;
+        // k_bayes gathers the rows of the (rare) restarts flagged by k_finalize from the fp64 table itself
         cudaEvent_t ea, eb;
         SCS_TRY(timing_begin(ctx, &ea, &eb));
         SCS_TRY(launch_estep_q(ctx, done));
-        const int WPB = 8;
-        dim3 rgrid((unsigned)std::min<int64_t>((N + WPB - 1) / WPB, (int64_t)(ctx->sm_count > 0 ? ctx->sm_count : 148) * 8), (unsigned)em.R);
-        SCS_DISPATCH_KP(em.KP, (k_spmm_rows<KPc><<<rgrid, WPB * 32, 0, ctx->stream>>>(N, ctx->E.lptr, ctx->E.lcode, ctx->E.hptr, ctx->E.hcode, ctx->E.hcnt,
-                                                                                     em.T, 2 * V * em.KP, em.L, N * em.KP, done, em.qbad)));
-        ctx->launches++;
         SCS_TRY(timing_end(ctx, 0, ea, eb));
+        src.qbad = em.qbad;
+        src.lptr = ctx->E.lptr; src.hptr = ctx->E.hptr; src.lcode = ctx->E.lcode; src.hcode = ctx->E.hcode; src.hcnt = ctx->E.hcnt;
+        src.T = em.T;
+        src.t_stride = 2 * V * em.KP;
     } else {
         SCS_TRY(launch_spmm(ctx, 0, em.KP, em.R, em.T, 2 * V * em.KP, em.L, N * em.KP, done));
     }
+    cudaEvent_t ba, bb;                                  // the Bayes kernel (kind 4)
+    SCS_TRY(timing_begin(ctx, &ba, &bb));
     dim3 grid((unsigned)em.nblk, (unsigned)em.R);
-    SCS_DISPATCH_KP(em.KP, (k_bayes<KPc><<<grid, 1024, 0, ctx->stream>>>(N, em.K, em.L, em.W, em.lps, em.partial, em.nblk, em.hq,
+    SCS_DISPATCH_KP(em.KP, (k_bayes<KPc><<<grid, 1024, 0, ctx->stream>>>(N, em.K, src, em.L, em.W, em.lps, em.partial, em.nblk, em.hq,
                                                                               em.h_stride, done, em.stats + 2 * V * em.KP,
                                                                               em.stats_stride, em.sched + 3 * em.R, em.sat,
                                                                               (double)std::max<int64_t>(4, N / 128))));
     ctx->launches += 1;
+    SCS_TRY(timing_end(ctx, 4, ba, bb));
     SCS_CUDA(cudaGetLastError());
     return 0;
 }
 
-constexpr int M_CHUNKS = 4;   // row ranges of the M-step sums whose all-reduce overlaps the next range's kernel (cells sharded over ranks)
+// Row ranges of the M-step sums whose all-reduce may overlap the next range's kernel (cells sharded over ranks).  Measured on
+// 8 x B200 at config 4 (25k cells per rank, profiles/r02_bench_8gpu_chunked.json): 4 ranges LOSE to one -- 1.00 ms against
+// 0.86 ms per iteration.  The sparse M-step is a persistent kernel that fills every SM (768-1024 threads, ~210 KB of shared
+// memory per CTA), so an NCCL kernel on the second stream only gets SMs as a range's CTAs drain, and then holds them against
+// the next range's CTAs: the M-step went 155 -> 202 us and four latency-bound 4 MB collectives cost more than one of 17 MB.
+// The default is therefore ONE range (plus the posterior tail, which does overlap the M-step); SCS_M_CHUNKS=n re-enables it.
+constexpr int M_CHUNKS_MAX = 8;
+static int m_chunks_wanted() {
+    const char* e = std::getenv("SCS_M_CHUNKS");
+    const int n = e ? atoi(e) : 1;
+    return n < 1 ? 1 : n > M_CHUNKS_MAX ? M_CHUNKS_MAX : n;
+}
 
 // One sum all-reduce of a piece of the statistics of every live restart, stats -> gstats, on the communication stream, after
 // `after` (an event of the main stream) has fired.  Timed (kind 3) when the step is sampled.
@@ -355,9 +369,9 @@ static int run_m(scs_ctx* ctx, const int32_t* done, int track, int check_conv) {
     // live restart set, the tiled pair -- which those restarts can no longer take -- is not launched at all)
     if (!(sparse && em.sparse_only))
         SCS_TRY(launch_spmm(ctx, 1, em.KP, em.R, em.W, N * em.KP, em.stats, em.stats_stride, done, gate));
-    // (a piece of the sums is worth its own launch from ~16 M entries per rank on: below that the launches cost more than the
-    // overlap hides; decided from the pool's global size so that every rank issues the same collectives)
-    const int nchunks = multi ? (int)std::min<int64_t>(M_CHUNKS, std::max<int64_t>(1, ctx->entries_global / ctx->world / (16 << 20))) : 1;
+    // (more than one range only on request, and only from ~16 M entries per rank on; decided from the pool's global size so
+    // that every rank issues the same collectives)
+    const int nchunks = multi ? (int)std::min<int64_t>(m_chunks_wanted(), std::max<int64_t>(1, ctx->entries_global / ctx->world / (16 << 20))) : 1;
     const int64_t nrows = ctx->M.nrows;
     // rows [lo, hi) of chunk c: the keys of build_row_order put row i into chunk i * nchunks / nrows
     auto chunk_lo = [&](int c) { return ((int64_t)c * nrows + nchunks - 1) / nchunks; };

@@ -227,8 +227,43 @@ inline int bayes_cells_per_block(int KP) { return KP <= 16 ? 64 : 32; }
 // cells skip the pass), so every block does the same work whatever N is and the grid can be sized to the SM count.
 __device__ __forceinline__ int64_t bayes_cell_lo(int64_t N, int b, int nblk) { return N * b / nblk; }
 
+// The E-step sums normally reach k_bayes through L (written by k_combine_q or the fp64 SpMM kernels).  With the fixed-point
+// E-step a restart whose table did not fit the format (qbad[r], set by k_finalize) has no sums: k_bayes gathers that
+// restart's rows from the fp64 table right here -- every lane walks the cell's entries for its own state -- and writes L for
+// the readers of lP_c_s.  Rare (a dying cluster), so it is the slow simple loop, not a kernel of its own standing by.
+struct LSource {
+    const int32_t* qbad = nullptr;    // [R]; nullptr: L is always in memory
+    const int64_t* lptr = nullptr;    // cell-major stream (count-1 / count>1 entries)
+    const int64_t* hptr = nullptr;
+    const uint32_t* lcode = nullptr;
+    const uint32_t* hcode = nullptr;
+    const int32_t* hcnt = nullptr;
+    const double* T = nullptr;        // [R][2V][KP]
+    int64_t t_stride = 0;
+};
+
 template <int KP>
-__global__ void __launch_bounds__(1024) k_bayes(int64_t N, int K, const double* __restrict__ L, double* __restrict__ W,
+__device__ __forceinline__ double bayes_row_from_table(const LSource& s, int r, int64_t c, bool cell, int i, int K) {
+    const double* T = s.T + (int64_t)r * s.t_stride;
+    double acc = 0.0;
+    if (cell && i < K) {
+        const int64_t lb = s.lptr[c], le = s.lptr[c + 1];
+        int64_t e = lb;
+        for (; e + 2 <= le; e += 2) {
+            const double x0 = __ldg(T + (int64_t)(__ldg(s.lcode + e) >> 1) * KP + i);
+            const double x1 = __ldg(T + (int64_t)(__ldg(s.lcode + e + 1) >> 1) * KP + i);
+            acc += x0;
+            acc += x1;
+        }
+        for (; e < le; ++e) acc += __ldg(T + (int64_t)(__ldg(s.lcode + e) >> 1) * KP + i);
+        for (int64_t h = s.hptr[c]; h < s.hptr[c + 1]; ++h)
+            acc += (double)__ldg(s.hcnt + h) * __ldg(T + (int64_t)(__ldg(s.hcode + h) >> 1) * KP + i);
+    }
+    return acc;
+}
+
+template <int KP>
+__global__ void __launch_bounds__(1024) k_bayes(int64_t N, int K, const LSource src, double* __restrict__ L, double* __restrict__ W,
                                                const double* __restrict__ lps, double* __restrict__ partial, int nblk,
                                                uint32_t* __restrict__ hq, int64_t h_stride, const int32_t* __restrict__ done,
                                                double* __restrict__ tail /* stats + tail_off */, int64_t stats_stride,
@@ -246,7 +281,13 @@ __global__ void __launch_bounds__(1024) k_bayes(int64_t N, int K, const double* 
     for (int64_t c0 = c_lo + (threadIdx.x >> 5) * (32 / C::GL); c0 < c_hi; c0 += C::CPB) {   // warp-uniform
         const int64_t c = c0 + (threadIdx.x & 31) / C::GL;
         const bool cell = c < c_hi, live = cell && i < K;
-        const double Li = live ? L[((int64_t)r * N + c) * KP + i] : 0.0;
+        double Li;
+        if (src.qbad && src.qbad[r]) {
+            Li = bayes_row_from_table<KP>(src, r, c, cell, i, K);
+            if (cell && i < KP) L[((int64_t)r * N + c) * KP + i] = Li;
+        } else {
+            Li = live ? L[((int64_t)r * N + c) * KP + i] : 0.0;
+        }
         const double ti = Li + si;                                   // L_i + s_i
         double denom = 0.0;
         for (int j = 0; j < K; ++j) {                                // j ascending, left to right, as the reference adds

@@ -10,7 +10,7 @@
 // carries an absolute error of at most 2^-(F+1), and then nothing is lost any more -- an fp64 accumulation of ~1500 terms
 // of magnitude ~1 rounds at 2^-43 per add.  tests/test_gpu_qpath.py measures both paths against extended-precision sums.
 // A table that does not fit the format (NaN / -inf of a dying cluster, |x| >= 64) raises the restart's `qbad` flag in
-// k_finalize and that restart's E-step runs in fp64 (k_spmm_rows) for that iteration.
+// k_finalize and that restart's rows are gathered from the fp64 table by k_bayes for that iteration.
 //
 // Row layout (LANES = 4 or 8 lanes of 16 bytes; lane j holds values a = 2j, b = 2j+1 and one byte pair of the "extra"
 // value x = 2*LANES when K is odd-full (K = 9 / 17)), as two 64-bit words:
@@ -20,7 +20,7 @@
 // pb at bit 24; a unit holds < 65536 codes, which keeps the low field below 2^24).  Two 64-bit adds on the integer pipe
 // and one IMAD.WIDE on the multiply pipe per 16 bytes -- an IMAD.WIDE per 32-bit word (which would also carry a per-entry
 // count) measured multiply-pipe bound at 2.7x the shared-memory floor.  Counts therefore are not multiplied: an entry of
-// count c <= Q_REP_MAX is c codes, larger counts (rare in droplet data) are added in fp64 by the combine kernel.
+// count c <= Q_REP_MAX is c codes, larger counts (rare in droplet data) are added in fp64 by k_combine_q.
 //
 // Stream: 32-bit words of two codes, word = rowA << SA | rowB << (SA + 14), SA = log2(row bytes): the first row's byte
 // offset is one AND away, the second's a shift and an AND.  Padding codes point at one of the two all-zero rows TR, TR + 1
@@ -168,6 +168,7 @@ k_estep_q(int TR, int64_t xrows, const int64_t* __restrict__ tptr, const uint32_
         auto flush = [&](int upto) {       // flush every unit that ends at or before stream position `upto`
             do {
                 uint64_t* dst = part + (u * LANES + li) * 3;
+                SCS_ASSERT(u >= 0 && (u * LANES + li) * 3 + 2 < part_stride);
                 dst[0] = acc.a;
                 dst[1] = acc.b;
                 dst[2] = acc.pp;
@@ -199,6 +200,7 @@ k_estep_q(int TR, int64_t xrows, const int64_t* __restrict__ tptr, const uint32_
                 for (int jj = 0; jj < UW; ++jj) {
                     const int wi = j0 + jj;              // word wi of the batch sits in lane wi / 2 of the group, component wi & 1
                     const uint32_t w = __shfl_sync(0xffffffffu, (wi & 1) ? mine.y : mine.x, g * LANES + wi / 2);
+                    SCS_ASSERT(((w & QC::MASK) >> QC::SA) <= (uint32_t)TR + 1 && (((w >> 14) & QC::MASK) >> QC::SA) <= (uint32_t)TR + 1);
                     v[2 * jj] = lds_u32x4(smem_base + ((w & QC::MASK) | lane_off));
                     v[2 * jj + 1] = lds_u32x4(smem_base + (((w >> 14) & QC::MASK) | lane_off));
                 }

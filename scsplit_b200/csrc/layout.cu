@@ -537,6 +537,7 @@ __global__ void k_qtile_scatter(int64_t nrows, int ntiles, int TR, const int64_t
         const int64_t g = (int64_t)(lcode[i] >> 1);
         const int64_t t = g / TR;
         const int64_t u = t * nrows + row;
+        SCS_ASSERT(t < ntiles && i - b - ulo[u] >= 0 && tptr[u] + (i - b - ulo[u]) < tptr[u + 1]);
         tcode[tptr[u] + (i - b - ulo[u])] = (uint16_t)(g - t * TR);
     }
     for (int64_t t = lane; t < ntiles; t += 32) {
@@ -548,6 +549,7 @@ __global__ void k_qtile_scatter(int64_t nrows, int ntiles, int TR, const int64_t
             const uint16_t rowt = (uint16_t)((int64_t)(hcode[h] >> 1) - t * TR);
             for (int64_t c = q_codes_of(hcnt[h]); c > 0; --c) tcode[pos++] = rowt;
         }
+        SCS_ASSERT(pos <= end);
         for (; pos < end; ++pos) tcode[pos] = (uint16_t)TR;
     }
 }

@@ -200,6 +200,10 @@ k_mstep_sparse(int64_t nrows, int64_t njobs, int64_t N, int K, const int32_t* __
 #pragma unroll
             for (int j = 0; j < UV; ++j) trim_vec(cur[j], v + j * SPARSE_GS, a, m);
 #pragma unroll
+            for (int j = 0; j < UV; ++j)   // every code (cell << 1 | dup) addresses the staged table: cell <= h_stride (the NOP word)
+                SCS_ASSERT((cur[j].x >> 1) <= (uint32_t)h_stride && (cur[j].y >> 1) <= (uint32_t)h_stride && (cur[j].z >> 1) <= (uint32_t)h_stride &&
+                           (cur[j].w >> 1) <= (uint32_t)h_stride);
+#pragma unroll
             for (int j = 0; j < UV; ++j) {
                 q[4 * j + 0] = lds_u32(tab + ((cur[j].x & ~1u) << 1));
                 q[4 * j + 1] = lds_u32(tab + ((cur[j].y & ~1u) << 1));
@@ -259,6 +263,7 @@ k_mstep_sparse(int64_t nrows, int64_t njobs, int64_t N, int K, const int32_t* __
             int base = 0, nval = KP;
             GR::run(v, out, li, base, nval);
             if (act) {
+                SCS_ASSERT(job.row >= 0 && job.row < nrows);
                 double* y = S + job.row * KP;
 #pragma unroll
                 for (int i = 0; i < GR::LEFT; ++i)

@@ -171,6 +171,7 @@ k_spmm_tiled(int64_t nrows, int TR, int64_t xrows, const int64_t* __restrict__ t
 #pragma unroll
                 for (int jj = 0; jj < UW; ++jj) {         // 2*UW LDS.128 in flight per lane before the adds
                     const uint32_t w = __shfl_sync(0xffffffffu, mine, g * C::GS + j0 + jj);
+                    SCS_ASSERT((w & 0xffffu) <= (uint32_t)TR && (w >> 16) <= (uint32_t)TR);
                     v[2 * jj] = lds_f64x2(lane_base + (w & 0xffffu) * (KP * 8));
                     v[2 * jj + 1] = lds_f64x2(lane_base + (w >> 16) * (KP * 8));
                 }
@@ -193,6 +194,7 @@ k_spmm_tiled(int64_t nrows, int TR, int64_t xrows, const int64_t* __restrict__ t
             e = (u < uend) ? lim : e;
             // flush every unit the stream has passed (an empty unit is passed immediately and stores zeros)
             while (u < uend && e >= b1) {
+                SCS_ASSERT(u >= 0 && (u + 1) * KP <= part_stride);
                 if (li < C::CH)
                     *reinterpret_cast<double2*>(part + u * KP + 2 * li) = make_double2(c0.x + c1.x, c0.y + c1.y);
                 if constexpr (C::SIDE) {                  // the side chunk's sum is spread over the lanes of the group

@@ -237,9 +237,10 @@ class Engine:
         check(self.lib.scs_set_timing(self.h, int(every) if on else 0))
 
     def kernel_times(self, reset=False):
-        out = (ctypes.c_double * 6)()
+        out = (ctypes.c_double * 8)()
         check(self.lib.scs_kernel_times(self.h, out, 1 if reset else 0))
-        return dict(e_us=out[0], m_us=out[1], e_n=int(out[2]), m_n=int(out[3]), allreduce_us=out[4], allreduce_n=int(out[5]))
+        return dict(e_us=out[0], m_us=out[1], e_n=int(out[2]), m_n=int(out[3]), allreduce_us=out[4], allreduce_n=int(out[5]),
+                    bayes_us=out[6], bayes_n=int(out[7]))
 
     def set_variant(self, v):
         check(self.lib.scs_set_variant(self.h, int(v)))
