@@ -479,6 +479,21 @@ def run_cuda_arm(args):
     if world == 1 and rank == 0 and not args.quick:
         extras["regimes"] = dict(saturated_ms_per_step=1000.0 * dev_s / args.steps, **regime_times(Engine, pool, P0, local))
         extras["small_configs"] = small_config_times(Engine, local)
+        try:     # the whole `scSplit run` CLI, CSV files in, result files out (tools/cli_e2e.py), next to the recorded reference runs
+            import importlib.util
+            import io
+            import contextlib
+            spec = importlib.util.spec_from_file_location("cli_e2e", os.path.join(ROOT, "tools", "cli_e2e.py"))
+            mod = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(mod)
+            with contextlib.redirect_stdout(io.StringIO()):          # ("Repeat n was chosen." belongs to the CLI, not to this line)
+                r = mod.run(argparse.Namespace(workload=args.workload, ems=30, seed=2003, keep=None))
+            extras["cli_e2e"] = {k: r[k] for k in ("workload", "wall_s", "phases_s", "em_iterations", "csv_mb", "assigned_cells", "agreement_with_truth")}
+            extras["cli_e2e"]["reference"] = "profiles/r02_ref_cli_c3.json: the reference CLI took 1099 s for the same CSVs with -e 2 (this CLI: 1.3 s, identical partition, profiles/r02_cli_e2e_c3_e2.json); with -e 30 it was not run (~70 min estimated, BASELINE.md)"
+            if os.path.exists("scSplit_dist_variants.txt"):
+                os.remove("scSplit_dist_variants.txt")
+        except Exception as exc:
+            extras["cli_e2e"] = {"error": "%s: %s" % (type(exc).__name__, exc)}
 
     # ---- second leg: config 4, cells sharded over the ranks, NCCL all-reduce per iteration (N = 1: the anchor)
     cells = None

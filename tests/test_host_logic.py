@@ -130,3 +130,57 @@ def test_csv_parser_matches_pandas(tmp_path):
     open(rg, "w").write("SNV,a,b\n1:5,1\n")
     with pytest.raises(Exception):
         cli.read_count_csv(rg)
+
+
+def test_positions_to_drop_equals_np_unique():
+    """initialiser._positions_to_drop (scSplit:113-114) returns what np.unique(int(beta * n)) returns, from the same draws."""
+    from scsplit_b200 import initialiser as I
+    for n in (0, 4, 50, 3000, 30000):
+        r1, r2 = np.random.RandomState(n + 1), np.random.RandomState(n + 1)
+        got = I._positions_to_drop(r1, n)
+        want = np.unique((r2.beta(1, 10, int(0.1 * n + 0.5)) * n).astype(np.int64))
+        assert np.array_equal(got, want)
+        assert r1.rand() == r2.rand()                  # same number of variates consumed
+
+
+def test_synthetic_pool_is_the_same_from_threads():
+    from scsplit_b200 import synth
+    a = synth.make_pool(700, 2500, 3, 0.05, 0.05, seed=11)
+    b = synth.make_pool(700, 2500, 3, 0.05, 0.05, seed=11, workers=3)
+    assert (a.ref != b.ref).nnz == 0 and (a.alt != b.alt).nnz == 0 and np.array_equal(a.truth, b.truth)
+    c = synth.make_pool(700, 2500, 3, 0.05, 0.05, seed=11, cell_lo=1000, cell_hi=2100, workers=2)
+    assert (a.ref[:, 1000:2100] != c.ref).nnz == 0 and (a.alt[:, 1000:2100] != c.alt).nnz == 0
+
+
+def test_fixed_point_format_helpers():
+    """Host mirror of the fixed-point E-step's format arithmetic (csrc/estep_q.cuh): fraction bits from the deepest cell, the
+    byte-pair packing of the extra value, and the wrap-around recovery of the sums."""
+    def frac_bits(depth):
+        b = 0
+        while (1 << b) <= depth and b < 62:
+            b += 1
+        return min(49, 63 - 6 - b)
+    assert frac_bits(1600) == 46 and frac_bits(3100) == 45 and frac_bits(1) == 49 and frac_bits((1 << 17)) == 39
+    rng = np.random.default_rng(0)
+    F, n = 46, 1500
+    x = -rng.uniform(0, 40, size=(n, 9))
+    q = np.rint(-x * 2.0 ** F).astype(np.uint64)
+    assert (q < (1 << 55)).all()
+    cnt = rng.integers(1, 9, size=n).astype(np.uint64)
+    # lane j: q0 = a | pa << 56, q1 = b | pb << 56 with pa/pb bytes 2j, 2j+1 of the ninth value; all sums mod 2^64
+    tot = np.zeros(9, dtype=object)
+    for j in range(4):
+        a, b, ex = q[:, 2 * j], q[:, 2 * j + 1], q[:, 8]
+        pa, pb = (ex >> np.uint64(16 * j)) & np.uint64(255), (ex >> np.uint64(16 * j + 8)) & np.uint64(255)
+        s0 = int(sum(int(c) * (int(v) | (int(p) << 56)) for c, v, p in zip(cnt, a, pa))) % (1 << 64)
+        s1 = int(sum(int(c) * (int(v) | (int(p) << 56)) for c, v, p in zip(cnt, b, pb))) % (1 << 64)
+        spa, spb = int(sum(int(c) * int(p) for c, p in zip(cnt, pa))), int(sum(int(c) * int(p) for c, p in zip(cnt, pb)))
+        assert spa < (1 << 24)
+        tot[2 * j] = (s0 - (spa << 56)) % (1 << 64)
+        tot[2 * j + 1] = (s1 - (spb << 56)) % (1 << 64)
+        tot[8] = tot[8] + (spa << (16 * j)) + (spb << (16 * j + 8))
+    want = [int(sum(int(c) * int(v) for c, v in zip(cnt, q[:, k]))) for k in range(9)]
+    assert [int(t) for t in tot] == want
+    L = -np.array(want, dtype=np.float64) * 2.0 ** -F
+    exact = (cnt[:, None].astype(np.float64) * x).sum(axis=0)
+    assert np.allclose(L, exact, rtol=1e-12, atol=0)

@@ -24,6 +24,13 @@ def main():
     ap.add_argument("--seed", type=int, default=2002)
     ap.add_argument("--keep", default=None)
     args = ap.parse_args()
+    print(json.dumps(run(args)))
+    if os.path.exists("scSplit_dist_variants.txt"):
+        os.remove("scSplit_dist_variants.txt")
+
+
+def run(args):
+    """args: workload, ems, seed, keep.  Returns the dict that main() prints."""
     from scsplit_b200 import cli, synth, models as M
     cfg = synth.CONFIGS[args.workload]
     pool = synth.make_config(args.workload)
@@ -58,8 +65,10 @@ def main():
            "wall_s": wall, "phases_s": phases, "em_iterations": log.count("E-M Iteration "), "csv_mb": os.path.getsize(rp) / 1e6,
            "clusters": res["Cluster"].value_counts().to_dict(), "assigned_cells": int(len(res)),
            "agreement_with_truth": partition_agreement(res["Cluster"].values, truth)}
-    gpath = os.path.join(ROOT, "tests", "golden", "cli_%s.npz" % args.workload)
-    if os.path.exists(gpath):
+    gpath = os.path.join(ROOT, "tests", "golden", "cli_%s_e%d.npz" % (args.workload, args.ems))   # reference run with the same -e
+    if not os.path.exists(gpath):
+        gpath = os.path.join(ROOT, "tests", "golden", "cli_%s.npz" % args.workload)
+    if os.path.exists(gpath) and int(np.load(gpath)["ems"] if "ems" in np.load(gpath) else 30) == args.ems:
         g = np.load(gpath)
         ref = pd.Series(g["result_cluster"], index=g["result_barcode"])
         both = res[res["Barcode"].isin(ref.index)]
@@ -68,11 +77,9 @@ def main():
         out["reference_assigned_cells"] = int(len(ref))
         out["cells_assigned_by_both"] = int(len(both))
         out["agreement_with_reference"] = partition_agreement(both["Cluster"].values, ref[both["Barcode"]].values)
-    print(json.dumps(out))
     if not args.keep:
         shutil.rmtree(tmp, ignore_errors=True)
-    if os.path.exists("scSplit_dist_variants.txt"):
-        os.remove("scSplit_dist_variants.txt")
+    return out
 
 
 if __name__ == "__main__":
