@@ -123,9 +123,11 @@ struct EmState {
     int32_t* done = nullptr;    // [R]
     int nblk = 0;
     // One EM iteration (E-step + M-step launches) captured as a CUDA graph, per launch set: [check_conv][sparse_only].  A set is
-    // captured the second time it is needed (the first pass does the lazy builds and attribute calls a capture cannot hold).
+    // captured once it has been launched GRAPH_AFTER times the plain way: the first pass does the lazy builds and attribute
+    // calls a capture cannot hold, and capture + instantiation only pay back over a dozen or so replays (a restart of a
+    // handful of iterations, e.g. one end-to-end call of bench.py, never captures).
     cudaGraphExec_t graph[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
-    bool graph_warm[2][2] = {{false, false}, {false, false}};
+    int graph_warm[2][2] = {{0, 0}, {0, 0}};
     int graph_launches[2][2] = {{0, 0}, {0, 0}};   // kernels inside each captured iteration
 };
 

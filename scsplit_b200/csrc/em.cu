@@ -69,7 +69,7 @@ int launch_spmm(scs_ctx* ctx, int kind, int KP, int R, const double* X, int64_t 
         const int WPB = 8;
         dim3 grid((unsigned)((s.nrows + WPB - 1) / WPB), (unsigned)R);
         SCS_DISPATCH_KP(KP, (k_spmm_rows<KPc><<<grid, WPB * 32, 0, ctx->stream>>>(s.nrows, s.lptr, s.lcode, s.hptr, s.hcode, s.hcnt, X,
-                                                                                  x_stride, Y, y_stride, done, nullptr)));
+                                                                                  x_stride, Y, y_stride, done)));
         ctx->launches++;
     }
     SCS_TRY(timing_end(ctx, kind, ea, eb));
@@ -584,14 +584,18 @@ int scs_mstep(scs_ctx* ctx) {
 // One iteration: the launches of run_e + run_m, replayed from a CUDA graph where one exists for the current launch set.
 static int em_one_iteration(scs_ctx* ctx, const int32_t* done, int check_conv) {
     EmState& em = ctx->em;
-    const bool graphs = ctx->use_graphs && ctx->world == 1 && !ctx->timing && !std::getenv("SCS_NO_GRAPH");
+    constexpr int GRAPH_AFTER = 8;
+    // an iteration whose kernels are being timed (every ctx->timing-th) is launched the plain way: events cannot sit inside a replay
+    const bool sampled = ctx->timing && (ctx->phase_seen[0] % ctx->timing) == 0;
+    const bool graphs = ctx->use_graphs && ctx->world == 1 && !sampled && !std::getenv("SCS_NO_GRAPH");
     const int a = check_conv ? 1 : 0, b = em.sparse_only ? 1 : 0;
     if (graphs && em.graph[a][b]) {
         SCS_CUDA(cudaGraphLaunch(em.graph[a][b], ctx->stream));
         ctx->launches += em.graph_launches[a][b];
+        if (ctx->timing) { ctx->phase_seen[0]++; ctx->phase_seen[1]++; }     // (what run_e / run_m would have counted)
         return 0;
     }
-    if (graphs && em.graph_warm[a][b]) {
+    if (graphs && em.graph_warm[a][b] >= GRAPH_AFTER) {
         const int64_t l0 = ctx->launches;
         cudaGraph_t g = nullptr;
         SCS_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
@@ -612,6 +616,7 @@ static int em_one_iteration(scs_ctx* ctx, const int32_t* done, int check_conv) {
                 em.graph[a][b] = x;
                 em.graph_launches[a][b] = (int)(ctx->launches - l0);
                 ctx->launches = l0;
+                if (ctx->timing) { ctx->phase_seen[0]--; ctx->phase_seen[1]--; }   // the capture pass counted itself; the replay below counts again
                 return em_one_iteration(ctx, done, check_conv);
             }
             cudaGetLastError();
@@ -621,7 +626,7 @@ static int em_one_iteration(scs_ctx* ctx, const int32_t* done, int check_conv) {
     }
     SCS_TRY(run_e(ctx, done));
     SCS_TRY(run_m(ctx, done, 1, check_conv));
-    em.graph_warm[a][b] = true;
+    em.graph_warm[a][b]++;
     return 0;
 }
 

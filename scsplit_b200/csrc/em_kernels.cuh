@@ -1,13 +1,15 @@
 // EM kernels of the scSplit hot path (sm_100a).  See DESIGN.md for the roofline of each.
 //
-//   k_spmm_rows      v1 SpMM (warp per row, gathers from global); the production SpMM is k_spmm_tiled (spmm_tiled.cuh)
+//   k_spmm_rows      v1 SpMM (warp per row, gathers from global; scs_set_variant 1); the production kernels are k_estep_q
+//                    (E-step sums in exact fixed point, estep_q.cuh), k_mstep_sparse (mstep_sparse.cuh) and k_spmm_tiled (spmm_tiled.cuh)
 //                    Y[row,:] = sum_{count-1 entries} X[g(code),:] + sum_{count>1 entries} cnt * X[g(code),:]
 //                    E-step:  rows = cells,          X = log table T[2V][KP],  Y = L[N][KP]     (scSplit:175-178)
 //                    M-step:  rows = 2V pseudo-rows, X = W[N][KP],             Y = S[2V][KP]    (scSplit:196)
-//   k_bayes          W, per-cell LL, packed sparse posterior word, fixed-order block partials    (scSplit:181-188)
+//   k_bayes          W, per-cell LL, packed sparse posterior word, fixed-order block partials    (scSplit:181-188); also the fp64
+//                    stand-in of the fixed-point E-step for a restart whose table does not fit the format
 //   k_colsum_partial the same partials for an injected W (step-level M-step entry)
 //   k_reduce_stats   block partials -> colsum[K], LL, dense-cell count (step-level path; the EM loop does it in k_bayes)  (scSplit:188,198)
-//   k_finalize       S, k_alt -> P, log2 P, log2(1-P)                                             (scSplit:196, 176-177)
+//   k_finalize       S, k_alt -> P, log2 P, log2(1-P) in fp64 and as packed fixed point            (scSplit:196, 176-177)
 //   update_prior     colsum -> lP_s; LL history; bitwise stop rule (last block of k_finalize)      (scSplit:198, 156-161)
 //   (k_mstep_sparse, the M-step for saturated posteriors, lives in mstep_sparse.cuh)
 #pragma once
@@ -30,14 +32,13 @@ __global__ void __launch_bounds__(256) k_spmm_rows(int64_t nrows, const int64_t*
                                                    const uint32_t* __restrict__ lcode, const int64_t* __restrict__ hptr,
                                                    const uint32_t* __restrict__ hcode, const int32_t* __restrict__ hcnt,
                                                    const double* __restrict__ X, int64_t x_stride, double* __restrict__ Y,
-                                                   int64_t y_stride, const int32_t* __restrict__ done, const int32_t* __restrict__ only) {
+                                                   int64_t y_stride, const int32_t* __restrict__ done) {
     const int r = blockIdx.y;
     if (done && done[r]) return;
-    if (only && !only[r]) return;      // fp64 stand-in of the fixed-point E-step: only the restarts whose table did not fit
     const int lane = threadIdx.x & 31;
     X += (int64_t)r * x_stride;
     Y += (int64_t)r * y_stride;
-    // (grid-stride over the rows: the grid may be smaller than the row count, e.g. when this kernel only stands by)
+    // (grid-stride over the rows)
     for (int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < nrows; row += (int64_t)gridDim.x * (blockDim.x >> 5)) {
         double acc[KP];
 #pragma unroll
