@@ -100,6 +100,7 @@ int scs_destroy(scs_ctx* ctx) {
     free_stream(ctx, ctx->E);
     free_stream(ctx, ctx->M);
     dev_free(ctx, ctx->m_order);
+    dev_free(ctx, ctx->m_bp);
     dev_free(ctx, ctx->m_order_chunks);
     free_tiled(ctx, ctx->TE);
     free_tiled(ctx, ctx->TM);

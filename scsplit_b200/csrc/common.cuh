@@ -151,6 +151,9 @@ struct scs_ctx {
     double* part = nullptr;    // per-(tile,row) partial sums of the tiled SpMM
     int64_t part_doubles = 0;
     uint32_t smem_attr_set[3] = {0, 0, 0};  // bit KP/2: this device already has the large-shared-memory attribute of k_spmm_tiled<KP> / k_mstep_sparse<KP> / k_spmm_tiled<KP, packed>
+    int64_t* m_bp = nullptr;     // [(nblocks+1)][2V] entry pointers of the blocked sparse M-step (pools whose cells do not fit one block)
+    int m_bp_blocks = 0;
+    int64_t m_bp_cells = 0;
     int32_t* m_order = nullptr;  // [2V] pseudo-rows of the M stream by descending length (job order of the sparse M-step; built on first use)
     int64_t* sum_alt = nullptr;  // [V] integer row sums (global after comm_init)
     int64_t* sum_ref = nullptr;  // [V]
@@ -238,6 +241,8 @@ void free_tiled(scs_ctx* ctx, TiledStream& t);
 int build_tiled(scs_ctx* ctx, const Stream& s, TiledStream& t, int KP, int TR, int pad, int ncta, int ngroups, int order_gpw = 0);
 // rows by descending light-entry count, ties by index; with nchunks > 1 that order inside each of nchunks equal row ranges
 int build_row_order(scs_ctx* ctx, const Stream& s, int32_t** order, int nchunks = 1);
+// per-(block of `block` gathered rows, stream row) entry pointers: bp[b * nrows + row], b = 0 .. nblocks
+int build_block_ptrs(scs_ctx* ctx, const Stream& s, int nblocks, int64_t block, int64_t** bp);
 // tile-major stream of the fixed-point E-step; *ok = 0 when the pool's cells are too deep for a useful fraction (F < 40)
 int build_qtiled(scs_ctx* ctx, const Stream& s, TiledStream& t, int lanes, int TR, int ncta, int ngroups, int* F, int* ok);
 

@@ -349,7 +349,8 @@ static int run_m(scs_ctx* ctx, const int32_t* done, int track, int check_conv) {
     const bool multi = ctx->world > 1;
     // M-step sums: the sparse kernel when (nearly) all posterior rows are saturated, else the tiled SpMM; both are launched
     // and the dense-path cell count in the statistics tail (written by the last block of k_bayes, or by k_reduce_stats on the step-level path) gates which one does the work
-    const int sparse_threads = (ctx->variant == 0 || ctx->variant == 3) ? sparse_threads_for(N, em.KP) : 0;
+    const SparsePlan plan = (ctx->variant == 0 || ctx->variant == 3) ? sparse_plan_for(N, em.KP) : SparsePlan();
+    const int sparse_threads = plan.threads;
     const bool sparse = sparse_threads > 0;
     Gate gate;
     // N/32: measured at config 3 (tools/soft_phase_probe.py) -- the run's second iteration still has 14 % unsaturated cells,
@@ -380,20 +381,35 @@ static int run_m(scs_ctx* ctx, const int32_t* done, int track, int check_conv) {
         SCS_TRY(timing_begin(ctx, &ea, &eb));
         int32_t*& order = nchunks > 1 ? ctx->m_order_chunks : ctx->m_order;
         if (!order) SCS_TRY(build_row_order(ctx, ctx->M, &order, nchunks));
-        const size_t smem = sparse_smem_bytes(em.h_stride, em.KP, sparse_threads);
+        // pools whose cells do not fit the kernel's shared-memory table in one piece: one launch per block of cells, each adding
+        // its share of every pseudo-row (entry pointers per block are built on first use)
+        if (plan.nblocks > 1 && (!ctx->m_bp || ctx->m_bp_blocks != plan.nblocks || ctx->m_bp_cells != plan.block_cells)) {
+            dev_free(ctx, ctx->m_bp);
+            SCS_TRY(build_block_ptrs(ctx, ctx->M, plan.nblocks, plan.block_cells, &ctx->m_bp));
+            ctx->m_bp_blocks = plan.nblocks;
+            ctx->m_bp_cells = plan.block_cells;
+        }
         dim3 grid((unsigned)(ctx->sm_count > 0 ? ctx->sm_count : 148), (unsigned)em.R);
         for (int c = 0; c < nchunks; ++c) {
             const int64_t lo = chunk_lo(c), hi = chunk_lo(c + 1);
-            SCS_DISPATCH_KP(em.KP, {
-                if (!(ctx->smem_attr_set[1] >> (KPc / 2) & 1u)) {
-                    SCS_CUDA(cudaFuncSetAttribute(k_mstep_sparse<KPc>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_BYTES + 1024));
-                    ctx->smem_attr_set[1] |= 1u << (KPc / 2);
-                }
-                k_mstep_sparse<KPc><<<grid, sparse_threads, smem, ctx->stream>>>(nrows, hi - lo, N, em.K, order + lo, ctx->M.lptr, ctx->M.lcode,
-                                                                               ctx->M.hptr, ctx->M.hcode, ctx->M.hcnt, em.hq, em.h_stride, em.W,
-                                                                               em.stats, em.stats_stride, gate, done, em.sched);
-            });
-            ctx->launches++;
+            for (int b = 0; b < plan.nblocks; ++b) {
+                CellBlock blk;
+                blk.lo = (int64_t)b * plan.block_cells;
+                blk.n = std::min<int64_t>(plan.block_cells, em.h_stride - blk.lo);
+                if (plan.nblocks > 1) { blk.lo_ptr = ctx->m_bp + (int64_t)b * nrows; blk.hi_ptr = ctx->m_bp + (int64_t)(b + 1) * nrows; }
+                blk.accumulate = b > 0;
+                const size_t smem = sparse_smem_bytes(blk.n, em.KP, sparse_threads);
+                SCS_DISPATCH_KP(em.KP, {
+                    if (!(ctx->smem_attr_set[1] >> (KPc / 2) & 1u)) {
+                        SCS_CUDA(cudaFuncSetAttribute(k_mstep_sparse<KPc>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_BYTES + 1024));
+                        ctx->smem_attr_set[1] |= 1u << (KPc / 2);
+                    }
+                    k_mstep_sparse<KPc><<<grid, sparse_threads, smem, ctx->stream>>>(nrows, hi - lo, N, em.K, order + lo, ctx->M.lptr, ctx->M.lcode,
+                                                                                   ctx->M.hptr, ctx->M.hcode, ctx->M.hcnt, em.hq, em.h_stride, em.W,
+                                                                                   em.stats, em.stats_stride, gate, done, em.sched, blk);
+                });
+                ctx->launches++;
+            }
             if (multi) SCS_TRY(reduce_piece(ctx, lo * em.KP, (hi - lo) * em.KP, ctx->ev_comm[c]));
         }
         SCS_TRY(timing_end(ctx, 2, ea, eb));

@@ -243,6 +243,25 @@ __device__ __forceinline__ int64_t row_lower_bound(const uint32_t* __restrict__ 
     return b;
 }
 
+// bp[b][row] = first entry of `row` whose index (code >> 1) is >= b * block (b = 0 .. nblocks); bp[0] = lptr[row], bp[nblocks] = end
+static __global__ void k_block_ptrs(int64_t nrows, int nblocks, int64_t block, const int64_t* __restrict__ lptr, const uint32_t* __restrict__ lcode,
+                                    int64_t* __restrict__ bp) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nrows * (nblocks + 1)) return;
+    const int64_t b = i / nrows, row = i - b * nrows;
+    const int64_t lo = lptr[row], hi = lptr[row + 1];
+    bp[i] = b == 0 ? lo : b == nblocks ? hi : row_lower_bound(lcode, lo, hi, b * block);
+}
+int build_block_ptrs(scs_ctx* ctx, const Stream& s, int nblocks, int64_t block, int64_t** bp) {
+    *bp = nullptr;
+    SCS_TRY(dev_alloc(ctx, bp, s.nrows * (nblocks + 1)));
+    const int64_t n = s.nrows * (nblocks + 1);
+    k_block_ptrs<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(s.nrows, nblocks, block, s.lptr, s.lcode, *bp);
+    ctx->launches++;
+    SCS_CUDA(cudaGetLastError());
+    return 0;
+}
+
 // one thread per unit u = tile * nrows + row: entries of `row` inside `tile`, padded to a multiple of `pad`
 __global__ void k_tile_counts(int64_t nrows, int ntiles, int TR, int pad, const int64_t* __restrict__ lptr,
                               const uint32_t* __restrict__ lcode, int64_t* __restrict__ cnt, int32_t* __restrict__ ulo) {

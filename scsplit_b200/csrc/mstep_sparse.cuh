@@ -25,12 +25,48 @@ inline size_t sparse_smem_bytes(int64_t h_stride, int KP, int threads) {
     return acc + sparse_tab_bytes(h_stride) + 16;
 }
 // threads per CTA of the sparse M-step for N cells and KP columns: as many warps as fit next to the N packed words (every
-// lane owns KP fp64 slots), at least 8 warps; 0 = the pool does not fit and the tiled SpMM keeps the M-step
+// lane owns KP fp64 slots), at least 8 warps; 0 = the pool does not fit in one piece
 inline int sparse_threads_for(int64_t N, int KP) {
     for (int t = SPARSE_THREADS; t >= 256; t -= 128)
         if (sparse_smem_bytes((N + 3) / 4 * 4, KP, t) <= (size_t)TILE_BYTES + 1024) return t;
     return 0;
 }
+// How the sparse M-step covers the cells: in one piece when their packed words fit shared memory next to the accumulators,
+// else in `nblocks` blocks of `block_cells` cells (a multiple of 4), one launch per block, each adding the block's share of
+// every pseudo-row to S (k_mstep_sparse, CellBlock).  threads == 0: no configuration fits (KP too wide).
+struct SparsePlan {
+    int threads = 0;
+    int nblocks = 0;
+    int64_t block_cells = 0;
+};
+inline SparsePlan sparse_plan_for(int64_t N, int KP) {
+    SparsePlan p;
+    p.threads = sparse_threads_for(N, KP);
+    if (p.threads) { p.nblocks = 1; p.block_cells = (N + 3) / 4 * 4; return p; }
+    // blocks: the most threads that still leave a block of 24k cells or more (every block walks all pseudo-rows again, so few
+    // large blocks beat many small ones; 24k is what one of 8 GPUs holds of BASELINE config 4), else of 8k or more
+    for (int pass = 0; pass < 2; ++pass)
+    for (int t = SPARSE_THREADS; t >= 256; t -= 128) {
+        const int64_t room = (int64_t)TILE_BYTES + 1024 - 16 - 132 - (int64_t)t * KP * 8;
+        const int64_t cap = room > 0 ? room / 4 / 4 * 4 : 0;
+        if (cap >= (pass == 0 ? 24576 : 8192)) {
+            p.threads = t;
+            p.nblocks = (int)((N + cap - 1) / cap);
+            p.block_cells = ((N + p.nblocks - 1) / p.nblocks + 3) / 4 * 4;     // equal blocks, each a multiple of 4 cells
+            return p;
+        }
+    }
+    return p;
+}
+// One block of cells of a blocked sparse M-step launch: cells [lo, lo + n) (n a multiple of 4; the last block may reach past
+// N into the padding of hq), the entries of pseudo-row g inside the block are lcode[lo_ptr[g] .. hi_ptr[g]) (nullptr: the
+// whole row), accumulate = add to S instead of overwriting it (every block but the first).
+struct CellBlock {
+    int64_t lo = 0, n = 0;
+    const int64_t* lo_ptr = nullptr;
+    const int64_t* hi_ptr = nullptr;
+    int accumulate = 0;
+};
 
 __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {   // read-only table: free to be scheduled early
     uint32_t v;
@@ -99,28 +135,28 @@ k_mstep_sparse(int64_t nrows, int64_t njobs, int64_t N, int K, const int32_t* __
                const uint32_t* __restrict__ lcode,
                const int64_t* __restrict__ hptr, const uint32_t* __restrict__ hcode, const int32_t* __restrict__ hcnt,
                const uint32_t* __restrict__ hq, int64_t h_stride, const double* __restrict__ W, double* __restrict__ S,
-               int64_t s_stride, const Gate gate, const int32_t* __restrict__ done, int32_t* __restrict__ sched) {
+               int64_t s_stride, const Gate gate, const int32_t* __restrict__ done, int32_t* __restrict__ sched, const CellBlock blk) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int r = blockIdx.y;
     if (done && done[r]) return;
     if (gate.dense && !gate_takes_sparse(gate, r)) return;   // too many unsaturated cells: the tiled SpMM runs instead
     const size_t ACC_BYTES = (size_t)blockDim.x * KP * 8;
     unsigned char* s_tab = smem + ACC_BYTES;
-    uint64_t* bar = reinterpret_cast<uint64_t*>(s_tab + sparse_tab_bytes(h_stride));
+    uint64_t* bar = reinterpret_cast<uint64_t*>(s_tab + sparse_tab_bytes(blk.n));
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) {
         mbar_init(bar, 1);
         fence_proxy_async();
-        const uint32_t bytes = (uint32_t)(h_stride * 4);
+        const uint32_t bytes = (uint32_t)(blk.n * 4);
         mbar_expect_tx(bar, bytes);
-        const char* src = reinterpret_cast<const char*>(hq + (int64_t)r * h_stride);
+        const char* src = reinterpret_cast<const char*>(hq + (int64_t)r * h_stride + blk.lo);
         for (uint32_t off = 0; off < bytes; off += 32768u) bulk_g2s(s_tab + off, src + off, min(32768u, bytes - off), bar);
-        // word h_stride of the table (past the copied part): where the codes of lanes beyond a row's end point
-        reinterpret_cast<uint32_t*>(s_tab)[h_stride] = SPARSE_NOP;
+        // word blk.n of the table (past the copied part): where the codes of lanes beyond a row's end point
+        reinterpret_cast<uint32_t*>(s_tab)[blk.n] = SPARSE_NOP;
     }
     // this lane's accumulator slots: [warp][state][lane], zeroed once; every row leaves them zero again
     uint32_t acc_base = smem_u32(smem) + (uint32_t)warp * (KP * 256u) + (uint32_t)lane * 8u;
-    uint32_t tab = smem_u32(s_tab);
+    uint32_t tab = smem_u32(s_tab) - (uint32_t)(blk.lo * 4);         // indexed by the GLOBAL cell number (wraps below the table; never dereferenced there)
     asm volatile("" : "+r"(acc_base), "+r"(tab));                    // keep both in registers (no re-derivation per entry)
 #pragma unroll
     for (int k = 0; k < KP; ++k) sts_f64(acc_base + k * 256u, 0.0);
@@ -136,7 +172,7 @@ k_mstep_sparse(int64_t nrows, int64_t njobs, int64_t N, int K, const int32_t* __
 #endif
     constexpr int UV = SCS_SPARSE_UV;
     const int npairs = (int)((njobs + GPW - 1) / GPW);    // `order` lists the njobs pseudo-rows of this launch
-    const uint32_t nop_code = (uint32_t)h_stride << 1;               // code whose table word is SPARSE_NOP
+    const uint32_t nop_code = (uint32_t)(blk.lo + blk.n) << 1;       // code whose table word is SPARSE_NOP
     // A row (pair) is a short job (a few hundred entries), so the chain ticket -> row bounds -> first codes is software-
     // pipelined across rows: the ticket is drawn two rows ahead, the bounds are loaded one row ahead, and the first code
     // vectors of the next row are requested before the current row's reduction tree runs.
@@ -153,8 +189,8 @@ k_mstep_sparse(int64_t nrows, int64_t njobs, int64_t N, int K, const int32_t* __
         const int64_t idx = (int64_t)ticket * GPW + g;
         j.row = (ticket < npairs && idx < njobs) ? (int64_t)__ldg(order + idx) : nrows;
         const bool act = j.row < nrows;
-        j.lb = act ? __ldg(lptr + j.row) : 0;
-        j.n = act ? (int)(__ldg(lptr + j.row + 1) - j.lb) : 0;
+        j.lb = act ? __ldg((blk.lo_ptr ? blk.lo_ptr : lptr) + j.row) : 0;
+        j.n = act ? (int)(__ldg(blk.hi_ptr ? blk.hi_ptr + j.row : lptr + j.row + 1) - j.lb) : 0;
         return j;
     };
     // The codes are read as 16-byte vectors from the aligned address below the row start (`a` elements early), UV vectors
@@ -200,9 +236,11 @@ k_mstep_sparse(int64_t nrows, int64_t njobs, int64_t N, int K, const int32_t* __
 #pragma unroll
             for (int j = 0; j < UV; ++j) trim_vec(cur[j], v + j * SPARSE_GS, a, m);
 #pragma unroll
-            for (int j = 0; j < UV; ++j)   // every code (cell << 1 | dup) addresses the staged table: cell <= h_stride (the NOP word)
-                SCS_ASSERT((cur[j].x >> 1) <= (uint32_t)h_stride && (cur[j].y >> 1) <= (uint32_t)h_stride && (cur[j].z >> 1) <= (uint32_t)h_stride &&
-                           (cur[j].w >> 1) <= (uint32_t)h_stride);
+            for (int j = 0; j < UV; ++j) {  // every code (cell << 1 | dup) addresses the staged block: lo <= cell <= lo + n (the NOP word)
+                const uint32_t c_lo = (uint32_t)blk.lo, c_hi = (uint32_t)(blk.lo + blk.n);
+                SCS_ASSERT((cur[j].x >> 1) >= c_lo && (cur[j].x >> 1) <= c_hi && (cur[j].y >> 1) >= c_lo && (cur[j].y >> 1) <= c_hi &&
+                           (cur[j].z >> 1) >= c_lo && (cur[j].z >> 1) <= c_hi && (cur[j].w >> 1) >= c_lo && (cur[j].w >> 1) <= c_hi);
+            }
 #pragma unroll
             for (int j = 0; j < UV; ++j) {
                 q[4 * j + 0] = lds_u32(tab + ((cur[j].x & ~1u) << 1));
@@ -245,6 +283,7 @@ k_mstep_sparse(int64_t nrows, int64_t njobs, int64_t N, int K, const int32_t* __
         const int64_t hb = act ? hptr[job.row] : 0, he = act ? hptr[job.row + 1] : 0;
         for (int64_t h = hb + li; h < he; h += SPARSE_GS) {
             const uint32_t c = __ldg(hcode + h) >> 1;
+            if ((int64_t)c < blk.lo || (int64_t)c >= blk.lo + blk.n) continue;      // (a count>1 entry of another block of cells)
             const uint32_t q = lds_u32(tab + c * 4u);
             const double cnt = (double)__ldg(hcnt + h);
             if (q != SPARSE_DENSE) sparse_rmw(acc_base, q, cnt);
@@ -267,7 +306,7 @@ k_mstep_sparse(int64_t nrows, int64_t njobs, int64_t N, int K, const int32_t* __
                 double* y = S + job.row * KP;
 #pragma unroll
                 for (int i = 0; i < GR::LEFT; ++i)
-                    if (i < nval) y[base + i] = out[i];
+                    if (i < nval) y[base + i] = blk.accumulate ? y[base + i] + out[i] : out[i];   // (blocks run as successive launches)
             }
         }
         job = job_nxt;

@@ -572,17 +572,19 @@ def test_sparse_mstep_long_rows_with_soft_cells(E):
     assert np.allclose(res[0][1]["S"], res[2][1]["S"], rtol=1e-12, atol=1e-30)
 
 
-@pytest.mark.parametrize("N", [40000, 47000, 60000])
-def test_sparse_mstep_thread_budget(N, E):
-    """Pools whose packed posteriors leave room for fewer than 1024 sparse-M-step threads (40k cells: 512; 47k: 256) or for
-    none (60k: the tiled SpMM keeps the M-step): six EM iterations against the tiled-only variant."""
+@pytest.mark.parametrize("N,K", [(40000, 9), (47000, 9), (60000, 9), (130000, 9), (61000, 17)])
+def test_sparse_mstep_thread_budget(N, K, E):
+    """Pools whose packed posteriors leave room for fewer than 1024 sparse-M-step threads (40k cells: 512; 47k: 256) or do not
+    fit one shared-memory table at all (60k: two blocks of cells, 130k: five, 61k at K = 17: three -- one launch per block,
+    each adding its share of every pseudo-row): six EM iterations against the tiled-only variant."""
     from scsplit_b200 import synth
     from scsplit_b200._lib import SCS_L, SCS_P
-    V, K = 1200, 9
-    pool = synth.make_pool(V, N, 8, 0.05, 0.3, seed=N)
+    V = 1200
+    pool = synth.make_pool(V, N, K - 1, 0.05, 0.3, seed=N)
     lab = np.full(N, -1, dtype=np.int32)
-    for k in range(K):                                    # a few true members per state: saturates within 3 iterations
-        lab[np.flatnonzero((pool.truth == k % 8) & ~pool.is_doublet)[:40]] = k
+    for k in range(K - 1):                                # a few true members per state: saturates within 3 iterations
+        lab[np.flatnonzero((pool.truth == k) & ~pool.is_doublet)[:40]] = k
+    lab[np.flatnonzero(pool.is_doublet)[:40]] = K - 1
     out = {}
     for variant in (0, 2):
         with E(pool.ref, pool.alt) as eng:
