@@ -150,7 +150,7 @@ static int launch_estep_q(scs_ctx* ctx, const int32_t* done) {
     EmState& em = ctx->em;
     TiledStream& t = ctx->QE;
     const int lanes = em.q_lanes;
-    const int64_t part_stride = t.nunits * lanes * 3;
+    const int64_t part_stride = t.nunits * q_part_words(lanes);
     if (ctx->qpart_words < part_stride * em.R) {
         dev_free(ctx, ctx->qpart);
         SCS_TRY(dev_alloc(ctx, &ctx->qpart, part_stride * em.R));
@@ -476,7 +476,7 @@ int scs_em_footprint(scs_ctx* ctx, int K, int64_t out[2]) {
     const int lanes = q_lanes_for(K);
     if (lanes) {
         const int64_t ntq = (2 * V + q_tile_rows(lanes, 2 * V) - 1) / q_tile_rows(lanes, 2 * V);
-        b += 2 * V * 2 * lanes * 8 + ntq * N * lanes * 24;                  // fixed-point table, its per-unit sums
+        b += 2 * V * 2 * lanes * 8 + ntq * N * q_part_words(lanes) * 8;      // fixed-point table, its per-unit sums
     }
     const int64_t nte = (2 * V + tile_rows_for((int)KP, 2 * V) - 1) / tile_rows_for((int)KP, 2 * V);
     const int64_t ntm = (N + tile_rows_for((int)KP, N) - 1) / tile_rows_for((int)KP, N);

@@ -55,6 +55,10 @@ inline int q_frac_bits(int64_t depth) {
     return f > Q_MAX_F ? Q_MAX_F : f;
 }
 
+// per-unit sums of k_estep_q, word-major: [sum q0 of lanes 0..L-1 | sum q1 of lanes 0..L-1 | byte-pair sums of lanes 0..3]
+// (lanes 4..7 of a 128-byte row carry no byte pair): 12 words per unit at 64-byte rows, 20 at 128-byte rows
+__host__ __device__ constexpr int q_part_words(int lanes) { return lanes == 4 ? 12 : 20; }
+
 // quantise one table value; *bad is raised when it does not fit the format
 __device__ __forceinline__ uint64_t q_quant(double x, double scale, bool* bad) {
     const bool ok = (x <= 0.0) && (x > -(double)(1 << Q_INT_BITS));      // false for NaN, -inf, positive values
@@ -102,7 +106,7 @@ template <int LANES> struct QCode {
 // A group of LANES lanes consumes its run as a continuous stream, one entry per LDS.128; a unit is flushed by a (rare,
 // divergent) branch where it ends -- units are padded to whole blocks of 8 codes, so that is looked for once per 8 codes --
 // so there is one accumulator set and no per-entry predication.
-// part[(unit * LANES + lane) * 3 + {0,1,2}] = sum q0, sum q1, byte-pair sums (raw; k_combine_q takes them apart).
+// part[unit * q_part_words + {0, LANES, 2 * LANES} + lane] = sum q0, sum q1, byte-pair sums (raw; k_combine_q takes them apart).
 template <int LANES>
 __global__ void __launch_bounds__(TILED_THREADS, 1)
 k_estep_q(int TR, int64_t xrows, const int64_t* __restrict__ tptr, const uint32_t* __restrict__ tword,
@@ -167,11 +171,11 @@ k_estep_q(int TR, int64_t xrows, const int64_t* __restrict__ tptr, const uint32_
         acc.zero();
         auto flush = [&](int upto) {       // flush every unit that ends at or before stream position `upto`
             do {
-                uint64_t* dst = part + (u * LANES + li) * 3;
-                SCS_ASSERT(u >= 0 && (u * LANES + li) * 3 + 2 < part_stride);
+                uint64_t* dst = part + u * q_part_words(LANES) + li;
+                SCS_ASSERT(u >= 0 && (u + 1) * q_part_words(LANES) <= part_stride);
                 dst[0] = acc.a;
-                dst[1] = acc.b;
-                dst[2] = acc.pp;
+                dst[LANES] = acc.b;
+                if (li < 4) dst[2 * LANES] = acc.pp;
                 acc.zero();
                 ++u;
                 b1 = b2; b2 = b3;
@@ -216,8 +220,10 @@ k_estep_q(int TR, int64_t xrows, const int64_t* __restrict__ tptr, const uint32_
 }
 
 // L[c, :] = -(sum over tiles of the unit sums) * 2^-F + the row's entries of count > Q_REP_MAX in fp64.  Four threads per
-// (cell, lane), each taking every fourth tile (the integer adds are order-free), folded by shuffles; the few fp64 terms
-// are added in stream order.  Warp lane = s * 8 + q: q picks one of 8 consecutive (cell, lane) pairs, s the tile class.
+// (cell, lane) pair, each taking every fourth tile (the integer adds are order-free), folded by shuffles; the few fp64 terms
+// are added in stream order.  Warp lane = s * 8 + q: q picks one of 8 consecutive pairs, s the tile class; the word-major
+// layout of the unit sums makes every load of 8 pairs one or two fully used 32-byte sectors per class.  (Measured at a
+// config-4 shard, 270 MB of unit sums from HBM: 8 classes per warp 124 us, a block of 8 warps with one class each 96 us.)
 constexpr int QC_SUB = 4;
 template <int LANES>
 __global__ void __launch_bounds__(256) k_combine_q(int64_t nrows, int K, int KP, int ntiles, const uint64_t* __restrict__ part,
@@ -225,6 +231,7 @@ __global__ void __launch_bounds__(256) k_combine_q(int64_t nrows, int K, int KP,
                                                    const uint32_t* __restrict__ hcode, const int32_t* __restrict__ hcnt,
                                                    const double* __restrict__ T, int64_t t_stride, double* __restrict__ L,
                                                    int64_t l_stride, const int32_t* __restrict__ done, const int32_t* __restrict__ qbad) {
+    constexpr int PW = q_part_words(LANES);
     const int r = blockIdx.y;
     if (done && done[r]) return;
     if (qbad[r]) return;
@@ -237,8 +244,9 @@ __global__ void __launch_bounds__(256) k_combine_q(int64_t nrows, int K, int KP,
     T += (int64_t)r * t_stride;
     uint64_t sa = 0, sb = 0, pa = 0, pb = 0;
     if (live) {
-        const uint64_t* p = part + (c * LANES + li) * 3;
-        const int64_t tstride = nrows * LANES * 3;
+        const uint64_t* p = part + c * PW + li;
+        const int64_t tstride = nrows * PW;
+        const bool has_pp = li < 4;                      // (lanes 4..7 of a 128-byte row carry no byte pair and store none)
         int t = sub;
         constexpr int CB = 3;
         for (; t + (CB - 1) * QC_SUB < ntiles; t += CB * QC_SUB) {
@@ -246,16 +254,16 @@ __global__ void __launch_bounds__(256) k_combine_q(int64_t nrows, int K, int KP,
 #pragma unroll
             for (int q = 0; q < CB; ++q) {
                 x[q][0] = __ldcs(p + (int64_t)(t + q * QC_SUB) * tstride);
-                x[q][1] = __ldcs(p + (int64_t)(t + q * QC_SUB) * tstride + 1);
-                x[q][2] = __ldcs(p + (int64_t)(t + q * QC_SUB) * tstride + 2);
+                x[q][1] = __ldcs(p + (int64_t)(t + q * QC_SUB) * tstride + LANES);
+                x[q][2] = has_pp ? __ldcs(p + (int64_t)(t + q * QC_SUB) * tstride + 2 * LANES) : 0ull;
             }
 #pragma unroll
             for (int q = 0; q < CB; ++q) { sa += x[q][0]; sb += x[q][1]; pa += x[q][2] & 0xffffffull; pb += x[q][2] >> 24; }
         }
         for (; t < ntiles; t += QC_SUB) {
-            const uint64_t x2 = __ldcs(p + (int64_t)t * tstride + 2);
+            const uint64_t x2 = has_pp ? __ldcs(p + (int64_t)t * tstride + 2 * LANES) : 0ull;
             sa += __ldcs(p + (int64_t)t * tstride);
-            sb += __ldcs(p + (int64_t)t * tstride + 1);
+            sb += __ldcs(p + (int64_t)t * tstride + LANES);
             pa += x2 & 0xffffffull;
             pb += x2 >> 24;
         }
@@ -271,7 +279,7 @@ __global__ void __launch_bounds__(256) k_combine_q(int64_t nrows, int K, int KP,
     sb -= pb << 56;
     uint64_t sx = li < 4 ? (pa << (16 * li)) + (pb << (16 * li + 8)) : 0ull;
 #pragma unroll
-    for (int o = LANES / 2; o; o >>= 1) sx += __shfl_xor_sync(0xffffffffu, sx, o);   // (the LANES pairs of a cell are neighbours)
+    for (int o = 2; o; o >>= 1) sx += __shfl_xor_sync(0xffffffffu, sx, o);   // lanes 0..3 of a row are neighbours in the warp
     if (!live || sub) return;
     auto val = [&](uint64_t s, int k) { return (k < K && s) ? -((double)s * scale_inv) : 0.0; };
     double y0 = val(sa, 2 * li), y1 = val(sb, 2 * li + 1), yx = val(sx, 2 * LANES);
