@@ -88,6 +88,11 @@ int scs_em_begin(scs_ctx* ctx, int R, int K, const double* P0, int max_iter);
 /* Run up to n_iter more iterations on every unconverged restart. check_conv=1 applies the reference's
  * stop rule (bitwise-equal consecutive LL, scSplit:156) on the device; 0 runs exactly n_iter (benchmarks). */
 int scs_em_iterate(scs_ctx* ctx, int n_iter, int check_conv);
+/* Capture the launches of one iteration as CUDA graphs now (both M-step launch sets of the given check_conv), so that the next
+ * scs_em_iterate replays them from its first iteration; executes nothing.  Needs at least one iteration to have run since
+ * scs_em_begin (the first pass does the lazy builds a capture cannot hold); otherwise, and on a multi-rank context, a no-op.
+ * scs_em_iterate captures by itself after 8 plain iterations; this is for callers that time a short loop (bench.py). */
+int scs_em_capture(scs_ctx* ctx, int check_conv);
 /* Device time in milliseconds (CUDA events on the context's stream) of the launches of the last scs_em_iterate. */
 int scs_em_last_ms(scs_ctx* ctx, double* ms);
 /* Run to the reference's stopping rule (cap max_iter). */

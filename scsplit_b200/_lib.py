@@ -30,6 +30,7 @@ SIGNATURES = {
     "scs_em_footprint": (c_int, [c_void_p, c_int, POINTER(c_int64)]),
     "scs_em_begin": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int]),
     "scs_em_iterate": (c_int, [c_void_p, c_int, c_int]),
+    "scs_em_capture": (c_int, [c_void_p, c_int]),
     "scs_em_last_ms": (c_int, [c_void_p, POINTER(c_double)]),
     "scs_em_run": (c_int, [c_void_p]),
     "scs_estep": (c_int, [c_void_p]),

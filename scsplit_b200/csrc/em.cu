@@ -597,52 +597,79 @@ int scs_mstep(scs_ctx* ctx) {
     return 0;
 }
 
+// Capture the launches of one iteration (run_e + run_m) for launch set [check_conv][sparse_only] and instantiate the graph.
+// Nothing executes.  The set must have been launched the plain way before (lazy builds, function attributes): graph_warm says so.
+// A failure switches graph replay off for the context and leaves plain launches in charge.
+static int em_capture_set(scs_ctx* ctx, int a, int b) {
+    EmState& em = ctx->em;
+    if (em.graph[a][b]) return 0;
+    const int32_t* done = a ? em.done : nullptr;
+    const int64_t l0 = ctx->launches;
+    const int64_t seen0 = ctx->phase_seen[0], seen1 = ctx->phase_seen[1];
+    const int hint0 = em.sparse_only, timing0 = ctx->timing;
+    em.sparse_only = b;                                  // what run_m looks at to leave the tiled pair out
+    ctx->timing = 0;                                     // no event records inside a capture
+    cudaGraph_t g = nullptr;
+    cudaError_t e = cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal);
+    int rc = 0;
+    if (e == cudaSuccess) {
+        rc = run_e(ctx, done);
+        if (!rc) rc = run_m(ctx, done, 1, a);
+        e = cudaStreamEndCapture(ctx->stream, &g);
+    }
+    em.sparse_only = hint0;
+    ctx->timing = timing0;
+    ctx->phase_seen[0] = seen0;
+    ctx->phase_seen[1] = seen1;
+    const int nlaunch = (int)(ctx->launches - l0);
+    ctx->launches = l0;
+    cudaGraphExec_t x = nullptr;
+    if (!rc && e == cudaSuccess && g) e = cudaGraphInstantiate(&x, g, 0);
+    if (g) cudaGraphDestroy(g);
+    if (rc || e != cudaSuccess || !x) {
+        cudaGetLastError();
+        ctx->use_graphs = 0;
+        return rc;
+    }
+    em.graph[a][b] = x;
+    em.graph_launches[a][b] = nlaunch;
+    return 0;
+}
+// the lazy builds of set [a][b] are done once the set itself or (for b = 1, a subset of the launches of b = 0) set [a][0] has run
+static bool em_set_is_warm(const EmState& em, int a, int b) { return em.graph_warm[a][b] > 0 || (b == 1 && em.graph_warm[a][0] > 0); }
+
 // One iteration: the launches of run_e + run_m, replayed from a CUDA graph where one exists for the current launch set.
 static int em_one_iteration(scs_ctx* ctx, const int32_t* done, int check_conv) {
     EmState& em = ctx->em;
-    constexpr int GRAPH_AFTER = 8;
+    constexpr int GRAPH_AFTER = 8;   // plain iterations of an EM state before graphs are captured by themselves (scs_em_capture does it at once)
     // an iteration whose kernels are being timed (every ctx->timing-th) is launched the plain way: events cannot sit inside a replay
     const bool sampled = ctx->timing && (ctx->phase_seen[0] % ctx->timing) == 0;
     const bool graphs = ctx->use_graphs && ctx->world == 1 && !sampled && !std::getenv("SCS_NO_GRAPH");
     const int a = check_conv ? 1 : 0, b = em.sparse_only ? 1 : 0;
-    if (graphs && em.graph[a][b]) {
+    if (graphs && !em.graph[a][b] && em_set_is_warm(em, a, b) &&
+        em.graph_warm[a][0] + em.graph_warm[a][1] >= GRAPH_AFTER)
+        SCS_TRY(em_capture_set(ctx, a, b));
+    if (graphs && ctx->use_graphs && em.graph[a][b]) {
         SCS_CUDA(cudaGraphLaunch(em.graph[a][b], ctx->stream));
         ctx->launches += em.graph_launches[a][b];
         if (ctx->timing) { ctx->phase_seen[0]++; ctx->phase_seen[1]++; }     // (what run_e / run_m would have counted)
         return 0;
     }
-    if (graphs && em.graph_warm[a][b] >= GRAPH_AFTER) {
-        const int64_t l0 = ctx->launches;
-        cudaGraph_t g = nullptr;
-        SCS_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
-        int rc = run_e(ctx, done);
-        if (!rc) rc = run_m(ctx, done, 1, check_conv);
-        const cudaError_t e = cudaStreamEndCapture(ctx->stream, &g);
-        if (rc || e != cudaSuccess || !g) {
-            if (g) cudaGraphDestroy(g);
-            cudaGetLastError();
-            ctx->use_graphs = 0;                         // fall back to plain launches for the rest of this context
-            ctx->launches = l0;
-            if (rc) return rc;
-        } else {
-            cudaGraphExec_t x = nullptr;
-            const cudaError_t e2 = cudaGraphInstantiate(&x, g, 0);
-            cudaGraphDestroy(g);
-            if (e2 == cudaSuccess && x) {
-                em.graph[a][b] = x;
-                em.graph_launches[a][b] = (int)(ctx->launches - l0);
-                ctx->launches = l0;
-                if (ctx->timing) { ctx->phase_seen[0]--; ctx->phase_seen[1]--; }   // the capture pass counted itself; the replay below counts again
-                return em_one_iteration(ctx, done, check_conv);
-            }
-            cudaGetLastError();
-            ctx->use_graphs = 0;
-            ctx->launches = l0;
-        }
-    }
     SCS_TRY(run_e(ctx, done));
     SCS_TRY(run_m(ctx, done, 1, check_conv));
     em.graph_warm[a][b]++;
+    return 0;
+}
+
+int scs_em_capture(scs_ctx* ctx, int check_conv) {
+    SCS_CHECK(ctx && ctx->em.R, "EM state not initialised (call scs_em_begin)");
+    SCS_CUDA(cudaSetDevice(ctx->device));
+    EmState& em = ctx->em;
+    if (!ctx->use_graphs || ctx->world != 1 || std::getenv("SCS_NO_GRAPH")) return 0;
+    const int a = check_conv ? 1 : 0;
+    SCS_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int b = 0; b < 2 && ctx->use_graphs; ++b)
+        if (em_set_is_warm(em, a, b)) SCS_TRY(em_capture_set(ctx, a, b));
     return 0;
 }
 

@@ -136,6 +136,10 @@ class Engine:
     def em_iterate(self, n_iter, check_conv=True):
         check(self.lib.scs_em_iterate(self.h, int(n_iter), 1 if check_conv else 0))
 
+    def em_capture(self, check_conv=True):
+        """Capture one iteration's launches as CUDA graphs now (after at least one iteration has run); executes nothing."""
+        check(self.lib.scs_em_capture(self.h, 1 if check_conv else 0))
+
     def last_ms(self):
         """Device milliseconds (CUDA events on the library's stream) of the last em_iterate call."""
         ms = ctypes.c_double(0.0)
