@@ -327,10 +327,11 @@ def cells_leg(args, rank, world, local, barrier):
     peak, _ = load_peaks()
     return {
         "workload": workload_string(name, V, N_total, K, int(nnzU[0])),
-        "parallelism": "cells sharded over %d GPUs (%d cells each), statistics all-reduced by NCCL in %s per iteration, overlapped with the M-step kernels" % (
-            world, per, "5 pieces" if kt["allreduce_n"] else "one piece") if world > 1 else "single GPU, whole pool",
+        "parallelism": "cells sharded over %d GPUs (%d cells each); per iteration NCCL all-reduces the posterior tail (overlapping the M-step kernels) and the M-step sums S, %d collectives" % (
+            world, per, round(kt["allreduce_n"] / max(kt["m_n"], 1))) if world > 1 else "single GPU, whole pool",
         "n_gpus": world, "steps": steps, "warmup": warmup, "value": steps / dev_s, "unit": UNIT, "ms_per_step": 1000.0 * dev_s / steps,
-        "scaling": "strong", "e_us": kt["e_us"], "m_us": kt["m_us"], "allreduce_us": kt["allreduce_us"],
+        "scaling": "strong", "e_us": kt["e_us"], "m_us": kt["m_us"], "bayes_us": kt["bayes_us"], "allreduce_us": kt["allreduce_us"],
+        "allreduce_us_is": "elapsed on the communication stream per iteration (includes the time a collective waits for SMs behind the kernels it overlaps)",
         "allreduce_pieces_timed": kt["allreduce_n"], "allreduce_doubles": 2 * V * (K + (K & 1)) + (K + (K & 1)) + 2,
         "estep": "fixed point, %d-byte rows, F=%d" % (16 * einfo["q_lanes"], einfo["q_frac_bits"]) if einfo["q_lanes"] else "fp64",
         "hbm_frac_of_iteration": (eb + mb) / world / (dev_s / steps) / 1e9 / peak,

@@ -307,8 +307,8 @@ static int run_e(scs_ctx* ctx, const int32_t* done) {
 }
 
 // Row ranges of the M-step sums whose all-reduce may overlap the next range's kernel (cells sharded over ranks).  Measured on
-// 8 x B200 at config 4 (25k cells per rank, profiles/r02_bench_8gpu_chunked.json): 4 ranges LOSE to one -- 1.00 ms against
-// 0.86 ms per iteration.  The sparse M-step is a persistent kernel that fills every SM (768-1024 threads, ~210 KB of shared
+// 8 x B200 at config 4 (25k cells per rank, profiles/r02_bench_8gpu_chunked.json vs r02_bench_8gpu.json): 4 ranges LOSE to
+// one -- 1.00 ms against 0.92 ms per iteration.  The sparse M-step is a persistent kernel that fills every SM (768-1024 threads, ~210 KB of shared
 // memory per CTA), so an NCCL kernel on the second stream only gets SMs as a range's CTAs drain, and then holds them against
 // the next range's CTAs: the M-step went 155 -> 202 us and four latency-bound 4 MB collectives cost more than one of 17 MB.
 // The default is therefore ONE range (plus the posterior tail, which does overlap the M-step); SCS_M_CHUNKS=n re-enables it.
