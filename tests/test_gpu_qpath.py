@@ -191,3 +191,51 @@ def test_dead_cluster_runs_match_fp64_variant(name, E):
         assert np.array_equal(W0 >= 0.99, W3 >= 0.99)
     assert_close(P0, P3, 1e-9, "P %s" % name)
     assert_close(ll0, ll3, 1e-9, "LL %s" % name)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_pools_run_against_oracle(seed, E):
+    """Randomised differential test of whole runs: shapes, state counts, depths and count distributions drawn at random;
+    five iterations from a random seed assignment (stop rule off) against the numpy oracle: L, W, P, lP_s, LL at 1e-9,
+    identical >= 0.99 assignments; and the same bits from a second run (graph replay, batched next to a copy)."""
+    from scipy.sparse import csr_matrix
+    from oracle import em_oracle as O
+    from scsplit_b200._lib import SCS_L, SCS_LPS, SCS_P, SCS_W
+    rng = np.random.default_rng(1000 + seed)
+    V = int(rng.integers(40, 5000))
+    N = int(rng.integers(8, 1500))
+    K = int(rng.choice([1, 2, 3, 5, 8, 9, 10, 13, 16, 17, 18, 24, 32]))
+    dens = float(rng.choice([0.01, 0.05, 0.2, 0.6]))
+    top = int(rng.choice([1, 2, 9, 40, 500]))
+    n_s = max(1, min(K, 6))
+    G = rng.choice([0.01, 0.5, 0.99], size=(V, n_s), p=[0.5, 0.3, 0.2])
+    truth = rng.integers(0, n_s, N)
+    depth = (rng.random((V, N)) < dens) * rng.integers(1, top + 1, size=(V, N))
+    alt = rng.binomial(depth, G[:, truth])
+    ref = depth - alt
+    if N > 3:
+        alt[:, 1] = 0
+        ref[:, 1] = 0                                      # an empty cell
+    ref_s, alt_s = csr_matrix(ref.astype(np.int32)), csr_matrix(alt.astype(np.int32))
+    lab = np.full(N, -1, dtype=np.int32)
+    pick = rng.choice(N, min(N, 2 * K), replace=False)
+    lab[pick] = np.arange(pick.size) % K
+    k_alt = O.kalt(ref_s, alt_s)
+    P0 = O.seed_af(ref_s, alt_s, k_alt, lab, K)
+    want = O.run_em(ref_s, alt_s, P0, k_alt, fixed_iters=5)
+    with E(ref_s, alt_s) as eng:
+        assert np.array_equal(eng.seed_af(lab, K), P0)
+        eng.em_begin(np.stack([P0, P0]))
+        eng.em_iterate(5, check_conv=False)
+        it, cv, ll = eng.em_status()
+        got = [(eng.get(SCS_L, r), eng.get(SCS_W, r), eng.get(SCS_P, r), eng.get(SCS_LPS, r)) for r in range(2)]
+    what = "seed %d: V=%d N=%d K=%d density %.2f counts<=%d" % (seed, V, N, K, dens, top)
+    for r in range(2):
+        assert_close(got[r][0], want["L"], RTOL, "L " + what)
+        assert_close(got[r][2], want["P"], RTOL, "P " + what)
+        assert_close(got[r][3], want["lPs"], RTOL, "lP_s " + what)
+        assert_close(ll[r], want["LL"], RTOL, "LL " + what)
+        with np.errstate(invalid="ignore"):
+            assert np.array_equal(got[r][1] >= 0.99, want["W"] >= 0.99), what
+    for a, b in zip(got[0], got[1]):
+        assert np.array_equal(a, b, equal_nan=True), "batched copies differ: " + what
