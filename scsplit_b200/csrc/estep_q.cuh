@@ -114,7 +114,7 @@ k_estep_q(int TR, int64_t xrows, const int64_t* __restrict__ tptr, const uint32_
           const uint64_t* __restrict__ Xq, int64_t xq_stride, uint64_t* __restrict__ part, int64_t part_stride,
           const int32_t* __restrict__ done, const int32_t* __restrict__ qbad) {
     using QC = QCode<LANES>;
-    constexpr int ROWB = LANES * 16, GPW = 32 / LANES, BE = 4 * LANES;   // BE: codes per batch of one group
+    constexpr int ROWB = LANES * 16, GPW = 32 / LANES, BE = 8 * LANES;   // BE: codes per batch of one group
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + (((size_t)(TR + 2) * ROWB + 127) & ~(size_t)127));
 
@@ -185,25 +185,25 @@ k_estep_q(int TR, int64_t xrows, const int64_t* __restrict__ tptr, const uint32_
         };
         if (b1 <= 0) flush(0);                           // empty units at the head of the run
         int pos = 0;
-        // every lane holds two stream words (four codes) of the current batch: LDG.64, so that a warp's stream loads touch
-        // each 32-byte sector once per 16 codes of a group.  (Staging the words in shared memory instead of shuffling them
-        // measured no better: a 16-byte broadcast read still costs one wavefront per quarter-warp.)
-        const uint2 zero2 = make_uint2(zero_word, zero_word);
-        uint2 word = (4 * li < run) ? __ldcs(reinterpret_cast<const uint2*>(words) + li) : zero2;
+        // every lane holds four stream words (eight codes) of the current batch: one LDG.128, so that a warp's stream loads
+        // touch each 32-byte sector once per 32 codes of a group.  (Staging the words in shared memory instead of shuffling
+        // them measured no better: a 16-byte broadcast read still costs one wavefront per quarter-warp.)
+        const uint4 zero4 = make_uint4(zero_word, zero_word, zero_word, zero_word);
+        uint4 word = (8 * li < run) ? __ldcs(reinterpret_cast<const uint4*>(words) + li) : zero4;
         while (__any_sync(0xffffffffu, u < uend)) {
-            const uint2 mine = word;
+            const uint4 mine = word;
             {   // this lane's words of the next batch (positions beyond the run read as padding; runs are multiples of 8 codes)
-                const int nw = (pos + BE) / 4 + li;
-                word = (4 * nw < run) ? __ldcs(reinterpret_cast<const uint2*>(words) + nw) : zero2;
+                const int nw = (pos + BE) / 8 + li;
+                word = (8 * nw < run) ? __ldcs(reinterpret_cast<const uint4*>(words) + nw) : zero4;
             }
             constexpr int UW = 4;                        // stream words (code pairs) whose rows are requested before the adds
 #pragma unroll
-            for (int j0 = 0; j0 < 2 * LANES; j0 += UW) {
+            for (int j0 = 0; j0 < 4 * LANES; j0 += UW) {  // (block j0 / 4 of the batch is exactly the four words of lane j0 / 4)
                 uint4 v[2 * UW];
+                const uint32_t mw[4] = {mine.x, mine.y, mine.z, mine.w};
 #pragma unroll
                 for (int jj = 0; jj < UW; ++jj) {
-                    const int wi = j0 + jj;              // word wi of the batch sits in lane wi / 2 of the group, component wi & 1
-                    const uint32_t w = __shfl_sync(0xffffffffu, (wi & 1) ? mine.y : mine.x, g * LANES + wi / 2);
+                    const uint32_t w = __shfl_sync(0xffffffffu, mw[jj], g * LANES + j0 / 4);
                     SCS_ASSERT(((w & QC::MASK) >> QC::SA) <= (uint32_t)TR + 1 && (((w >> 14) & QC::MASK) >> QC::SA) <= (uint32_t)TR + 1);
                     v[2 * jj] = lds_u32x4(smem_base + ((w & QC::MASK) | lane_off));
                     v[2 * jj + 1] = lds_u32x4(smem_base + (((w >> 14) & QC::MASK) | lane_off));
