@@ -296,26 +296,30 @@ __global__ void k_tile_scatter(int64_t nrows, int ntiles, int TR, const int64_t*
 
 // cost of the units [lo, u): entries plus a fixed charge per unit (flush + bounds), in entry units
 constexpr int64_t UNIT_COST = 8;
-__device__ __forceinline__ int64_t plan_cost(const int64_t* __restrict__ tptr, int64_t lo, int64_t u) {
-    return (tptr[u] - tptr[lo]) + UNIT_COST * (u - lo);
+// `tile_cost` (entries) is charged for every tile boundary inside the range -- a CTA whose range runs into the next tile loads a
+// second table tile (a few microseconds with every CTA pulling its tile from L2 at once) and should get fewer entries for it;
+// `nrows` units make a tile.  tile_cost = 0 inside a segment (one tile by construction).
+__device__ __forceinline__ int64_t plan_cost(const int64_t* __restrict__ tptr, int64_t lo, int64_t u, int64_t nrows = 1, int64_t tile_cost = 0) {
+    return (tptr[u] - tptr[lo]) + UNIT_COST * (u - lo) + (tile_cost ? tile_cost * ((u > lo ? (u - 1) / nrows : lo / nrows) - lo / nrows) : 0);
 }
-__device__ __forceinline__ int64_t plan_cut(const int64_t* __restrict__ tptr, int64_t lo, int64_t hi, int64_t part, int64_t nparts) {
+__device__ __forceinline__ int64_t plan_cut(const int64_t* __restrict__ tptr, int64_t lo, int64_t hi, int64_t part, int64_t nparts,
+                                            int64_t nrows = 1, int64_t tile_cost = 0) {
     if (part <= 0) return lo;
     if (part >= nparts) return hi;
-    const int64_t total = plan_cost(tptr, lo, hi);
+    const int64_t total = plan_cost(tptr, lo, hi, nrows, tile_cost);
     const int64_t target = (total / nparts) * part + ((total % nparts) * part) / nparts;
     int64_t a = lo, b = hi;
     while (a < b) {          // first unit u with cost(lo, u) >= target
         const int64_t mid = (a + b) >> 1;
-        if (plan_cost(tptr, lo, mid) < target) a = mid + 1; else b = mid;
+        if (plan_cost(tptr, lo, mid, nrows, tile_cost) < target) a = mid + 1; else b = mid;
     }
     return a;
 }
 // cu[j] = first unit of CTA j (equal-cost split of all units)
-__global__ void k_plan_ctas(const int64_t* __restrict__ tptr, int64_t nunits, int ncta, int64_t* __restrict__ cu) {
+__global__ void k_plan_ctas(const int64_t* __restrict__ tptr, int64_t nunits, int ncta, int64_t* __restrict__ cu, int64_t nrows, int64_t tile_cost) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j > ncta) return;
-    cu[j] = plan_cut(tptr, 0, nunits, j, ncta);
+    cu[j] = plan_cut(tptr, 0, nunits, j, ncta, nrows, tile_cost);
 }
 // Tile segments of the CTA ranges: CTA j runs the pieces of [cu[j], cu[j+1]) between tile boundaries (a tile owns nrows
 // consecutive units).  At most ncta + ntiles pieces; the unused tail of the arrays is left as empty segments.  One block:
@@ -489,7 +493,9 @@ int build_tiled(scs_ctx* ctx, const Stream& s, TiledStream& t, int KP, int TR, i
     SCS_TRY(dev_alloc(ctx, &t.seg_ptr, ncta + 1));
     SCS_TRY(dev_alloc(ctx, &t.seg_tile, t.nseg));
     SCS_TRY(dev_alloc(ctx, &t.gb, (int64_t)t.nseg * (ngroups + 1)));
-    k_plan_ctas<<<(ncta + 1 + 127) / 128, 128, 0, st>>>(t.tptr, t.nunits, ncta, d_cu);
+    const char* tc_env = std::getenv("SCS_TILE_COST");   // (see build_qtiled; the same charge per extra tile, in entries)
+    const int64_t tile_cost = tc_env ? atoll(tc_env) : (int64_t)TR * KP * 8 / 8;
+    k_plan_ctas<<<(ncta + 1 + 127) / 128, 128, 0, st>>>(t.tptr, t.nunits, ncta, d_cu, s.nrows, tile_cost);
     k_plan_segments<<<1, 1024, 0, st>>>(d_cu, ncta, s.nrows, t.nseg, t.seg_ptr, t.seg_tile, d_lo, d_hi);
     k_plan_groups<<<t.nseg, 256, 0, st>>>(t.tptr, d_lo, d_hi, ngroups, t.gb);
     ctx->launches += 3;
@@ -683,7 +689,12 @@ int build_qtiled(scs_ctx* ctx, const Stream& s, TiledStream& t, int lanes, int T
     SCS_TRY(dev_alloc(ctx, &t.seg_ptr, ncta + 1));
     SCS_TRY(dev_alloc(ctx, &t.seg_tile, t.nseg));
     SCS_TRY(dev_alloc(ctx, &t.gb, (int64_t)t.nseg * (ngroups + 1)));
-    k_plan_ctas<<<(ncta + 1 + 127) / 128, 128, 0, st>>>(tptr, nunits, ncta, d_cu);
+    // what running into a second tile costs a CTA, in codes: measured at config 3 (E-step sums 118.2 us with 0, 117.5 / 116.7 /
+    // 114.5 / 109.6 / 112.4 / 116.1 us with 4k / 12k / 20k / 30k / 50k / 150k): far more than the 5 us of the load itself -- the CTA
+    // drains at the segment's end and every group starts cold again.  tile bytes / 8 = 29k for the 227 KB tile.
+    const char* tc_env = std::getenv("SCS_Q_TILE_COST");
+    const int64_t tile_cost = tc_env ? atoll(tc_env) : (int64_t)(TR + 2) * lanes * 16 / 8;
+    k_plan_ctas<<<(ncta + 1 + 127) / 128, 128, 0, st>>>(tptr, nunits, ncta, d_cu, s.nrows, tile_cost);
     k_plan_segments<<<1, 1024, 0, st>>>(d_cu, ncta, s.nrows, t.nseg, t.seg_ptr, t.seg_tile, d_lo, d_hi);
     k_plan_groups<<<t.nseg, 256, 0, st>>>(tptr, d_lo, d_hi, ngroups, t.gb);
     ctx->launches += 3;
