@@ -428,12 +428,13 @@ struct TableOut {
     int32_t* qbad_next = nullptr; // [R] staging of the flag while the blocks of an EM-loop launch are still writing the table
 };
 
-constexpr int FIN_THREADS = 256;
-inline int finalize_rows_per_block(int KP) { return FIN_THREADS / KP; }
+constexpr int FIN_THREADS = 256, FIN_RPT = 2;           // threads per block; SNVs per thread (two independent log2 chains in flight)
+inline int finalize_rows_per_block(int KP) { return FIN_RPT * (FIN_THREADS / KP); }
 
 // P = (altW + k_alt) / ((altW + refW) + 1);  T[v] = log2 P, T[V+v] = log2(1 - P)   (scSplit:196, 176-177)
-// A block owns FIN_THREADS / KP whole SNVs (thread = one (SNV, state)), so that the packed fixed-point rows -- which mix the
-// states of a row into 16-byte lanes -- can be put together from shared memory.  With Pin the probabilities are taken as
+// A block owns FIN_RPT * (FIN_THREADS / KP) whole SNVs (thread = one state of FIN_RPT SNVs), so that the packed fixed-point
+// rows -- which mix the states of a row into 16-byte lanes -- can be put together from shared memory, and so that the grid
+// of a 30k-SNV table is half a wave instead of a wave and a sliver.  With Pin the probabilities are taken as
 // given (EM start, scs_em_set(SCS_P), post-EM scores) instead of computed from the statistics.
 // With `prior` (the EM loop) the LAST block of a restart to finish also runs update_prior (block counter in prior.count,
 // left at zero again): by then every block has read the stop flag, so a restart that stops NOW still gets this
@@ -442,35 +443,46 @@ static __global__ void __launch_bounds__(FIN_THREADS) k_finalize(int64_t V, int 
                                                           const double* __restrict__ kalt, const double* __restrict__ Pin,
                                                           double* __restrict__ P, const TableOut out,
                                                           const int32_t* __restrict__ done, const PriorArgs prior) {
-    __shared__ double s_l[2][FIN_THREADS];
+    __shared__ double s_l[2][FIN_RPT * FIN_THREADS];
     const int r = blockIdx.y;
     if (done && done[r]) return;
-    const int rpb = FIN_THREADS / KP;
+    const int rph = FIN_THREADS / KP, rpb = FIN_RPT * rph;             // SNVs per pass of the threads / per block
     const int64_t v0 = (int64_t)blockIdx.x * rpb;
     const int rl = threadIdx.x / KP, k = threadIdx.x - rl * KP;
-    const int64_t v = v0 + rl;
-    double lp = 0.0, lq = 0.0;
-    if (rl < rpb && v < V) {
-        double p = 0.0;
-        if (k < K) {
+    double lp[FIN_RPT], lq[FIN_RPT], p[FIN_RPT];
+#pragma unroll
+    for (int h = 0; h < FIN_RPT; ++h) {
+        const int64_t v = v0 + h * rph + rl;
+        p[h] = 0.0;
+        if (rl < rph && v < V && k < K) {
             if (Pin) {
-                p = Pin[((int64_t)r * V + v) * KP + k];
+                p[h] = Pin[((int64_t)r * V + v) * KP + k];
             } else {
                 const double* S = stats + (int64_t)r * stats_stride;
                 const double a = S[v * KP + k], rf = S[(V + v) * KP + k];
-                p = (a + kalt[v]) / ((a + rf) + 1.0);
+                p[h] = (a + kalt[v]) / ((a + rf) + 1.0);
             }
-            lp = log2(p);
-            lq = log2(1.0 - p);
         }
-        if (P) P[((int64_t)r * V + v) * KP + k] = p;
-        if (out.T) {
-            out.T[((int64_t)r * 2 * V + v) * KP + k] = lp;
-            out.T[((int64_t)r * 2 * V + V + v) * KP + k] = lq;
+    }
+#pragma unroll
+    for (int h = 0; h < FIN_RPT; ++h) {
+        const int64_t v = v0 + h * rph + rl;
+        const bool live = rl < rph && v < V;
+        lp[h] = (live && k < K) ? log2(p[h]) : 0.0;
+        lq[h] = (live && k < K) ? log2(1.0 - p[h]) : 0.0;
+        if (live) {
+            if (P) P[((int64_t)r * V + v) * KP + k] = p[h];
+            if (out.T) {
+                out.T[((int64_t)r * 2 * V + v) * KP + k] = lp[h];
+                out.T[((int64_t)r * 2 * V + V + v) * KP + k] = lq[h];
+            }
         }
     }
     if (out.Tq) {                                        // (uniform over the grid)
-        if (threadIdx.x < rpb * KP) { s_l[0][threadIdx.x] = lp; s_l[1][threadIdx.x] = lq; }
+        if (rl < rph) {
+#pragma unroll
+            for (int h = 0; h < FIN_RPT; ++h) { s_l[0][(h * rph + rl) * KP + k] = lp[h]; s_l[1][(h * rph + rl) * KP + k] = lq[h]; }
+        }
         __syncthreads();
         const int QL = out.qlanes;
         bool bad = false;

@@ -299,27 +299,29 @@ constexpr int64_t UNIT_COST = 8;
 // `tile_cost` (entries) is charged for every tile boundary inside the range -- a CTA whose range runs into the next tile loads a
 // second table tile (a few microseconds with every CTA pulling its tile from L2 at once) and should get fewer entries for it;
 // `nrows` units make a tile.  tile_cost = 0 inside a segment (one tile by construction).
-__device__ __forceinline__ int64_t plan_cost(const int64_t* __restrict__ tptr, int64_t lo, int64_t u, int64_t nrows = 1, int64_t tile_cost = 0) {
-    return (tptr[u] - tptr[lo]) + UNIT_COST * (u - lo) + (tile_cost ? tile_cost * ((u > lo ? (u - 1) / nrows : lo / nrows) - lo / nrows) : 0);
+__device__ __forceinline__ int64_t plan_cost(const int64_t* __restrict__ tptr, int64_t lo, int64_t u, int64_t nrows = 1, int64_t tile_cost = 0,
+                                             int64_t unit_cost = UNIT_COST) {
+    return (tptr[u] - tptr[lo]) + unit_cost * (u - lo) + (tile_cost ? tile_cost * ((u > lo ? (u - 1) / nrows : lo / nrows) - lo / nrows) : 0);
 }
 __device__ __forceinline__ int64_t plan_cut(const int64_t* __restrict__ tptr, int64_t lo, int64_t hi, int64_t part, int64_t nparts,
-                                            int64_t nrows = 1, int64_t tile_cost = 0) {
+                                            int64_t nrows = 1, int64_t tile_cost = 0, int64_t unit_cost = UNIT_COST) {
     if (part <= 0) return lo;
     if (part >= nparts) return hi;
-    const int64_t total = plan_cost(tptr, lo, hi, nrows, tile_cost);
+    const int64_t total = plan_cost(tptr, lo, hi, nrows, tile_cost, unit_cost);
     const int64_t target = (total / nparts) * part + ((total % nparts) * part) / nparts;
     int64_t a = lo, b = hi;
     while (a < b) {          // first unit u with cost(lo, u) >= target
         const int64_t mid = (a + b) >> 1;
-        if (plan_cost(tptr, lo, mid, nrows, tile_cost) < target) a = mid + 1; else b = mid;
+        if (plan_cost(tptr, lo, mid, nrows, tile_cost, unit_cost) < target) a = mid + 1; else b = mid;
     }
     return a;
 }
 // cu[j] = first unit of CTA j (equal-cost split of all units)
-__global__ void k_plan_ctas(const int64_t* __restrict__ tptr, int64_t nunits, int ncta, int64_t* __restrict__ cu, int64_t nrows, int64_t tile_cost) {
+__global__ void k_plan_ctas(const int64_t* __restrict__ tptr, int64_t nunits, int ncta, int64_t* __restrict__ cu, int64_t nrows, int64_t tile_cost,
+                            int64_t unit_cost = UNIT_COST) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j > ncta) return;
-    cu[j] = plan_cut(tptr, 0, nunits, j, ncta, nrows, tile_cost);
+    cu[j] = plan_cut(tptr, 0, nunits, j, ncta, nrows, tile_cost, unit_cost);
 }
 // Tile segments of the CTA ranges: CTA j runs the pieces of [cu[j], cu[j+1]) between tile boundaries (a tile owns nrows
 // consecutive units).  At most ncta + ntiles pieces; the unused tail of the arrays is left as empty segments.  One block:
@@ -356,10 +358,10 @@ __global__ void __launch_bounds__(1024) k_plan_segments(const int64_t* __restric
 }
 // gb[seg][G] = first unit of row group G inside segment [lo, hi)
 __global__ void k_plan_groups(const int64_t* __restrict__ tptr, const int64_t* __restrict__ seg_lo, const int64_t* __restrict__ seg_hi,
-                              int ngroups, int64_t* __restrict__ gb) {
+                              int ngroups, int64_t* __restrict__ gb, int64_t unit_cost = UNIT_COST) {
     const int seg = blockIdx.x;
     for (int G = threadIdx.x; G <= ngroups; G += blockDim.x)
-        gb[(int64_t)seg * (ngroups + 1) + G] = plan_cut(tptr, seg_lo[seg], seg_hi[seg], G, ngroups);
+        gb[(int64_t)seg * (ngroups + 1) + G] = plan_cut(tptr, seg_lo[seg], seg_hi[seg], G, ngroups, 1, 0, unit_cost);
 }
 
 // ---- build-time order of the entries inside the units of a packed tile-major stream (spmm_tiled.cuh, "packed" groups).
@@ -694,9 +696,11 @@ int build_qtiled(scs_ctx* ctx, const Stream& s, TiledStream& t, int lanes, int T
     // drains at the segment's end and every group starts cold again.  tile bytes / 8 = 29k for the 227 KB tile.
     const char* tc_env = std::getenv("SCS_Q_TILE_COST");
     const int64_t tile_cost = tc_env ? atoll(tc_env) : (int64_t)(TR + 2) * lanes * 16 / 8;
-    k_plan_ctas<<<(ncta + 1 + 127) / 128, 128, 0, st>>>(tptr, nunits, ncta, d_cu, s.nrows, tile_cost);
+    const char* uc_env = std::getenv("SCS_Q_UNIT_COST");
+    const int64_t unit_cost = uc_env ? atoll(uc_env) : UNIT_COST;
+    k_plan_ctas<<<(ncta + 1 + 127) / 128, 128, 0, st>>>(tptr, nunits, ncta, d_cu, s.nrows, tile_cost, unit_cost);
     k_plan_segments<<<1, 1024, 0, st>>>(d_cu, ncta, s.nrows, t.nseg, t.seg_ptr, t.seg_tile, d_lo, d_hi);
-    k_plan_groups<<<t.nseg, 256, 0, st>>>(tptr, d_lo, d_hi, ngroups, t.gb);
+    k_plan_groups<<<t.nseg, 256, 0, st>>>(tptr, d_lo, d_hi, ngroups, t.gb, unit_cost);
     ctx->launches += 3;
     if (lanes == 4 && !std::getenv("SCS_Q_NO_ORDER")) {
         uint8_t* d_phase = nullptr;
