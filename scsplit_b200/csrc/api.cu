@@ -105,6 +105,7 @@ int scs_destroy(scs_ctx* ctx) {
     free_tiled(ctx, ctx->TE);
     free_tiled(ctx, ctx->TM);
     free_tiled(ctx, ctx->QE);
+    free_lockstep(ctx, ctx->LK);
     dev_free(ctx, ctx->qpart);
     dev_free(ctx, ctx->part);
     dev_free(ctx, ctx->sum_alt);

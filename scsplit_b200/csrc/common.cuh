@@ -82,6 +82,22 @@ struct TiledStream {
     int64_t* gb = nullptr;        // [nseg][ngroups + 1] unit boundaries
 };
 
+// Lock-step stream of the fixed-point E-step (estep_lk.cuh): the units (cell, table tile) of a tile sorted by length and dealt
+// 32 at a time to "tasks" -- 32 units of one padded length, one per lane -- whose codes lie lane-interleaved: stream row x
+// holds one 32-bit word (two 16-bit codes) for each of the 32 lanes.
+struct LockstepStream {
+    int lanes = 0;              // 16-byte chunks per table row: 4 (64-byte rows, K <= 9) or 8 (128-byte rows, K <= 17)
+    int TR = 0, ntiles = 0;
+    int64_t ntasks = 0, nrows = 0;
+    uint32_t* words = nullptr;      // [nrows][32]
+    int64_t* task_row = nullptr;    // [ntasks + 1] first stream row of each task (tasks in tile-major order)
+    int32_t* task_cell = nullptr;   // [ntasks][32] cell of each lane's unit, -1 = the lane has none
+    int32_t* tile_task = nullptr;   // [ntiles + 1] first task of each tile
+    int ncta = 0;
+    int64_t* cta_row = nullptr;     // [ncta + 1] stream-row ranges of the CTAs (equal cost; a tile boundary inside a range is charged)
+    int32_t* xheavy = nullptr;      // [N] entries of each cell with count > Q_REP_MAX (k_bayes adds them in fp64)
+};
+
 struct NcclApi;  // dlopen'ed function table (comm.cu)
 
 // Which kernel does a restart's M-step sums: the sparse kernel (saturated posteriors) or the tiled SpMM.  The decision is a
@@ -112,6 +128,7 @@ struct EmState {
     uint64_t* Tq = nullptr;     // [R][2V][2 * q_lanes] fixed-point copy of T (estep_q.cuh); nullptr = the E-step runs in fp64
     int32_t* qbad = nullptr;    // [R] the restart's table does not fit the fixed-point format: its E-step runs in fp64
     int q_lanes = 0, q_F = 0;
+    unsigned long long* Lq = nullptr;   // [R][N][KP] integer E-step totals of the lock-step kernel (estep_lk.cuh); k_bayes leaves them at zero
     int32_t* sat = nullptr;     // [R] latched: the restart's dense-row count has been at or below the saturation threshold
     uint32_t* hq = nullptr;     // [R][h_stride] packed (state, 1 - weight) of a saturated posterior row, or SPARSE_DENSE
     int64_t h_stride = 0;       // N rounded up to 4 (16-byte multiples for the bulk copy)
@@ -144,6 +161,7 @@ struct scs_ctx {
     scs::Stream M;   // SNV-major (2V pseudo-rows)
     scs::TiledStream TE, TM;   // tile-major copies for the current KP
     scs::TiledStream QE;       // tile-major cell-major stream of the fixed-point E-step (estep_q.cuh): KP field = lanes per row
+    scs::LockstepStream LK;    // lock-step stream of the fixed-point E-step (estep_lk.cuh), the default form
     int q_state[2] = {0, 0};   // per row width (4 / 8 lanes): 0 = not tried, 1 = built, -1 = the pool does not fit the format
     int q_F = 0;               // fraction bits of the fixed-point tables of this pool
     uint64_t* qpart = nullptr; // per-(unit, lane) integer sums of the fixed-point E-step
@@ -245,6 +263,9 @@ int build_row_order(scs_ctx* ctx, const Stream& s, int32_t** order, int nchunks 
 int build_block_ptrs(scs_ctx* ctx, const Stream& s, int nblocks, int64_t block, int64_t** bp);
 // tile-major stream of the fixed-point E-step; *ok = 0 when the pool's cells are too deep for a useful fraction (F < 40)
 int build_qtiled(scs_ctx* ctx, const Stream& s, TiledStream& t, int lanes, int TR, int ncta, int ngroups, int* F, int* ok);
+// lock-step stream of the fixed-point E-step (same conditions as build_qtiled)
+int build_lockstep(scs_ctx* ctx, const Stream& s, LockstepStream& t, int lanes, int TR, int ncta, int* F, int* ok);
+void free_lockstep(scs_ctx* ctx, LockstepStream& t);
 
 // em.cu
 int launch_spmm(scs_ctx* ctx, int kind /*0=E,1=M*/, int KP, int R, const double* X, int64_t x_stride, double* Y,

@@ -5,6 +5,7 @@
 #include "em_kernels.cuh"
 #include "spmm_tiled.cuh"
 #include "mstep_sparse.cuh"
+#include "estep_lk.cuh"
 
 namespace scs {
 
@@ -127,6 +128,10 @@ int launch_spmm_tiled(scs_ctx* ctx, int kind, int KP, int R, const double* X, in
 
 // Fixed-point E-step (estep_q.cuh): tile-major stream with inline counts, built on first use per row width.
 // Returns the lanes per row (4 / 8) when this pool and K can use it, else 0.
+// The lock-step form (estep_lk.cuh: a lane per entry, integer totals by RED, no combine kernel) is the default; SCS_Q_GROUPS=1
+// selects the row-group form (estep_q.cuh: a group of lanes per entry, per-unit sums + k_combine_q) for A/B measurements.
+static bool lk_wanted() { return std::getenv("SCS_Q_GROUPS") == nullptr; }
+
 static int q_prepare(scs_ctx* ctx, int K) {
     if (ctx->variant != 0 || std::getenv("SCS_NO_Q")) return 0;
     const int lanes = q_lanes_for(K);
@@ -136,6 +141,16 @@ static int q_prepare(scs_ctx* ctx, int K) {
     const int ctas = ctx->sm_count > 0 ? ctx->sm_count : 148;
     const int ngroups = (TILED_THREADS / 32) * (32 / lanes);
     const int TR = q_tile_rows(lanes, ctx->E.xrows);
+    if (lk_wanted()) {
+        if (ctx->LK.lanes != lanes || ctx->LK.TR != TR || ctx->LK.ncta != ctas || !ctx->LK.words) {
+            int ok = 0, F = 0;
+            if (build_lockstep(ctx, ctx->E, ctx->LK, lanes, TR, ctas, &F, &ok)) return -1;
+            ctx->q_state[idx] = ok ? 1 : -1;
+            if (!ok) return 0;
+            ctx->q_F = F;
+        }
+        return lanes;
+    }
     if (ctx->QE.KP != lanes || ctx->QE.TR != TR || ctx->QE.ncta != ctas || ctx->QE.ngroups != ngroups || !ctx->QE.tcode) {
         int ok = 0, F = 0;
         if (build_qtiled(ctx, ctx->E, ctx->QE, lanes, TR, ctas, ngroups, &F, &ok)) return -1;
@@ -146,8 +161,31 @@ static int q_prepare(scs_ctx* ctx, int K) {
     return lanes;
 }
 
+static int launch_estep_lk(scs_ctx* ctx, const int32_t* done) {
+    EmState& em = ctx->em;
+    const LockstepStream& t = ctx->LK;
+    const int lanes = em.q_lanes;
+    const size_t smem = ((((size_t)(t.TR + 2) * lanes * 16) + 127) & ~(size_t)127) + 16;
+    if (!(ctx->smem_attr_set[2] >> (26 + lanes / 8) & 1u)) {
+        if (lanes == 4) SCS_CUDA(cudaFuncSetAttribute(k_estep_lk<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, Q_SMEM_BYTES));
+        else SCS_CUDA(cudaFuncSetAttribute(k_estep_lk<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, Q_SMEM_BYTES));
+        ctx->smem_attr_set[2] |= 1u << (26 + lanes / 8);
+    }
+    LkStreamView v;
+    v.words = t.words; v.task_row = t.task_row; v.task_cell = t.task_cell; v.tile_task = t.tile_task; v.cta_row = t.cta_row;
+    v.ntiles = t.ntiles; v.TR = t.TR; v.xrows = ctx->E.xrows;
+    dim3 grid((unsigned)t.ncta, (unsigned)em.R);
+    const int64_t xq_stride = 2 * ctx->V * 2 * lanes;
+    if (lanes == 4) k_estep_lk<4><<<grid, LK_THREADS, smem, ctx->stream>>>(v, em.Tq, xq_stride, em.Lq, ctx->N * em.KP, em.K, em.KP, done, em.qbad);
+    else k_estep_lk<8><<<grid, LK_THREADS, smem, ctx->stream>>>(v, em.Tq, xq_stride, em.Lq, ctx->N * em.KP, em.K, em.KP, done, em.qbad);
+    ctx->launches += 1;
+    SCS_CUDA(cudaGetLastError());
+    return 0;
+}
+
 static int launch_estep_q(scs_ctx* ctx, const int32_t* done) {
     EmState& em = ctx->em;
+    if (em.Lq) return launch_estep_lk(ctx, done);
     TiledStream& t = ctx->QE;
     const int lanes = em.q_lanes;
     const int64_t part_stride = t.nunits * q_part_words(lanes);
@@ -187,7 +225,7 @@ int em_free(scs_ctx* ctx) {
     for (auto& row : em.graph)
         for (auto& g : row)
             if (g) { cudaGraphExecDestroy(g); g = nullptr; }
-    dev_free(ctx, em.Tq); dev_free(ctx, em.qbad); dev_free(ctx, em.gstats);
+    dev_free(ctx, em.Tq); dev_free(ctx, em.qbad); dev_free(ctx, em.gstats); dev_free(ctx, em.Lq);
     ctx->h_done.clear();
     dev_free(ctx, em.T); dev_free(ctx, em.P); dev_free(ctx, em.L); dev_free(ctx, em.W); dev_free(ctx, em.stats); dev_free(ctx, em.lps);
     dev_free(ctx, em.hq); dev_free(ctx, em.sched);
@@ -290,6 +328,12 @@ static int run_e(scs_ctx* ctx, const int32_t* done) {
         src.lptr = ctx->E.lptr; src.hptr = ctx->E.hptr; src.lcode = ctx->E.lcode; src.hcode = ctx->E.hcode; src.hcnt = ctx->E.hcnt;
         src.T = em.T;
         src.t_stride = 2 * V * em.KP;
+        if (em.Lq) {
+            src.Lq = em.Lq;
+            src.xheavy = ctx->LK.xheavy;
+            src.scale_inv = ldexp(1.0, -em.q_F);
+            src.rep_max = Q_REP_MAX;
+        }
     } else {
         SCS_TRY(launch_spmm(ctx, 0, em.KP, em.R, em.T, 2 * V * em.KP, em.L, N * em.KP, done));
     }
@@ -476,7 +520,8 @@ int scs_em_footprint(scs_ctx* ctx, int K, int64_t out[2]) {
     const int lanes = q_lanes_for(K);
     if (lanes) {
         const int64_t ntq = (2 * V + q_tile_rows(lanes, 2 * V) - 1) / q_tile_rows(lanes, 2 * V);
-        b += 2 * V * 2 * lanes * 8 + ntq * N * q_part_words(lanes) * 8;      // fixed-point table, its per-unit sums
+        // fixed-point table; integer totals (lock-step form) or per-unit sums (row-group form)
+        b += 2 * V * 2 * lanes * 8 + (lk_wanted() ? N * KP * 8 : ntq * N * q_part_words(lanes) * 8);
     }
     const int64_t nte = (2 * V + tile_rows_for((int)KP, 2 * V) - 1) / tile_rows_for((int)KP, 2 * V);
     const int64_t ntm = (N + tile_rows_for((int)KP, N) - 1) / tile_rows_for((int)KP, N);
@@ -530,6 +575,10 @@ int scs_em_begin(scs_ctx* ctx, int R, int K, const double* P0, int max_iter) {
             SCS_TRY(dev_alloc(ctx, &em.Tq, (int64_t)R * 2 * V * 2 * lanes));
             SCS_TRY(dev_alloc(ctx, &em.qbad, 2 * R));   // [R] flags, [R] their staging inside k_finalize
             SCS_CUDA(cudaMemsetAsync(em.qbad, 0, (size_t)R * 8, ctx->stream));
+            if (lk_wanted()) {
+                SCS_TRY(dev_alloc(ctx, &em.Lq, (int64_t)R * N * em.KP));
+                SCS_CUDA(cudaMemsetAsync(em.Lq, 0, (size_t)R * N * em.KP * 8, ctx->stream));
+            }
         }
     }
     SCS_TRY(dev_alloc(ctx, &em.T, (int64_t)R * 2 * V * KP));
@@ -743,15 +792,17 @@ int scs_em_status(scs_ctx* ctx, int32_t* iters, int32_t* converged, double* ll) 
     return 0;
 }
 
-int scs_em_info(scs_ctx* ctx, int64_t out[4]) {
+int scs_em_info(scs_ctx* ctx, int64_t out[6]) {
     SCS_CHECK(ctx && ctx->em.R, "EM state not initialised (call scs_em_begin)");
     SCS_CHECK(out, "null output");
     SCS_CUDA(cudaSetDevice(ctx->device));
     EmState& em = ctx->em;
     out[0] = em.Tq ? em.q_lanes : 0;
     out[1] = em.Tq ? em.q_F : 0;
-    out[2] = em.Tq ? ctx->QE.ntiles : ctx->TE.ntiles;
+    out[2] = em.Lq ? ctx->LK.ntiles : em.Tq ? ctx->QE.ntiles : ctx->TE.ntiles;
     out[3] = 0;
+    out[4] = em.Lq ? 2 : em.Tq ? 1 : 0;
+    out[5] = em.Lq ? ctx->LK.ntasks : 0;
     if (em.Tq) {
         std::vector<int32_t> bad((size_t)em.R);
         SCS_CUDA(cudaMemcpyAsync(bad.data(), em.qbad, (size_t)em.R * 4, cudaMemcpyDeviceToHost, ctx->stream));

@@ -241,6 +241,12 @@ struct LSource {
     const int32_t* hcnt = nullptr;
     const double* T = nullptr;        // [R][2V][KP]
     int64_t t_stride = 0;
+    // lock-step fixed-point E-step (estep_lk.cuh): the sums arrive as 64-bit integer totals, L = -total * 2^-F; k_bayes adds the
+    // entries whose counts were too large for repeated codes (xheavy[c] of them in cell c) in fp64, writes L and zeroes the totals
+    unsigned long long* Lq = nullptr; // [R][N][KP]
+    const int32_t* xheavy = nullptr;  // [N]
+    double scale_inv = 0.0;           // 2^-F
+    int rep_max = 0;                  // counts up to this were written as repeated codes
 };
 
 template <int KP>
@@ -286,6 +292,22 @@ __global__ void __launch_bounds__(1024) k_bayes(int64_t N, int K, const LSource 
         if (src.qbad && src.qbad[r]) {
             Li = bayes_row_from_table<KP>(src, r, c, cell, i, K);
             if (cell && i < KP) L[((int64_t)r * N + c) * KP + i] = Li;
+        } else if (src.Lq) {
+            Li = 0.0;
+            if (cell && i < KP) {
+                unsigned long long* q = src.Lq + ((int64_t)r * N + c) * KP + i;
+                const unsigned long long sq = *q;
+                if (sq) *q = 0ull;                                       // the next E-step adds to zero again
+                if (i < K && sq) Li = -((double)sq * src.scale_inv);
+                if (src.xheavy[c] && i < K) {                            // (rare) counts above Q_REP_MAX, in stream order
+                    const double* T = src.T + (int64_t)r * src.t_stride;
+                    for (int64_t h = src.hptr[c]; h < src.hptr[c + 1]; ++h) {
+                        const int cnt = __ldg(src.hcnt + h);
+                        if (cnt > src.rep_max) Li += (double)cnt * __ldg(T + (int64_t)(__ldg(src.hcode + h) >> 1) * KP + i);
+                    }
+                }
+                L[((int64_t)r * N + c) * KP + i] = Li;
+            }
         } else {
             Li = live ? L[((int64_t)r * N + c) * KP + i] : 0.0;
         }

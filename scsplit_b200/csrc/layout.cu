@@ -13,6 +13,7 @@
 
 #include "common.cuh"
 #include "estep_q.cuh"
+#include "estep_lk.cuh"
 
 namespace scs {
 
@@ -529,7 +530,7 @@ __device__ __forceinline__ int64_t q_codes_of(int64_t c) { return c <= Q_REP_MAX
 // one thread per unit: padded code count, where the unit's light / heavy entries start inside the row
 __global__ void k_qunit_counts(int64_t nrows, int ntiles, int TR, const int64_t* __restrict__ lptr, const uint32_t* __restrict__ lcode,
                                const int64_t* __restrict__ hptr, const uint32_t* __restrict__ hcode, const int32_t* __restrict__ hcnt,
-                               int64_t* __restrict__ cnt, int32_t* __restrict__ ulo, int32_t* __restrict__ uho) {
+                               int64_t* __restrict__ cnt, int32_t* __restrict__ ulo, int32_t* __restrict__ uho, int pad = Q_UNIT_PAD) {
     const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (u >= nrows * ntiles) return;
     const int64_t t = u / nrows, row = u - t * nrows;
@@ -538,7 +539,7 @@ __global__ void k_qunit_counts(int64_t nrows, int ntiles, int TR, const int64_t*
     const int64_t hlo = row_lower_bound(hcode, hb, he, t * TR), hhi = row_lower_bound(hcode, hb, he, (t + 1) * (int64_t)TR);
     int64_t n = hi - lo;
     for (int64_t h = hlo; h < hhi; ++h) n += q_codes_of(hcnt[h]);
-    cnt[u] = (n + Q_UNIT_PAD - 1) / Q_UNIT_PAD * Q_UNIT_PAD;
+    cnt[u] = (n + pad - 1) / pad * pad;
     ulo[u] = (int32_t)(lo - b);
     uho[u] = (int32_t)(hlo - hb);
 }
@@ -718,6 +719,315 @@ int build_qtiled(scs_ctx* ctx, const Stream& s, TiledStream& t, int lanes, int T
     else k_qpack_words<8><<<(unsigned)((total / 2 + 255) / 256), 256, 0, st>>>(total / 2, reinterpret_cast<uint32_t*>(t.tcode));
     ctx->launches++;
     SCS_CUDA(cudaGetLastError());
+    *ok = 1;
+    return 0;
+}
+
+// ---- lock-step stream of the fixed-point E-step (estep_lk.cuh) ----------------------------------------------------
+// The units (cell, table tile) of a tile are sorted by length and dealt 32 at a time to tasks; a task's 32 units are read by
+// the 32 lanes of a warp side by side, so they are padded to one length.  For 64-byte rows the lanes l and l + 4 of a quarter
+// warp read the same 16-byte chunk position of their rows at every step, which is conflict-free exactly when the two rows lie
+// in different halves of a 128-byte bank line, i.e. differ in parity.  Units are therefore PAIRED: A (lanes 0..3 of a
+// quarter) lists its even rows first and then its odd rows, B (lanes 4..7) its odd rows first and then its even rows; with
+// e / o the even / odd codes of a unit, the pair needs max(eA, oB) + max(oA, eB) positions, the shorter list of either part
+// padded by codes of the all-zero row of the right parity (rows TR and TR + 1 of the tile are zero).  That is eA + oA when B
+// is A's mirror image, so inside every class of equal length the units are sorted by e - o and the i-th smallest is paired
+// with the i-th largest.  The pairs of a tile are then sorted by the positions they need and cut into tasks of 16 pairs.
+// The order inside a unit does not matter: the sums are integers.
+
+constexpr int LK_FIELD = 21;                                   // bits of the length / imbalance fields of a sort key
+constexpr uint64_t LK_FMASK = (1ull << LK_FIELD) - 1;
+constexpr uint64_t LK_NONE = ~0ull;                            // key of an empty unit / of a unit that is the second of its pair
+
+// one thread per unit: key = tile | codes | (even - odd + 2^20), the unit's id, its codes in even rows
+__global__ void k_lk_unit_keys(int64_t nunits, int64_t ncells, int lanes, const int64_t* __restrict__ tptr, const uint16_t* __restrict__ tcode,
+                               uint64_t* __restrict__ key, uint32_t* __restrict__ val, int32_t* __restrict__ ue) {
+    const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= nunits) return;
+    const int64_t b = tptr[u], e = tptr[u + 1], len = e - b;
+    val[u] = (uint32_t)u;
+    if (len == 0) { key[u] = LK_NONE; ue[u] = 0; return; }
+    int64_t ev = 0;
+    for (int64_t i = b; i < e; ++i) ev += !(tcode[i] & 1u);
+    if (lanes != 4) ev = len;                                  // a 128-byte row spans every bank: parity means nothing
+    const int64_t d = 2 * ev - len;
+    key[u] = ((uint64_t)(u / ncells) << (2 * LK_FIELD)) | ((uint64_t)len << LK_FIELD) | (uint64_t)((lanes == 4 ? d : 0) + (1 << (LK_FIELD - 1)));
+    ue[u] = (int32_t)ev;
+}
+
+// first i in [0, n) with (key[i] >> shift) >= want (upper: > want)
+__device__ __forceinline__ int64_t lk_bound(const uint64_t* __restrict__ key, int64_t n, uint64_t want, int shift, bool upper) {
+    int64_t lo = 0, hi = n;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        const uint64_t k = key[mid] >> shift;
+        if (upper ? k <= want : k < want) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+// one thread per unit in sorted order: the i-th unit of its (tile, length) class is paired with the i-th from the class's end;
+// the first of a pair gets the pair's key = tile | positions needed (even), the second (and every empty unit) LK_NONE
+__global__ void k_lk_pairs(int64_t nunits, int lanes, const uint64_t* __restrict__ key_s, const uint32_t* __restrict__ val_s,
+                           const int32_t* __restrict__ ue, const int64_t* __restrict__ tptr, uint64_t* __restrict__ pkey, uint32_t* __restrict__ pval,
+                           int32_t* __restrict__ pair_u) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nunits) return;
+    pval[i] = (uint32_t)i;
+    const uint64_t k = key_s[i];
+    pkey[i] = LK_NONE;
+    if (k == LK_NONE) return;
+    const uint64_t cls = k >> LK_FIELD;
+    const int64_t s = lk_bound(key_s, nunits, cls, LK_FIELD, false), e = lk_bound(key_s, nunits, cls, LK_FIELD, true);
+    const int64_t j = s + e - 1 - i;
+    if (i > j) return;
+    const int64_t uA = val_s[i], uB = j != i ? (int64_t)val_s[j] : -1;
+    const int64_t lenA = tptr[uA + 1] - tptr[uA], eA = ue[uA], oA = lenA - eA;
+    const int64_t lenB = uB >= 0 ? tptr[uB + 1] - tptr[uB] : 0, eB = uB >= 0 ? ue[uB] : 0, oB = lenB - eB;
+    int64_t n = lanes == 4 ? max(eA, oB) + max(oA, eB) : max(lenA, lenB);
+    n = (n + 1) & ~(int64_t)1;
+    pair_u[2 * i] = (int32_t)uA;
+    pair_u[2 * i + 1] = (int32_t)uB;
+    pkey[i] = ((k >> (2 * LK_FIELD)) << (2 * LK_FIELD)) | ((uint64_t)n << LK_FIELD);
+}
+
+// one block: where each tile's pairs start in the sorted pair list, and its first task (16 pairs per task)
+__global__ void k_lk_tiles(int ntiles, int64_t n, const uint64_t* __restrict__ pkey_s, int64_t* __restrict__ ps, int32_t* __restrict__ tile_task) {
+    for (int t = threadIdx.x; t <= ntiles; t += blockDim.x) ps[t] = lk_bound(pkey_s, n, (uint64_t)t << (2 * LK_FIELD), 0, false);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int64_t acc = 0;
+        for (int t = 0; t < ntiles; ++t) { tile_task[t] = (int32_t)acc; acc += (ps[t + 1] - ps[t] + 15) / 16; }
+        tile_task[ntiles] = (int32_t)acc;
+    }
+}
+
+// tile of task k: the last t with tile_task[t] <= k (empty tiles share their first task with the next tile)
+__device__ __forceinline__ int lk_tile_of(const int32_t* __restrict__ tile_task, int ntiles, int64_t k) {
+    int lo = 0, hi = ntiles - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (tile_task[mid] <= k) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
+// one thread per task: stream rows (two positions each) = half the positions of its longest (= last) pair
+__global__ void k_lk_task_len(int64_t ntasks, int ntiles, const int32_t* __restrict__ tile_task, const int64_t* __restrict__ ps,
+                              const uint64_t* __restrict__ pkey_s, int64_t* __restrict__ rows) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= ntasks) return;
+    const int t = lk_tile_of(tile_task, ntiles, k);
+    const int64_t last = min(ps[t] + 16 * (k - tile_task[t]) + 15, ps[t + 1] - 1);
+    rows[k] = (int64_t)((pkey_s[last] >> LK_FIELD) & LK_FMASK) / 2;
+}
+
+// one thread per (task, lane): the lane's unit and its codes in the pair's order, written lane-interleaved
+template <int C>
+__global__ void k_lk_emit(int64_t ntasks, int ntiles, int64_t ncells, int TR, const int32_t* __restrict__ tile_task, const int64_t* __restrict__ ps,
+                          const uint32_t* __restrict__ pval_s, const int32_t* __restrict__ pair_u, const int32_t* __restrict__ ue,
+                          const int64_t* __restrict__ tptr, const uint16_t* __restrict__ tcode, const int64_t* __restrict__ task_row,
+                          int32_t* __restrict__ task_cell, uint32_t* __restrict__ words) {
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t k = gid >> 5;
+    const int lane = (int)(gid & 31);
+    if (k >= ntasks) return;
+    const int t = lk_tile_of(tile_task, ntiles, k);
+    const int m = (lane >> 2) & 1;                                 // 0: unit A of the pair, 1: unit B
+    const int64_t p = ps[t] + 16 * (k - tile_task[t]) + ((lane >> 3) * 4 + (lane & 3));
+    int64_t uA = -1, uB = -1;
+    if (p < ps[t + 1]) {
+        const int64_t i = pval_s[p];
+        uA = pair_u[2 * i];
+        uB = pair_u[2 * i + 1];
+    }
+    const int64_t lenA = uA >= 0 ? tptr[uA + 1] - tptr[uA] : 0, eA = uA >= 0 ? ue[uA] : 0, oA = lenA - eA;
+    const int64_t lenB = uB >= 0 ? tptr[uB + 1] - tptr[uB] : 0, eB = uB >= 0 ? ue[uB] : 0, oB = lenB - eB;
+    const int64_t n1 = C == 4 ? max(eA, oB) : max(lenA, lenB), n2 = C == 4 ? max(oA, eB) : 0;
+    const int64_t u = m ? uB : uA;
+    task_cell[k * 32 + lane] = u >= 0 ? (int32_t)(u - (int64_t)t * ncells) : -1;
+    const int64_t x0 = task_row[k], nk = 2 * (task_row[k + 1] - x0);
+    const uint32_t zrow[2] = {(uint32_t)(TR + (TR & 1)), (uint32_t)(TR + ((TR & 1) ^ 1))};     // the zero row of parity 0 / 1
+    const int64_t b = u >= 0 ? tptr[u] : 0, e = u >= 0 ? tptr[u + 1] : 0;
+    const uint32_t f = (uint32_t)m;                                // parity of the rows this lane lists first
+    int64_t pos = 0;
+    uint32_t half = 0;
+    auto put = [&](uint32_t row) {
+        const uint32_t c = LkCode<C>::code(row, lane);
+        SCS_ASSERT(c < 65536u && pos < nk);
+        if (pos & 1) words[(x0 + (pos >> 1)) * 32 + lane] = half | (c << 16);
+        else half = c;
+        ++pos;
+    };
+    for (int64_t i = b; i < e; ++i) {
+        const uint32_t row = tcode[i];
+        if (C != 4 || (row & 1u) == f) put(row);
+    }
+    while (pos < n1) put(zrow[f]);
+    if (C == 4) {
+        for (int64_t i = b; i < e; ++i) {
+            const uint32_t row = tcode[i];
+            if ((row & 1u) != f) put(row);
+        }
+        while (pos < n1 + n2) put(zrow[f ^ 1u]);
+    }
+    while (pos < nk) put(zrow[f]);
+}
+
+// Equal-cost ranges of stream rows for the CTAs.  Running into another table tile costs a CTA far more than the load itself
+// (it drains, loads 227 KB, and every warp starts cold): a range is charged `charge` rows for every tile boundary inside it.
+__global__ void k_lk_plan(int ncta, int ntiles, int64_t nrows, const int32_t* __restrict__ tile_task, const int64_t* __restrict__ task_row,
+                          int64_t charge, int64_t* __restrict__ cta_row) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j > ncta) return;
+    auto cost = [&](int64_t x) {                                   // of the rows [0, x)
+        int64_t c = x;
+        for (int t = 1; t < ntiles; ++t) {
+            const int64_t r = task_row[tile_task[t]];
+            if (tile_task[t] < tile_task[t + 1] && r > 0 && r < x) c += charge;
+        }
+        return c;
+    };
+    if (j == 0 || j == ncta) { cta_row[j] = j ? nrows : 0; return; }
+    const int64_t total = cost(nrows), target = (total * j + ncta - 1) / ncta;
+    int64_t lo = 0, hi = nrows;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (cost(mid) < target) lo = mid + 1; else hi = mid;
+    }
+    // a target inside the jump of a tile boundary: cut AT the boundary instead of one row into the next tile
+    if (lo > 0 && cost(lo) - cost(lo - 1) > 1 && cost(lo - 1) < target) --lo;
+    cta_row[j] = lo;
+}
+
+// one thread per cell: entries whose count is too large to be written as repeated codes
+__global__ void k_lk_xheavy(int64_t ncells, const int64_t* __restrict__ hptr, const int32_t* __restrict__ hcnt, int32_t* __restrict__ xheavy) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncells) return;
+    int n = 0;
+    for (int64_t h = hptr[c]; h < hptr[c + 1]; ++h) n += hcnt[h] > Q_REP_MAX;
+    xheavy[c] = n;
+}
+
+void free_lockstep(scs_ctx* ctx, LockstepStream& t) {
+    dev_free(ctx, t.words);
+    dev_free(ctx, t.task_row);
+    dev_free(ctx, t.task_cell);
+    dev_free(ctx, t.tile_task);
+    dev_free(ctx, t.cta_row);
+    dev_free(ctx, t.xheavy);
+    t = LockstepStream();
+}
+
+template <typename KT, typename VT>
+static int lk_sort_pairs(cudaStream_t st, Scratch& tmps, const KT* kin, KT* kout, const VT* vin, VT* vout, int64_t n, int b0, int b1) {
+    size_t tb = 0;
+    SCS_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, kin, kout, vin, vout, n, b0, b1, st));
+    void* tmp = nullptr;
+    SCS_TRY(tmps.get_bytes(&tmp, tb));
+    SCS_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tb, kin, kout, vin, vout, n, b0, b1, st));
+    return 0;
+}
+
+int build_lockstep(scs_ctx* ctx, const Stream& s, LockstepStream& t, int lanes, int TR, int ncta, int* F, int* ok) {
+    free_lockstep(ctx, t);
+    *ok = 0;
+    SCS_CHECK(ncta >= 1 && ncta <= 4096, "work plan supports 1..4096 CTAs (got %d)", ncta);
+    cudaStream_t st = ctx->stream;
+    const int ntiles = (int)((s.xrows + TR - 1) / TR);
+    const int64_t nunits = (int64_t)ntiles * s.nrows;
+    SCS_CHECK(nunits < (1LL << 31) && ntiles < (1 << (LK_FIELD - 1)), "pool too large for the lock-step stream (%lld units)", (long long)nunits);
+    Scratch tmps(st);
+    int32_t *d_ulo = nullptr, *d_uho = nullptr;
+    int64_t *tptr = nullptr, *d_hv = nullptr;
+    SCS_TRY(tmps.get(&d_ulo, nunits));
+    SCS_TRY(tmps.get(&d_uho, nunits));
+    SCS_TRY(tmps.get(&d_hv, 2));
+    SCS_TRY(tmps.get(&tptr, nunits + 1));
+    SCS_CUDA(cudaMemsetAsync(d_hv, 0, 16, st));
+    SCS_CUDA(cudaMemsetAsync(tptr, 0, sizeof(int64_t), st));
+    const unsigned ugrid = (unsigned)((nunits + 255) / 256);
+    k_qunit_counts<<<ugrid, 256, 0, st>>>(s.nrows, ntiles, TR, s.lptr, s.lcode, s.hptr, s.hcode, s.hcnt, tptr + 1, d_ulo, d_uho, 1);
+    k_qrow_depth<<<(unsigned)((s.nrows + 255) / 256), 256, 0, st>>>(s.nrows, s.lptr, s.hptr, s.hcnt, reinterpret_cast<unsigned long long*>(d_hv));
+    {
+        size_t tb = 0;
+        SCS_CUDA(cub::DeviceScan::InclusiveSum(nullptr, tb, tptr + 1, tptr + 1, nunits, st));
+        void* tmp = nullptr;
+        SCS_TRY(tmps.get_bytes(&tmp, tb));
+        SCS_CUDA(cub::DeviceScan::InclusiveSum(tmp, tb, tptr + 1, tptr + 1, nunits, st));
+    }
+    ctx->launches += 4;
+    int64_t h_max = 0, total = 0;
+    SCS_CUDA(cudaMemcpyAsync(&h_max, d_hv, 8, cudaMemcpyDeviceToHost, st));
+    SCS_CUDA(cudaMemcpyAsync(&total, tptr + nunits, 8, cudaMemcpyDeviceToHost, st));
+    SCS_CUDA(cudaStreamSynchronize(st));
+    *F = (uint64_t)h_max < (1ull << 40) ? q_frac_bits(h_max) : 0;
+    if (*F < Q_MIN_F) return 0;                          // cells too deep for a useful fraction: fp64 keeps the E-step
+    uint16_t* tcode = nullptr;
+    SCS_TRY(tmps.get(&tcode, total + 2));
+    k_qtile_scatter<<<(unsigned)((s.nrows + 7) / 8), 256, 0, st>>>(s.nrows, ntiles, TR, s.lptr, s.lcode, s.hptr, s.hcode, s.hcnt, tptr, d_ulo, d_uho, tcode);
+    // units -> sorted by (tile, length, even - odd) -> pairs -> sorted by (tile, positions) -> tasks
+    uint64_t *key = nullptr, *key_s = nullptr, *pkey = nullptr, *pkey_s = nullptr;
+    uint32_t *val = nullptr, *val_s = nullptr, *pval = nullptr, *pval_s = nullptr;
+    int32_t *ue = nullptr, *pair_u = nullptr;
+    int64_t* ps = nullptr;
+    SCS_TRY(tmps.get(&key, nunits)); SCS_TRY(tmps.get(&key_s, nunits));
+    SCS_TRY(tmps.get(&val, nunits)); SCS_TRY(tmps.get(&val_s, nunits));
+    SCS_TRY(tmps.get(&ue, nunits));
+    SCS_TRY(tmps.get(&pair_u, 2 * nunits));
+    SCS_TRY(tmps.get(&ps, ntiles + 1));
+    k_lk_unit_keys<<<ugrid, 256, 0, st>>>(nunits, s.nrows, lanes, tptr, tcode, key, val, ue);
+    const int top = 2 * LK_FIELD + bits_for(ntiles + 1);  // (the key of an empty unit is all ones: it sorts behind every tile)
+    SCS_TRY(lk_sort_pairs(st, tmps, key, key_s, val, val_s, nunits, 0, top));
+    pkey = key; pval = val;                               // (the unsorted unit keys are not needed any more)
+    SCS_TRY(tmps.get(&pkey_s, nunits));
+    SCS_TRY(tmps.get(&pval_s, nunits));
+    k_lk_pairs<<<ugrid, 256, 0, st>>>(nunits, lanes, key_s, val_s, ue, tptr, pkey, pval, pair_u);
+    SCS_TRY(lk_sort_pairs(st, tmps, pkey, pkey_s, pval, pval_s, nunits, LK_FIELD, top));
+    SCS_TRY(dev_alloc(ctx, &t.tile_task, ntiles + 1));
+    k_lk_tiles<<<1, 256, 0, st>>>(ntiles, nunits, pkey_s, ps, t.tile_task);
+    ctx->launches += 12;
+    int32_t h_ntasks = 0;
+    SCS_CUDA(cudaMemcpyAsync(&h_ntasks, t.tile_task + ntiles, 4, cudaMemcpyDeviceToHost, st));
+    SCS_CUDA(cudaStreamSynchronize(st));
+    const int64_t ntasks = h_ntasks;
+    SCS_TRY(dev_alloc(ctx, &t.task_row, ntasks + 1));
+    SCS_TRY(dev_alloc(ctx, &t.task_cell, (ntasks + 1) * 32));
+    SCS_CUDA(cudaMemsetAsync(t.task_row, 0, sizeof(int64_t), st));
+    int64_t nrows = 0;
+    if (ntasks > 0) {
+        k_lk_task_len<<<(unsigned)((ntasks + 255) / 256), 256, 0, st>>>(ntasks, ntiles, t.tile_task, ps, pkey_s, t.task_row + 1);
+        size_t tb = 0;
+        SCS_CUDA(cub::DeviceScan::InclusiveSum(nullptr, tb, t.task_row + 1, t.task_row + 1, ntasks, st));
+        void* tmp = nullptr;
+        SCS_TRY(tmps.get_bytes(&tmp, tb));
+        SCS_CUDA(cub::DeviceScan::InclusiveSum(tmp, tb, t.task_row + 1, t.task_row + 1, ntasks, st));
+        SCS_CUDA(cudaMemcpyAsync(&nrows, t.task_row + ntasks, 8, cudaMemcpyDeviceToHost, st));
+        SCS_CUDA(cudaStreamSynchronize(st));
+        ctx->launches += 3;
+    }
+    SCS_TRY(dev_alloc(ctx, &t.words, nrows * 32 + 32));
+    if (ntasks > 0) {
+        const unsigned egrid = (unsigned)((ntasks * 32 + 255) / 256);
+        if (lanes == 4) k_lk_emit<4><<<egrid, 256, 0, st>>>(ntasks, ntiles, s.nrows, TR, t.tile_task, ps, pval_s, pair_u, ue, tptr, tcode, t.task_row, t.task_cell, t.words);
+        else k_lk_emit<8><<<egrid, 256, 0, st>>>(ntasks, ntiles, s.nrows, TR, t.tile_task, ps, pval_s, pair_u, ue, tptr, tcode, t.task_row, t.task_cell, t.words);
+        ctx->launches++;
+    }
+    SCS_TRY(dev_alloc(ctx, &t.cta_row, ncta + 1));
+    // (in stream rows of 64 codes; found by a sweep at config 3)
+    const char* tc_env = std::getenv("SCS_LK_TILE_COST");
+    const int64_t charge = tc_env ? atoll(tc_env) : (int64_t)(TR + 2) * lanes * 16 / 512;
+    k_lk_plan<<<(ncta + 1 + 127) / 128, 128, 0, st>>>(ncta, ntiles, nrows, t.tile_task, t.task_row, charge, t.cta_row);
+    SCS_TRY(dev_alloc(ctx, &t.xheavy, s.nrows));
+    k_lk_xheavy<<<(unsigned)((s.nrows + 255) / 256), 256, 0, st>>>(s.nrows, s.hptr, s.hcnt, t.xheavy);
+    ctx->launches += 2;
+    SCS_CUDA(cudaGetLastError());
+    t.lanes = lanes;
+    t.TR = TR;
+    t.ntiles = ntiles;
+    t.ntasks = ntasks;
+    t.nrows = nrows;
+    t.ncta = ncta;
     *ok = 1;
     return 0;
 }

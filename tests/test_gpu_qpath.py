@@ -1,4 +1,4 @@
-"""GPU tests of the fixed-point E-step (csrc/estep_q.cuh) through the C-ABI.
+"""GPU tests of the fixed-point E-step (csrc/estep_lk.cuh, csrc/estep_q.cuh) through the C-ABI.
 
 The E-step sums L[c,k] = sum_v A[v,c] log2 P[v,k] + R[v,c] log2(1-P[v,k]) (scSplit:175-178) run, by default, on a
 55-bit fixed-point copy of the log table with exact integer accumulation.  These tests pin that path against
@@ -114,6 +114,46 @@ def test_fixed_point_heavy_counts(K, E):
     assert_close(Lq, L_o, RTOL, "L heavy counts")
     assert_close(Lq, Lf, 1e-12, "L heavy counts vs fp64")
     assert np.all(Lq[3] == 0.0) and not np.signbit(Lq[3]).any()
+
+
+@pytest.mark.parametrize("K,V,N,dens", [(9, 9000, 700, 0.05), (4, 300, 37, 0.3), (17, 5000, 300, 0.04), (12, 2500, 2100, 0.02), (9, 12000, 90, 0.4)])
+def test_lockstep_form_equals_row_group_form_bitwise(K, V, N, dens, E, monkeypatch):
+    """The two forms of the fixed-point E-step (estep_lk.cuh: a lane per entry, totals by integer RED; estep_q.cuh: a group of
+    lanes per entry, per-unit sums + combine) add the same integers, so L must agree bit for bit -- over several table tiles
+    (V = 9000 / 12000: 2V rows against 3626 per tile), with counts above 8, empty cells, two restarts, and again when the step
+    is repeated (the totals are left at zero by k_bayes)."""
+    from scipy.sparse import csr_matrix
+    from scsplit_b200._lib import SCS_L, SCS_W
+    rng = np.random.default_rng(K * 1000 + N)
+    depth = (rng.random((V, N)) < dens) * rng.choice([1, 1, 1, 1, 2, 3, 8, 9, 40], size=(V, N))
+    alt = rng.binomial(depth, 0.4)
+    ref = depth - alt
+    alt[:, N // 2] = 0
+    ref[:, N // 2] = 0
+    ref_s, alt_s = csr_matrix(ref.astype(np.int32)), csr_matrix(alt.astype(np.int32))
+    P = np.stack([_random_P(V, K, 1), _random_P(V, K, 2)])
+    out = {}
+    for form in ("lock-step", "row groups"):
+        if form == "row groups":
+            monkeypatch.setenv("SCS_Q_GROUPS", "1")
+        else:
+            monkeypatch.delenv("SCS_Q_GROUPS", raising=False)
+        with E(ref_s, alt_s) as eng:
+            eng.em_begin(P)
+            info = eng.em_info()
+            assert info["q_form"] == form, info
+            eng.estep()
+            first = [eng.get(SCS_L, r) for r in range(2)]
+            eng.estep()
+            again = [eng.get(SCS_L, r) for r in range(2)]
+            eng.em_iterate(3, check_conv=False)
+            out[form] = (first, again, [eng.get(SCS_L, r) for r in range(2)], [eng.get(SCS_W, r) for r in range(2)])
+    L_o = alt.T.astype(np.float64) @ np.log2(P[0]) + ref.T.astype(np.float64) @ np.log2(1 - P[0])
+    assert_close(out["lock-step"][0][0], L_o, RTOL, "L lock-step vs dense product")
+    for r in range(2):
+        assert np.array_equal(out["lock-step"][0][r], out["lock-step"][1][r]), "a repeated E-step must give the same sums"
+        for part in range(4):
+            assert np.array_equal(out["lock-step"][part][r], out["row groups"][part][r], equal_nan=True), (part, r)
 
 
 def test_unfit_table_takes_fp64_per_restart(E):
