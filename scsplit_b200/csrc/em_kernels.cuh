@@ -296,10 +296,11 @@ __global__ void __launch_bounds__(1024) k_bayes(int64_t N, int K, const LSource 
             Li = 0.0;
             if (cell && i < KP) {
                 unsigned long long* q = src.Lq + ((int64_t)r * N + c) * KP + i;
-                const unsigned long long sq = *q;
-                if (sq) *q = 0ull;                                       // the next E-step adds to zero again
+                const unsigned long long sq = __ldcs(q);
+                const int nx = __ldg(src.xheavy + c);                    // (both loads are in flight before the store below)
+                *q = 0ull;                                               // the next E-step adds to zero again
                 if (i < K && sq) Li = -((double)sq * src.scale_inv);
-                if (src.xheavy[c] && i < K) {                            // (rare) counts above Q_REP_MAX, in stream order
+                if (nx && i < K) {                                       // (rare) counts above Q_REP_MAX, in stream order
                     const double* T = src.T + (int64_t)r * src.t_stride;
                     for (int64_t h = src.hptr[c]; h < src.hptr[c + 1]; ++h) {
                         const int cnt = __ldg(src.hcnt + h);
@@ -313,9 +314,13 @@ __global__ void __launch_bounds__(1024) k_bayes(int64_t N, int K, const LSource 
         }
         const double ti = Li + si;                                   // L_i + s_i
         double denom = 0.0;
-        for (int j = 0; j < K; ++j) {                                // j ascending, left to right, as the reference adds
+        // (unrolled over the padded state count: the K exponentials are independent and run side by side; only the adds are
+        // a chain.  With the loop bound K at run time the kernel evaluated them one after the other.)
+#pragma unroll
+        for (int j = 0; j < KP; ++j) {                               // j ascending, left to right, as the reference adds
             const double tj = __shfl_sync(0xffffffffu, ti, j, C::GL);
-            denom += exp2_bf((tj - Li) - si);
+            const double ej = exp2_bf((tj - Li) - si);
+            if (j < K) denom += ej;
         }
         const double wi = live ? 1.0 / denom : 0.0;
         if (cell && i < KP) W[((int64_t)r * N + c) * KP + i] = wi;

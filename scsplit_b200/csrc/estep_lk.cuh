@@ -23,8 +23,14 @@
 
 namespace scs {
 
-constexpr int LK_THREADS = 512;      // 16 warps: a lane keeps 3 * C 64-bit sums and up to 8 * C loaded words in registers
-constexpr int LK_RING = 8;           // stream rows a lane has requested ahead of the one it is adding
+#ifndef SCS_LK_THREADS
+#define SCS_LK_THREADS 512
+#endif
+#ifndef SCS_LK_RING
+#define SCS_LK_RING 8
+#endif
+constexpr int LK_THREADS = SCS_LK_THREADS;   // 16 warps: a lane keeps 3 * C 64-bit sums and up to 8 * C loaded words in registers
+constexpr int LK_RING = SCS_LK_RING;         // stream rows a lane has requested ahead of the one it is adding
 
 // 16-bit code of an entry: (byte offset of the lane's first chunk inside the tile) >> 2, i.e. row * ROWB / 4 with the
 // lane's chunk rotation (l mod C) already XORed in by the build; chunk step j reads at ((code << 2) ^ (j << 4))
@@ -100,68 +106,140 @@ k_estep_lk(const LkStreamView s, const uint64_t* __restrict__ Xq, int64_t xq_str
         x0 = seg_end;
         if (wa >= wb) continue;
 
-        int64_t tend = min(__ldg(s.task_row + k + 1), wb);          // where the lanes' current units end (or this warp's share does)
+        // stream rows are counted from the start of this warp's share
+        const int nrow = (int)(wb - wa);
+        int stop = (int)(min(__ldg(s.task_row + k + 1), wb) - wa);    // where the lanes' current units end (or the share does)
         int cell = __ldg(s.task_cell + (int64_t)k * 32 + lane);
         // the next task's end and cells are fetched a task ahead
-        int64_t tend_n = __ldg(s.task_row + min(k + 2, kt1));
+        int stop_n = (int)(min(__ldg(s.task_row + min(k + 2, kt1)), wb) - wa);
         int cell_n = (k + 1 < kt1) ? __ldg(s.task_cell + (int64_t)(k + 1) * 32 + lane) : -1;
 
         uint64_t a[C], b[C], pp[C];
 #pragma unroll
         for (int j = 0; j < C; ++j) a[j] = b[j] = pp[j] = 0ull;
+        // Add the lanes' sums to the totals of their cells.  A RED of 32 lanes to 32 different cells is 32 passes of the memory
+        // pipe (the same pipe the table reads need: nine such REDs per unit cost 18 us per E-step at config 3), so the sums are
+        // first transposed inside each group of 8 lanes (butterfly of shuffles: lane i ends up with slot i of each of the 8
+        // cells): then one RED covers 8 consecutive words of 4 cells, 4..8 lines instead of 32.  Slot 2j (+1) of a lane is the
+        // first (second) value of the chunk it read at step j, i.e. chunk j ^ rot of the row.
         auto flush = [&]() {
-            uint64_t x = 0ull;
+#ifdef SCS_LK_NO_RED     // (diagnostic build: what the kernel costs without its atomics; the results are wrong)
+            const bool live = cell == -2;
+#else
+            const bool live = cell >= 0;
+#endif
+            uint64_t x = 0ull, R[2 * C];
 #pragma unroll
             for (int j = 0; j < C; ++j) {
                 const int c = j ^ rot;                     // the chunk this lane read at step j
                 const uint64_t pa = pp[j] & 0xffffffull, pb = pp[j] >> 24;
-                const uint64_t va = a[j] - (pa << 56), vb = b[j] - (pb << 56);   // the byte pair rode on top (mod 2^64)
+                R[2 * j] = a[j] - (pa << 56);              // the byte pair rode on top (mod 2^64)
+                R[2 * j + 1] = b[j] - (pb << 56);
                 if (c < 4) x += (pa << (16 * c)) + (pb << (16 * c + 8));
-                if (cell >= 0) {
-                    SCS_ASSERT((int64_t)cell * KP + 2 * c + 1 < lq_stride || 2 * c >= K);
-                    if (2 * c < K && va) atomicAdd(Lq + (int64_t)cell * KP + 2 * c, (unsigned long long)va);
-                    if (2 * c + 1 < K && vb) atomicAdd(Lq + (int64_t)cell * KP + 2 * c + 1, (unsigned long long)vb);
-                }
                 a[j] = b[j] = pp[j] = 0ull;
             }
             // every lane holds all chunks of its rows, so the whole extra value is here
-            if (cell >= 0 && 2 * C < K && x) atomicAdd(Lq + (int64_t)cell * KP + 2 * C, (unsigned long long)x);
+            if (live && 2 * C < K && x) atomicAdd(Lq + (int64_t)cell * KP + 2 * C, (unsigned long long)x);
+            const int oi = lane & 7;
+#pragma unroll
+            for (int h = 0; h < 2 * C / 8; ++h) {
+#pragma unroll
+                for (int d = 4; d; d >>= 1) {
+                    const bool up = (oi & d) != 0;
+#pragma unroll
+                    for (int sl = 0; sl < 8; ++sl) {
+                        if (sl & d) continue;
+                        uint64_t& lo = R[8 * h + sl];
+                        uint64_t& hi = R[8 * h + (sl | d)];
+                        const uint64_t send = up ? lo : hi;
+                        const uint64_t recv = __shfl_xor_sync(0xffffffffu, send, d);
+                        if (up) lo = recv; else hi = recv;
+                    }
+                }
+            }
+#pragma unroll
+            for (int c8 = 0; c8 < 8; ++c8) {               // octet lane c8's cell; this lane holds its slots oi (+ 8 h)
+                const int cell_c = __shfl_sync(0xffffffffu, cell, (lane & ~7) | c8);
+                const int rot_c = c8 & (C - 1);
+#pragma unroll
+                for (int h = 0; h < 2 * C / 8; ++h) {
+                    const int slot = oi + 8 * h;
+                    const int v = 2 * ((slot >> 1) ^ rot_c) + (slot & 1);
+                    const uint64_t val = R[8 * h + c8];
+#ifdef SCS_LK_NO_RED
+                    if (cell_c == -2 && v < K && val) atomicAdd(Lq + (int64_t)cell_c * KP + v, (unsigned long long)val);
+#else
+                    SCS_ASSERT(cell_c < 0 || (int64_t)cell_c * KP + v < lq_stride || v >= K);
+                    if (cell_c >= 0 && v < K && val) atomicAdd(Lq + (int64_t)cell_c * KP + v, (unsigned long long)val);
+#endif
+                }
+            }
         };
 
+        // the two codes of one stream word: 2 * C LDS.128, integer adds
+        auto add_codes = [&](uint32_t a0, uint32_t a1) {
+            uint4 v0[C], v1[C];
+#pragma unroll
+            for (int j = 0; j < C; ++j) v0[j] = lds_u32x4(a0 ^ (uint32_t)(j << 4));
+#pragma unroll
+            for (int j = 0; j < C; ++j) v1[j] = lds_u32x4(a1 ^ (uint32_t)(j << 4));
+#pragma unroll
+            for (int j = 0; j < C; ++j) {
+                a[j] += ((uint64_t)v0[j].x | ((uint64_t)v0[j].y << 32)) + ((uint64_t)v1[j].x | ((uint64_t)v1[j].y << 32));
+                b[j] += ((uint64_t)v0[j].z | ((uint64_t)v0[j].w << 32)) + ((uint64_t)v1[j].z | ((uint64_t)v1[j].w << 32));
+                pp[j] += (uint64_t)q_pieces(v0[j].y, v0[j].w) + (uint64_t)q_pieces(v1[j].y, v1[j].w);
+            }
+        };
+        auto addr0 = [&](uint32_t w) { return smem_base + ((w & 0xffffu) << 2); };
+        auto addr1 = [&](uint32_t w) { return smem_base + ((w >> 14) & 0x3fffcu); };
+        auto add_row = [&](uint32_t w) {
+            SCS_ASSERT(((w & 0xffffu) << 2) < (uint32_t)(TR + 2) * ROWB && ((w >> 14) & 0x3fffcu) < (uint32_t)(TR + 2) * ROWB);
+            add_codes(addr0(w), addr1(w));
+        };
+        // A lane keeps the words of LK_RING rows in registers, row y (counted from the share's start) in ring[y % LK_RING], each
+        // requested LK_RING rows before it is used.  The requests are unconditional -- the stream ends in 2 * LK_RING rows of
+        // slack -- and land in fixed registers: nothing is ever moved while in flight.  (A predicated request made the compiler
+        // load into a temporary and MOVE it into the ring at once: the kernel then sat in long-scoreboard stalls, 123 us.)
+        auto boundary = [&](int x) {                     // the 32 units end here, or this warp's share does
+            flush();
+            ++k;
+            cell = cell_n;
+            stop = stop_n;
+            if (x < nrow) {
+                stop_n = (int)(min(__ldg(s.task_row + min(k + 2, kt1)), wb) - wa);
+                cell_n = (k + 1 < kt1) ? __ldg(s.task_cell + (int64_t)(k + 1) * 32 + lane) : -1;
+            }
+        };
         const uint32_t* wp = s.words + wa * 32 + lane;
         uint32_t ring[LK_RING];
 #pragma unroll
-        for (int i = 0; i < LK_RING; ++i) ring[i] = (wa + i < wb) ? __ldcs(wp + (int64_t)i * 32) : 0u;
-        for (int64_t x = wa; x < wb; x += LK_RING, wp += LK_RING * 32) {
+        for (int i = 0; i < LK_RING; ++i) ring[i] = __ldcs(wp + i * 32);
+        int x = 0;                                       // next row to add
+        for (int xb = 0; xb < nrow; xb += LK_RING, wp += LK_RING * 32) {
+            if (stop >= xb + LK_RING) {                  // the block lies inside the current piece
 #pragma unroll
-            for (int i = 0; i < LK_RING; ++i) {
-                if (x + i < wb) {                          // (warp-uniform)
-                    const uint32_t w = ring[i];
-                    if (x + i + LK_RING < wb) ring[i] = __ldcs(wp + (int64_t)(i + LK_RING) * 32);
-                    const uint32_t a0 = smem_base + ((w & 0xffffu) << 2), a1 = smem_base + ((w >> 14) & 0x3fffcu);
-                    SCS_ASSERT(((w & 0xffffu) << 2) < (uint32_t)(TR + 2) * ROWB && ((w >> 14) & 0x3fffcu) < (uint32_t)(TR + 2) * ROWB);
-                    uint4 v0[C], v1[C];
-#pragma unroll
-                    for (int j = 0; j < C; ++j) v0[j] = lds_u32x4(a0 ^ (uint32_t)(j << 4));
-#pragma unroll
-                    for (int j = 0; j < C; ++j) v1[j] = lds_u32x4(a1 ^ (uint32_t)(j << 4));
-#pragma unroll
-                    for (int j = 0; j < C; ++j) {
-                        a[j] += ((uint64_t)v0[j].x | ((uint64_t)v0[j].y << 32)) + ((uint64_t)v1[j].x | ((uint64_t)v1[j].y << 32));
-                        b[j] += ((uint64_t)v0[j].z | ((uint64_t)v0[j].w << 32)) + ((uint64_t)v1[j].z | ((uint64_t)v1[j].w << 32));
-                        pp[j] += (uint64_t)q_pieces(v0[j].y, v0[j].w) + (uint64_t)q_pieces(v1[j].y, v1[j].w);
-                    }
-                    if (x + i + 1 == tend) {               // (warp-uniform) the 32 units end here, or this warp's share does
-                        flush();
-                        ++k;
-                        cell = cell_n;
-                        tend = min(tend_n, wb);
-                        if (x + i + 1 < wb) {
-                            tend_n = __ldg(s.task_row + min(k + 2, kt1));
-                            cell_n = (k + 1 < kt1) ? __ldg(s.task_cell + (int64_t)(k + 1) * 32 + lane) : -1;
-                        }
-                    }
+                for (int i = 0; i < LK_RING; ++i) {
+                    // the word's two addresses are taken out first and named as inputs of the request, so that the request can
+                    // land in the register the word leaves (otherwise the ring is copied at the loop's end -- while in flight)
+                    const uint32_t a0 = addr0(ring[i]), a1 = addr1(ring[i]);
+                    SCS_ASSERT(a0 - smem_base < (uint32_t)(TR + 2) * ROWB && a1 - smem_base < (uint32_t)(TR + 2) * ROWB);
+                    asm volatile("ld.global.cs.u32 %0, [%1];" : "=r"(ring[i]) : "l"(wp + (i + LK_RING) * 32), "r"(a0), "r"(a1));
+                    add_codes(a0, a1);
                 }
+                x = xb + LK_RING;
+                if (x == stop) boundary(x);
+            } else {                                     // pieces end inside the block: rows [x, hi) at a time
+                const int bend = min(xb + LK_RING, nrow);
+                while (x < bend) {
+                    const int hi = min(stop, bend);
+#pragma unroll
+                    for (int i = 0; i < LK_RING; ++i)
+                        if (xb + i >= x && xb + i < hi) add_row(ring[i]);      // (warp-uniform)
+                    x = hi;
+                    if (x == stop) boundary(x);
+                }
+#pragma unroll
+                for (int i = 0; i < LK_RING; ++i) ring[i] = __ldcs(wp + (i + LK_RING) * 32);
             }
         }
     }
