@@ -128,9 +128,16 @@ int launch_spmm_tiled(scs_ctx* ctx, int kind, int KP, int R, const double* X, in
 
 // Fixed-point E-step (estep_q.cuh): tile-major stream with inline counts, built on first use per row width.
 // Returns the lanes per row (4 / 8) when this pool and K can use it, else 0.
-// The lock-step form (estep_lk.cuh: a lane per entry, integer totals by RED, no combine kernel) is the default; SCS_Q_GROUPS=1
-// selects the row-group form (estep_q.cuh: a group of lanes per entry, per-unit sums + k_combine_q) for A/B measurements.
-static bool lk_wanted() { return std::getenv("SCS_Q_GROUPS") == nullptr; }
+// Two forms of the fixed-point E-step.  Lock-step (estep_lk.cuh: a lane per entry, integer totals by RED, no combine kernel) is
+// the default for 64-byte rows (K <= 9): 84 us against 112 us at config 3.  For 128-byte rows (K <= 17) the row-group form
+// (estep_q.cuh: a group of lanes per entry, per-unit sums + k_combine_q) stays the default: measured on a config-4 shard
+// (25k cells, 67 table tiles, 44-code units) lock-step takes 509 us against 492 us -- its flush (two 8 x 8 transposes, 17 REDs)
+// comes round every 22 stream rows there.  SCS_Q_GROUPS=1 / SCS_Q_LOCKSTEP=1 force one form for every width (A/B measurements).
+static bool lk_wanted(int lanes) {
+    if (std::getenv("SCS_Q_GROUPS")) return false;
+    if (std::getenv("SCS_Q_LOCKSTEP")) return true;
+    return lanes == 4;
+}
 
 static int q_prepare(scs_ctx* ctx, int K) {
     if (ctx->variant != 0 || std::getenv("SCS_NO_Q")) return 0;
@@ -141,7 +148,7 @@ static int q_prepare(scs_ctx* ctx, int K) {
     const int ctas = ctx->sm_count > 0 ? ctx->sm_count : 148;
     const int ngroups = (TILED_THREADS / 32) * (32 / lanes);
     const int TR = q_tile_rows(lanes, ctx->E.xrows);
-    if (lk_wanted()) {
+    if (lk_wanted(lanes)) {
         if (ctx->LK.lanes != lanes || ctx->LK.TR != TR || ctx->LK.ncta != ctas || !ctx->LK.words) {
             int ok = 0, F = 0;
             if (build_lockstep(ctx, ctx->E, ctx->LK, lanes, TR, ctas, &F, &ok)) return -1;
@@ -176,8 +183,8 @@ static int launch_estep_lk(scs_ctx* ctx, const int32_t* done) {
     v.ntiles = t.ntiles; v.TR = t.TR; v.xrows = ctx->E.xrows;
     dim3 grid((unsigned)t.ncta, (unsigned)em.R);
     const int64_t xq_stride = 2 * ctx->V * 2 * lanes;
-    if (lanes == 4) k_estep_lk<4><<<grid, LK_THREADS, smem, ctx->stream>>>(v, em.Tq, xq_stride, em.Lq, ctx->N * em.KP, em.K, em.KP, done, em.qbad);
-    else k_estep_lk<8><<<grid, LK_THREADS, smem, ctx->stream>>>(v, em.Tq, xq_stride, em.Lq, ctx->N * em.KP, em.K, em.KP, done, em.qbad);
+    if (lanes == 4) k_estep_lk<4><<<grid, lk_threads(4), smem, ctx->stream>>>(v, em.Tq, xq_stride, em.Lq, ctx->N * em.KP, em.K, em.KP, done, em.qbad);
+    else k_estep_lk<8><<<grid, lk_threads(8), smem, ctx->stream>>>(v, em.Tq, xq_stride, em.Lq, ctx->N * em.KP, em.K, em.KP, done, em.qbad);
     ctx->launches += 1;
     SCS_CUDA(cudaGetLastError());
     return 0;
@@ -521,7 +528,7 @@ int scs_em_footprint(scs_ctx* ctx, int K, int64_t out[2]) {
     if (lanes) {
         const int64_t ntq = (2 * V + q_tile_rows(lanes, 2 * V) - 1) / q_tile_rows(lanes, 2 * V);
         // fixed-point table; integer totals (lock-step form) or per-unit sums (row-group form)
-        b += 2 * V * 2 * lanes * 8 + (lk_wanted() ? N * KP * 8 : ntq * N * q_part_words(lanes) * 8);
+        b += 2 * V * 2 * lanes * 8 + (lk_wanted(lanes) ? N * KP * 8 : ntq * N * q_part_words(lanes) * 8);
     }
     const int64_t nte = (2 * V + tile_rows_for((int)KP, 2 * V) - 1) / tile_rows_for((int)KP, 2 * V);
     const int64_t ntm = (N + tile_rows_for((int)KP, N) - 1) / tile_rows_for((int)KP, N);
@@ -575,7 +582,7 @@ int scs_em_begin(scs_ctx* ctx, int R, int K, const double* P0, int max_iter) {
             SCS_TRY(dev_alloc(ctx, &em.Tq, (int64_t)R * 2 * V * 2 * lanes));
             SCS_TRY(dev_alloc(ctx, &em.qbad, 2 * R));   // [R] flags, [R] their staging inside k_finalize
             SCS_CUDA(cudaMemsetAsync(em.qbad, 0, (size_t)R * 8, ctx->stream));
-            if (lk_wanted()) {
+            if (lk_wanted(lanes)) {
                 SCS_TRY(dev_alloc(ctx, &em.Lq, (int64_t)R * N * em.KP));
                 SCS_CUDA(cudaMemsetAsync(em.Lq, 0, (size_t)R * N * em.KP * 8, ctx->stream));
             }

@@ -29,7 +29,12 @@ namespace scs {
 #ifndef SCS_LK_RING
 #define SCS_LK_RING 8
 #endif
-constexpr int LK_THREADS = SCS_LK_THREADS;   // 16 warps: a lane keeps 3 * C 64-bit sums and up to 8 * C loaded words in registers
+// threads per CTA: a lane keeps 3 * C 64-bit sums, the ring and up to 8 loaded 16-byte chunks in registers -- 16 warps of 128
+// registers for 64-byte rows, 12 warps of 168 for 128-byte rows (at 128 the ring of the wide kernel spilled while in flight)
+#ifndef SCS_LK_THREADS8
+#define SCS_LK_THREADS8 384
+#endif
+__host__ __device__ constexpr int lk_threads(int C) { return C <= 4 ? SCS_LK_THREADS : SCS_LK_THREADS8; }
 constexpr int LK_RING = SCS_LK_RING;         // stream rows a lane has requested ahead of the one it is adding
 
 // 16-bit code of an entry: (byte offset of the lane's first chunk inside the tile) >> 2, i.e. row * ROWB / 4 with the
@@ -51,10 +56,12 @@ struct LkStreamView {
 };
 
 template <int C>
-__global__ void __launch_bounds__(LK_THREADS, 1)
+__global__ void __launch_bounds__(lk_threads(C), 1)
 k_estep_lk(const LkStreamView s, const uint64_t* __restrict__ Xq, int64_t xq_stride, unsigned long long* __restrict__ Lq, int64_t lq_stride,
            int K, int KP, const int32_t* __restrict__ done, const int32_t* __restrict__ qbad) {
-    constexpr int ROWB = C * 16;
+    // rows a lane keeps requested ahead = rows per unrolled block: 8 for 64-byte rows; 4 for 128-byte rows, whose block of 8
+    // (1200 instructions) ran out of the instruction cache: `no_instructions` was the top stall of the first capture
+    constexpr int ROWB = C * 16, RING = C <= 4 ? LK_RING : LK_RING / 2;
     extern __shared__ __align__(128) unsigned char smem[];
     const int TR = s.TR;
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + (((size_t)(TR + 2) * ROWB + 127) & ~(size_t)127));
@@ -178,16 +185,32 @@ k_estep_lk(const LkStreamView s, const uint64_t* __restrict__ Xq, int64_t xq_str
 
         // the two codes of one stream word: 2 * C LDS.128, integer adds
         auto add_codes = [&](uint32_t a0, uint32_t a1) {
-            uint4 v0[C], v1[C];
+            if constexpr (C <= 4) {                      // both rows requested before the adds: 8 LDS.128 in flight, three-input adds
+                uint4 v0[C], v1[C];
 #pragma unroll
-            for (int j = 0; j < C; ++j) v0[j] = lds_u32x4(a0 ^ (uint32_t)(j << 4));
+                for (int j = 0; j < C; ++j) v0[j] = lds_u32x4(a0 ^ (uint32_t)(j << 4));
 #pragma unroll
-            for (int j = 0; j < C; ++j) v1[j] = lds_u32x4(a1 ^ (uint32_t)(j << 4));
+                for (int j = 0; j < C; ++j) v1[j] = lds_u32x4(a1 ^ (uint32_t)(j << 4));
 #pragma unroll
-            for (int j = 0; j < C; ++j) {
-                a[j] += ((uint64_t)v0[j].x | ((uint64_t)v0[j].y << 32)) + ((uint64_t)v1[j].x | ((uint64_t)v1[j].y << 32));
-                b[j] += ((uint64_t)v0[j].z | ((uint64_t)v0[j].w << 32)) + ((uint64_t)v1[j].z | ((uint64_t)v1[j].w << 32));
-                pp[j] += (uint64_t)q_pieces(v0[j].y, v0[j].w) + (uint64_t)q_pieces(v1[j].y, v1[j].w);
+                for (int j = 0; j < C; ++j) {
+                    a[j] += ((uint64_t)v0[j].x | ((uint64_t)v0[j].y << 32)) + ((uint64_t)v1[j].x | ((uint64_t)v1[j].y << 32));
+                    b[j] += ((uint64_t)v0[j].z | ((uint64_t)v0[j].w << 32)) + ((uint64_t)v1[j].z | ((uint64_t)v1[j].w << 32));
+                    pp[j] += (uint64_t)q_pieces(v0[j].y, v0[j].w) + (uint64_t)q_pieces(v1[j].y, v1[j].w);
+                }
+            } else {                                     // a 128-byte row is 8 LDS.128 by itself: one row at a time (registers)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const uint32_t ah = h ? a1 : a0;
+                    uint4 v[C];
+#pragma unroll
+                    for (int j = 0; j < C; ++j) v[j] = lds_u32x4(ah ^ (uint32_t)(j << 4));
+#pragma unroll
+                    for (int j = 0; j < C; ++j) {
+                        a[j] += (uint64_t)v[j].x | ((uint64_t)v[j].y << 32);
+                        b[j] += (uint64_t)v[j].z | ((uint64_t)v[j].w << 32);
+                        pp[j] += (uint64_t)q_pieces(v[j].y, v[j].w);
+                    }
+                }
             }
         };
         auto addr0 = [&](uint32_t w) { return smem_base + ((w & 0xffffu) << 2); };
@@ -196,8 +219,8 @@ k_estep_lk(const LkStreamView s, const uint64_t* __restrict__ Xq, int64_t xq_str
             SCS_ASSERT(((w & 0xffffu) << 2) < (uint32_t)(TR + 2) * ROWB && ((w >> 14) & 0x3fffcu) < (uint32_t)(TR + 2) * ROWB);
             add_codes(addr0(w), addr1(w));
         };
-        // A lane keeps the words of LK_RING rows in registers, row y (counted from the share's start) in ring[y % LK_RING], each
-        // requested LK_RING rows before it is used.  The requests are unconditional -- the stream ends in 2 * LK_RING rows of
+        // A lane keeps the words of RING rows in registers, row y (counted from the share's start) in ring[y % RING], each
+        // requested RING rows before it is used.  The requests are unconditional -- the stream ends in 2 * LK_RING rows of
         // slack -- and land in fixed registers: nothing is ever moved while in flight.  (A predicated request made the compiler
         // load into a temporary and MOVE it into the ring at once: the kernel then sat in long-scoreboard stalls, 123 us.)
         auto boundary = [&](int x) {                     // the 32 units end here, or this warp's share does
@@ -211,35 +234,35 @@ k_estep_lk(const LkStreamView s, const uint64_t* __restrict__ Xq, int64_t xq_str
             }
         };
         const uint32_t* wp = s.words + wa * 32 + lane;
-        uint32_t ring[LK_RING];
+        uint32_t ring[RING];
 #pragma unroll
-        for (int i = 0; i < LK_RING; ++i) ring[i] = __ldcs(wp + i * 32);
+        for (int i = 0; i < RING; ++i) ring[i] = __ldcs(wp + i * 32);
         int x = 0;                                       // next row to add
-        for (int xb = 0; xb < nrow; xb += LK_RING, wp += LK_RING * 32) {
-            if (stop >= xb + LK_RING) {                  // the block lies inside the current piece
+        for (int xb = 0; xb < nrow; xb += RING, wp += RING * 32) {
+            if (stop >= xb + RING) {                  // the block lies inside the current piece
 #pragma unroll
-                for (int i = 0; i < LK_RING; ++i) {
+                for (int i = 0; i < RING; ++i) {
                     // the word's two addresses are taken out first and named as inputs of the request, so that the request can
                     // land in the register the word leaves (otherwise the ring is copied at the loop's end -- while in flight)
                     const uint32_t a0 = addr0(ring[i]), a1 = addr1(ring[i]);
                     SCS_ASSERT(a0 - smem_base < (uint32_t)(TR + 2) * ROWB && a1 - smem_base < (uint32_t)(TR + 2) * ROWB);
-                    asm volatile("ld.global.cs.u32 %0, [%1];" : "=r"(ring[i]) : "l"(wp + (i + LK_RING) * 32), "r"(a0), "r"(a1));
+                    asm volatile("ld.global.cs.u32 %0, [%1];" : "=r"(ring[i]) : "l"(wp + (i + RING) * 32), "r"(a0), "r"(a1));
                     add_codes(a0, a1);
                 }
-                x = xb + LK_RING;
+                x = xb + RING;
                 if (x == stop) boundary(x);
             } else {                                     // pieces end inside the block: rows [x, hi) at a time
-                const int bend = min(xb + LK_RING, nrow);
+                const int bend = min(xb + RING, nrow);
                 while (x < bend) {
                     const int hi = min(stop, bend);
 #pragma unroll
-                    for (int i = 0; i < LK_RING; ++i)
+                    for (int i = 0; i < RING; ++i)
                         if (xb + i >= x && xb + i < hi) add_row(ring[i]);      // (warp-uniform)
                     x = hi;
                     if (x == stop) boundary(x);
                 }
 #pragma unroll
-                for (int i = 0; i < LK_RING; ++i) ring[i] = __ldcs(wp + (i + LK_RING) * 32);
+                for (int i = 0; i < RING; ++i) ring[i] = __ldcs(wp + (i + RING) * 32);
             }
         }
     }

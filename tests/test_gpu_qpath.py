@@ -134,10 +134,9 @@ def test_lockstep_form_equals_row_group_form_bitwise(K, V, N, dens, E, monkeypat
     P = np.stack([_random_P(V, K, 1), _random_P(V, K, 2)])
     out = {}
     for form in ("lock-step", "row groups"):
-        if form == "row groups":
-            monkeypatch.setenv("SCS_Q_GROUPS", "1")
-        else:
-            monkeypatch.delenv("SCS_Q_GROUPS", raising=False)
+        monkeypatch.delenv("SCS_Q_GROUPS", raising=False)
+        monkeypatch.delenv("SCS_Q_LOCKSTEP", raising=False)
+        monkeypatch.setenv("SCS_Q_GROUPS" if form == "row groups" else "SCS_Q_LOCKSTEP", "1")   # (the default depends on the row width)
         with E(ref_s, alt_s) as eng:
             eng.em_begin(P)
             info = eng.em_info()
