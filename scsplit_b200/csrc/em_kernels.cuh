@@ -131,9 +131,9 @@ constexpr uint32_t SPARSE_NOP = 0x3f800001u;         // no entry (a lane past th
 // 1 - weight fits the float format.  Every lane of the group returns the word.
 template <int GL>
 __device__ __forceinline__ uint32_t sparsify_group(double wi, int i, int K) {
-    const int lane = threadIdx.x & 31;
-    const uint32_t gmask = (GL == 32 ? 0xffffffffu : ((1u << GL) - 1u) << (lane & ~(GL - 1)));
-    const uint32_t live = (K >= 32 ? 0xffffffffu : ((1u << K) - 1u) << (lane & ~(GL - 1))) & gmask;
+    const int lane = threadIdx.x & 31, base = (lane / GL) * GL;        // (lanes beyond the last whole group get an empty mask)
+    const uint32_t gmask = (GL == 32 ? 0xffffffffu : ((1u << GL) - 1u) << base);
+    const uint32_t live = (K >= 32 ? 0xffffffffu : ((1u << K) - 1u) << base) & gmask;
     const bool big = wi >= 0.5 && wi <= 1.5;
     const uint32_t bigm = __ballot_sync(0xffffffffu, big && i < K) & gmask;
     const uint32_t tinym = __ballot_sync(0xffffffffu, wi < SPARSE_TINY && i < K) & gmask;
@@ -148,15 +148,17 @@ __device__ __forceinline__ uint32_t sparsify_group(double wi, int i, int K) {
 }
 
 // Block statistics of k_bayes / k_colsum_partial: lane i of every cell group has accumulated column i's mass in `mass`, lane
-// 0 of the group the LL terms and the dense-row count.  Fixed order: the two groups of a warp (GL = 16), then the warps.
+// 0 of the group the LL terms and the dense-row count.  Fixed order: the groups of a warp, then the warps.
 template <int KP, int GL>
 __device__ __forceinline__ void block_stats_store(double mass, double ll, double dense, double* smem /*[warps][KP+2]*/,
                                                   double* out /*[KP+2]*/) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, i = lane & (GL - 1);
-    if (GL == 16) {
-        mass += __shfl_xor_sync(0xffffffffu, mass, 16);
-        ll += __shfl_xor_sync(0xffffffffu, ll, 16);
-        dense += __shfl_xor_sync(0xffffffffu, dense, 16);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, i = lane % GL;
+    const double mass0 = mass, ll0 = ll, dense0 = dense;
+#pragma unroll
+    for (int q = 1; q < 32 / GL; ++q) {              // the groups of the warp, in order, into its first group
+        mass += __shfl_down_sync(0xffffffffu, mass0, q * GL);
+        ll += __shfl_down_sync(0xffffffffu, ll0, q * GL);
+        dense += __shfl_down_sync(0xffffffffu, dense0, q * GL);
     }
     if (lane < GL && i < KP) smem[warp * (KP + 2) + i] = mass;
     if (lane == 0) {
@@ -218,11 +220,15 @@ __device__ __forceinline__ double exp2_bf(double x) {
 
 template <int KP>
 struct BayesCfg {
-    static constexpr int GL = KP <= 16 ? 16 : 32;     // lanes per cell
+    // lanes per cell.  The kernel is bound by the fp64 pipe (ten 2^x per lane and cell at K = 9; B200 issues 64 fp64 lanes per
+    // clock and SM), and a warp instruction costs the same whatever lanes are idle: K = 9 in groups of 16 wasted 7 lanes of
+    // 16, in groups of 10 (three cells per warp, lanes 30 and 31 idle) 2 of 32.
+    static constexpr int GL = KP <= 8 ? 8 : KP <= 10 ? 10 : KP <= 16 ? 16 : 32;
+    static constexpr int CPW = 32 / GL;               // cells per warp
     static constexpr int THREADS = 1024;
-    static constexpr int CPB = THREADS / GL;          // cells per block
+    static constexpr int CPB = (THREADS / 32) * CPW;  // cells per block and pass
 };
-inline int bayes_cells_per_block(int KP) { return KP <= 16 ? 64 : 32; }
+inline int bayes_cells_per_block(int KP) { return 32 * (32 / (KP <= 8 ? 8 : KP <= 10 ? 10 : KP <= 16 ? 16 : 32)); }
 
 // Block b of nblk owns the contiguous cells [N*b/nblk, N*(b+1)/nblk) and walks them CPB at a time (whole warps without
 // cells skip the pass), so every block does the same work whatever N is and the grid can be sized to the SM count.
@@ -280,14 +286,14 @@ __global__ void __launch_bounds__(1024) k_bayes(int64_t N, int K, const LSource 
     if (done && done[r]) return;
     __shared__ double s_red[32 * (KP + 2)];
     __shared__ int s_last;
-    const int i = threadIdx.x & (C::GL - 1);
+    const int grp = (threadIdx.x & 31) / C::GL, i = (threadIdx.x & 31) - grp * C::GL, gbase = grp * C::GL;
     const double si = i < K ? lps[(int64_t)r * KP + i] : 0.0;
     const int64_t c_lo = bayes_cell_lo(N, blockIdx.x, nblk), c_hi = bayes_cell_lo(N, blockIdx.x + 1, nblk);
     const double qnan = __longlong_as_double(0x7ff8000000000000LL);
     double mass = 0.0, llsum = 0.0, dense = 0.0;
-    for (int64_t c0 = c_lo + (threadIdx.x >> 5) * (32 / C::GL); c0 < c_hi; c0 += C::CPB) {   // warp-uniform
-        const int64_t c = c0 + (threadIdx.x & 31) / C::GL;
-        const bool cell = c < c_hi, live = cell && i < K;
+    for (int64_t c0 = c_lo + (threadIdx.x >> 5) * C::CPW; c0 < c_hi; c0 += C::CPB) {   // warp-uniform
+        const int64_t c = c0 + grp;
+        const bool cell = grp < C::CPW && c < c_hi, live = cell && i < K;       // (lanes beyond the last whole group idle)
         double Li;
         if (src.qbad && src.qbad[r]) {
             Li = bayes_row_from_table<KP>(src, r, c, cell, i, K);
@@ -318,21 +324,23 @@ __global__ void __launch_bounds__(1024) k_bayes(int64_t N, int K, const LSource 
         // a chain.  With the loop bound K at run time the kernel evaluated them one after the other.)
 #pragma unroll
         for (int j = 0; j < KP; ++j) {                               // j ascending, left to right, as the reference adds
-            const double tj = __shfl_sync(0xffffffffu, ti, j, C::GL);
+            const double tj = __shfl_sync(0xffffffffu, ti, min(gbase + j, 31));
             const double ej = exp2_bf((tj - Li) - si);
             if (j < K) denom += ej;
         }
         const double wi = live ? 1.0 / denom : 0.0;
         if (cell && i < KP) W[((int64_t)r * N + c) * KP + i] = wi;
         // total log-likelihood term: skipna max and skipna sum over the states.  Lanes beyond K carry NaN into the max
-        // (fmax drops NaN operands, and an all-NaN row stays NaN) and 0 into the sum; both run as xor trees.
-        double m = live ? Li : qnan;
+        // (fmax drops NaN operands, and an all-NaN row stays NaN) and 0 into the sum; every lane of the group gathers both.
+        const double mi = live ? Li : qnan;
+        double m = qnan;
 #pragma unroll
-        for (int o = C::GL / 2; o; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+        for (int j = 0; j < KP; ++j) m = fmax(m, __shfl_sync(0xffffffffu, mi, min(gbase + j, 31)));
         const double xi = exp2_bf((Li - m) + si);
-        double sum = (live && xi == xi) ? xi : 0.0;
+        const double xs = (live && xi == xi) ? xi : 0.0;
+        double sum = 0.0;
 #pragma unroll
-        for (int o = C::GL / 2; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        for (int j = 0; j < KP; ++j) sum += __shfl_sync(0xffffffffu, xs, min(gbase + j, 31));     // states ascending
         const uint32_t q = sparsify_group<C::GL>(wi, i, K);
         if (live && wi == wi) mass += wi;                            // column mass, NaN skipped (scSplit:198)
         if (cell && i == 0) {
@@ -368,12 +376,12 @@ __global__ void __launch_bounds__(1024) k_colsum_partial(int64_t N, int K, const
     using C = BayesCfg<KP>;
     const int r = blockIdx.y;
     __shared__ double s_red[32 * (KP + 2)];
-    const int i = threadIdx.x & (C::GL - 1);
+    const int grp = (threadIdx.x & 31) / C::GL, i = (threadIdx.x & 31) - grp * C::GL;
     const int64_t c_lo = bayes_cell_lo(N, blockIdx.x, nblk), c_hi = bayes_cell_lo(N, blockIdx.x + 1, nblk);
     double mass = 0.0, dense = 0.0;
-    for (int64_t c0 = c_lo + (threadIdx.x >> 5) * (32 / C::GL); c0 < c_hi; c0 += C::CPB) {   // warp-uniform
-        const int64_t c = c0 + (threadIdx.x & 31) / C::GL;
-        const bool cell = c < c_hi, live = cell && i < K;
+    for (int64_t c0 = c_lo + (threadIdx.x >> 5) * C::CPW; c0 < c_hi; c0 += C::CPB) {   // warp-uniform
+        const int64_t c = c0 + grp;
+        const bool cell = grp < C::CPW && c < c_hi, live = cell && i < K;
         const double wi = live ? W[((int64_t)r * N + c) * KP + i] : 0.0;
         const uint32_t q = sparsify_group<C::GL>(wi, i, K);
         if (live && wi == wi) mass += wi;

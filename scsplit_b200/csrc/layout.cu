@@ -723,6 +723,21 @@ int build_qtiled(scs_ctx* ctx, const Stream& s, TiledStream& t, int lanes, int T
     return 0;
 }
 
+// SCS_TRACE=1: host-side phase times of the layout build on stderr (each phase ends with a stream synchronise)
+struct PhaseTrace {
+    bool on;
+    cudaStream_t st;
+    std::chrono::steady_clock::time_point t0;
+    explicit PhaseTrace(cudaStream_t s) : on(std::getenv("SCS_TRACE") != nullptr), st(s), t0(std::chrono::steady_clock::now()) {}
+    void mark(const char* what) {
+        if (!on) return;
+        cudaStreamSynchronize(st);
+        auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[scs trace] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
+
 // ---- lock-step stream of the fixed-point E-step (estep_lk.cuh) ----------------------------------------------------
 // The units (cell, table tile) of a tile are sorted by length and dealt 32 at a time to tasks; a task's 32 units are read by
 // the 32 lanes of a warp side by side, so they are padded to one length.  For 64-byte rows the lanes l and l + 4 of a quarter
@@ -938,6 +953,7 @@ int build_lockstep(scs_ctx* ctx, const Stream& s, LockstepStream& t, int lanes, 
     const int64_t nunits = (int64_t)ntiles * s.nrows;
     SCS_CHECK(nunits < (1LL << 31) && ntiles < (1 << (LK_FIELD - 1)), "pool too large for the lock-step stream (%lld units)", (long long)nunits);
     Scratch tmps(st);
+    PhaseTrace trace(st);
     int32_t *d_ulo = nullptr, *d_uho = nullptr;
     int64_t *tptr = nullptr, *d_hv = nullptr;
     SCS_TRY(tmps.get(&d_ulo, nunits));
@@ -963,6 +979,7 @@ int build_lockstep(scs_ctx* ctx, const Stream& s, LockstepStream& t, int lanes, 
     SCS_CUDA(cudaStreamSynchronize(st));
     *F = (uint64_t)h_max < (1ull << 40) ? q_frac_bits(h_max) : 0;
     if (*F < Q_MIN_F) return 0;                          // cells too deep for a useful fraction: fp64 keeps the E-step
+    trace.mark("lk: unit counts + scan");
     uint16_t* tcode = nullptr;
     SCS_TRY(tmps.get(&tcode, total + 2));
     k_qtile_scatter<<<(unsigned)((s.nrows + 7) / 8), 256, 0, st>>>(s.nrows, ntiles, TR, s.lptr, s.lcode, s.hptr, s.hcode, s.hcnt, tptr, d_ulo, d_uho, tcode);
@@ -976,14 +993,19 @@ int build_lockstep(scs_ctx* ctx, const Stream& s, LockstepStream& t, int lanes, 
     SCS_TRY(tmps.get(&ue, nunits));
     SCS_TRY(tmps.get(&pair_u, 2 * nunits));
     SCS_TRY(tmps.get(&ps, ntiles + 1));
+    trace.mark("lk: scatter codes");
     k_lk_unit_keys<<<ugrid, 256, 0, st>>>(nunits, s.nrows, lanes, tptr, tcode, key, val, ue);
+    trace.mark("lk: unit keys");
     const int top = 2 * LK_FIELD + bits_for(ntiles + 1);  // (the key of an empty unit is all ones: it sorts behind every tile)
     SCS_TRY(lk_sort_pairs(st, tmps, key, key_s, val, val_s, nunits, 0, top));
+    trace.mark("lk: sort units");
     pkey = key; pval = val;                               // (the unsorted unit keys are not needed any more)
     SCS_TRY(tmps.get(&pkey_s, nunits));
     SCS_TRY(tmps.get(&pval_s, nunits));
     k_lk_pairs<<<ugrid, 256, 0, st>>>(nunits, lanes, key_s, val_s, ue, tptr, pkey, pval, pair_u);
+    trace.mark("lk: pairs");
     SCS_TRY(lk_sort_pairs(st, tmps, pkey, pkey_s, pval, pval_s, nunits, LK_FIELD, top));
+    trace.mark("lk: sort pairs");
     SCS_TRY(dev_alloc(ctx, &t.tile_task, ntiles + 1));
     k_lk_tiles<<<1, 256, 0, st>>>(ntiles, nunits, pkey_s, ps, t.tile_task);
     ctx->launches += 12;
@@ -1006,6 +1028,7 @@ int build_lockstep(scs_ctx* ctx, const Stream& s, LockstepStream& t, int lanes, 
         SCS_CUDA(cudaStreamSynchronize(st));
         ctx->launches += 3;
     }
+    trace.mark("lk: tasks");
     SCS_TRY(dev_alloc(ctx, &t.words, (nrows + 2 * LK_RING) * 32));     // (the kernel requests rows ahead without looking)
     SCS_CUDA(cudaMemsetAsync(t.words + nrows * 32, 0, (size_t)2 * LK_RING * 32 * 4, st));
     if (ntasks > 0) {
@@ -1014,6 +1037,7 @@ int build_lockstep(scs_ctx* ctx, const Stream& s, LockstepStream& t, int lanes, 
         else k_lk_emit<8><<<egrid, 256, 0, st>>>(ntasks, ntiles, s.nrows, TR, t.tile_task, ps, pval_s, pair_u, ue, tptr, tcode, t.task_row, t.task_cell, t.words);
         ctx->launches++;
     }
+    trace.mark("lk: emit");
     SCS_TRY(dev_alloc(ctx, &t.cta_row, ncta + 1));
     // (in stream rows of 64 codes; sweep at config 3, E-step sums: 95.2 us with no charge, 83.9 at 453, 82.8 at 1000, 84.8 at 2000, 88.0 at 3000)
     const char* tc_env = std::getenv("SCS_LK_TILE_COST");
@@ -1023,6 +1047,7 @@ int build_lockstep(scs_ctx* ctx, const Stream& s, LockstepStream& t, int lanes, 
     k_lk_xheavy<<<(unsigned)((s.nrows + 255) / 256), 256, 0, st>>>(s.nrows, s.hptr, s.hcnt, t.xheavy);
     ctx->launches += 2;
     SCS_CUDA(cudaGetLastError());
+    trace.mark("lk: plan + xheavy");
     t.lanes = lanes;
     t.TR = TR;
     t.ntiles = ntiles;
@@ -1032,21 +1057,6 @@ int build_lockstep(scs_ctx* ctx, const Stream& s, LockstepStream& t, int lanes, 
     *ok = 1;
     return 0;
 }
-
-// SCS_TRACE=1: host-side phase times of the layout build on stderr (each phase ends with a stream synchronise)
-struct PhaseTrace {
-    bool on;
-    cudaStream_t st;
-    std::chrono::steady_clock::time_point t0;
-    explicit PhaseTrace(cudaStream_t s) : on(std::getenv("SCS_TRACE") != nullptr), st(s), t0(std::chrono::steady_clock::now()) {}
-    void mark(const char* what) {
-        if (!on) return;
-        cudaStreamSynchronize(st);
-        auto t1 = std::chrono::steady_clock::now();
-        fprintf(stderr, "[scs trace] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
-        t0 = t1;
-    }
-};
 
 int build_layout(scs_ctx* ctx, const int64_t* ref_indptr, const int32_t* ref_indices, const void* ref_data,
                  const int64_t* alt_indptr, const int32_t* alt_indices, const void* alt_data, int data_bytes) {
