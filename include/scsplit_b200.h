@@ -106,7 +106,7 @@ int scs_em_status(scs_ctx* ctx, int32_t* iters, int32_t* converged, double* ll);
 /* how the E-step sums of the current EM state run: out[0] = lanes per fixed-point table row (4 or 8; 0 = the fp64 kernels do
  * the E-step), out[1] = fraction bits F of the fixed-point tables, out[2] = table tiles, out[3] = restarts whose table
  * currently does not fit the fixed-point format (their E-step runs in fp64), out[4] = form of the fixed-point E-step (0 = none,
- * 1 = a group of lanes per entry + combine kernel, 2 = lock-step: a lane per entry, integer totals by RED), out[5] = warp
+ * 1 = a group of lanes per entry + combine kernel, 2 = lock-step: a lane per entry, integer totals by RED, 3 = lock-step in two passes over two tables of 64-byte rows), out[5] = warp
  * tasks of the lock-step stream.  scSplit:175-178; DESIGN.md section 4. */
 int scs_em_info(scs_ctx* ctx, int64_t out[6]);
 int scs_em_get(scs_ctx* ctx, int restart, int what, double* out);

@@ -95,6 +95,7 @@ struct LockstepStream {
     int32_t* tile_task = nullptr;   // [ntiles + 1] first task of each tile
     int ncta = 0;
     int64_t* cta_row = nullptr;     // [ncta + 1] stream-row ranges of the CTAs (equal cost; a tile boundary inside a range is charged)
+    int32_t* cta_tile = nullptr;    // [ncta] tile of the first row of each range
     int32_t* xheavy = nullptr;      // [N] entries of each cell with count > Q_REP_MAX (k_bayes adds them in fp64)
 };
 
@@ -128,6 +129,9 @@ struct EmState {
     uint64_t* Tq = nullptr;     // [R][2V][2 * q_lanes] fixed-point copy of T (estep_q.cuh); nullptr = the E-step runs in fp64
     int32_t* qbad = nullptr;    // [R] the restart's table does not fit the fixed-point format: its E-step runs in fp64
     int q_lanes = 0, q_F = 0;
+    // lock-step E-step of a 16-value-wide table (K = 10..17): Tq is kept as TWO tables of 64-byte rows, [2][R][2V][8] -- values
+    // 0..8 (the ninth in byte pairs, as for K = 9) and values 9..16 -- and the kernel makes one pass over the stream per table
+    int q_split = 0;
     unsigned long long* Lq = nullptr;   // [R][N][KP] integer E-step totals of the lock-step kernel (estep_lk.cuh); k_bayes leaves them at zero
     int32_t* sat = nullptr;     // [R] latched: the restart's dense-row count has been at or below the saturation threshold
     uint32_t* hq = nullptr;     // [R][h_stride] packed (state, 1 - weight) of a saturated posterior row, or SPARSE_DENSE

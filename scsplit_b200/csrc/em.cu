@@ -129,15 +129,13 @@ int launch_spmm_tiled(scs_ctx* ctx, int kind, int KP, int R, const double* X, in
 // Fixed-point E-step (estep_q.cuh): tile-major stream with inline counts, built on first use per row width.
 // Returns the lanes per row (4 / 8) when this pool and K can use it, else 0.
 // Two forms of the fixed-point E-step.  Lock-step (estep_lk.cuh: a lane per entry, integer totals by RED, no combine kernel) is
-// the default for 64-byte rows (K <= 9): 84 us against 112 us at config 3.  For 128-byte rows (K <= 17) the row-group form
-// (estep_q.cuh: a group of lanes per entry, per-unit sums + k_combine_q) stays the default: measured on a config-4 shard
-// (25k cells, 67 table tiles, 44-code units) lock-step takes 509 us against 492 us -- its flush (two 8 x 8 transposes, 17 REDs)
-// comes round every 22 stream rows there.  SCS_Q_GROUPS=1 / SCS_Q_LOCKSTEP=1 force one form for every width (A/B measurements).
-static bool lk_wanted(int lanes) {
-    if (std::getenv("SCS_Q_GROUPS")) return false;
-    if (std::getenv("SCS_Q_LOCKSTEP")) return true;
-    return lanes == 4;
-}
+// the default: 84 us against 112 us at config 3 for the row-group form (estep_q.cuh: a group of lanes per entry, per-unit sums
+// + k_combine_q).  Tables of 10..17 values per row are read as two tables of 64-byte rows in two passes (EmState::q_split);
+// one pass over 128-byte rows (SCS_Q_WIDE=1) measured 509 us on a config-4 shard (25k cells, 67 table tiles, 44-code units: the
+// flush -- two 8 x 8 transposes, 17 REDs -- comes round every 22 stream rows), the row-group form 492 us.
+// SCS_Q_GROUPS=1 selects the row-group form for every width (A/B measurements).
+static bool lk_wanted(int) { return std::getenv("SCS_Q_GROUPS") == nullptr; }
+static bool lk_split(int lanes) { return lanes == 8 && std::getenv("SCS_Q_WIDE") == nullptr; }
 
 static int q_prepare(scs_ctx* ctx, int K) {
     if (ctx->variant != 0 || std::getenv("SCS_NO_Q")) return 0;
@@ -149,9 +147,11 @@ static int q_prepare(scs_ctx* ctx, int K) {
     const int ngroups = (TILED_THREADS / 32) * (32 / lanes);
     const int TR = q_tile_rows(lanes, ctx->E.xrows);
     if (lk_wanted(lanes)) {
-        if (ctx->LK.lanes != lanes || ctx->LK.TR != TR || ctx->LK.ncta != ctas || !ctx->LK.words) {
+        const int sl = lk_split(lanes) ? 4 : lanes;       // lanes (16-byte chunks) of the rows the stream addresses
+        const int STR = q_tile_rows(sl, ctx->E.xrows);
+        if (ctx->LK.lanes != sl || ctx->LK.TR != STR || ctx->LK.ncta != ctas || !ctx->LK.words) {
             int ok = 0, F = 0;
-            if (build_lockstep(ctx, ctx->E, ctx->LK, lanes, TR, ctas, &F, &ok)) return -1;
+            if (build_lockstep(ctx, ctx->E, ctx->LK, sl, STR, ctas, &F, &ok)) return -1;
             ctx->q_state[idx] = ok ? 1 : -1;
             if (!ok) return 0;
             ctx->q_F = F;
@@ -171,7 +171,7 @@ static int q_prepare(scs_ctx* ctx, int K) {
 static int launch_estep_lk(scs_ctx* ctx, const int32_t* done) {
     EmState& em = ctx->em;
     const LockstepStream& t = ctx->LK;
-    const int lanes = em.q_lanes;
+    const int lanes = t.lanes;                           // of the rows the stream addresses (4 when a wide table is split)
     const size_t smem = ((((size_t)(t.TR + 2) * lanes * 16) + 127) & ~(size_t)127) + 16;
     if (!(ctx->smem_attr_set[2] >> (26 + lanes / 8) & 1u)) {
         if (lanes == 4) SCS_CUDA(cudaFuncSetAttribute(k_estep_lk<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, Q_SMEM_BYTES));
@@ -179,13 +179,20 @@ static int launch_estep_lk(scs_ctx* ctx, const int32_t* done) {
         ctx->smem_attr_set[2] |= 1u << (26 + lanes / 8);
     }
     LkStreamView v;
-    v.words = t.words; v.task_row = t.task_row; v.task_cell = t.task_cell; v.tile_task = t.tile_task; v.cta_row = t.cta_row;
+    v.words = t.words; v.task_row = t.task_row; v.task_cell = t.task_cell; v.tile_task = t.tile_task; v.cta_row = t.cta_row; v.cta_tile = t.cta_tile;
     v.ntiles = t.ntiles; v.TR = t.TR; v.xrows = ctx->E.xrows;
     dim3 grid((unsigned)t.ncta, (unsigned)em.R);
-    const int64_t xq_stride = 2 * ctx->V * 2 * lanes;
-    if (lanes == 4) k_estep_lk<4><<<grid, lk_threads(4), smem, ctx->stream>>>(v, em.Tq, xq_stride, em.Lq, ctx->N * em.KP, em.K, em.KP, done, em.qbad);
-    else k_estep_lk<8><<<grid, lk_threads(8), smem, ctx->stream>>>(v, em.Tq, xq_stride, em.Lq, ctx->N * em.KP, em.K, em.KP, done, em.qbad);
-    ctx->launches += 1;
+    const int64_t xq_stride = 2 * ctx->V * 2 * lanes, lq_stride = ctx->N * em.KP;
+    if (em.q_split) {                                    // values 0..8 from the first table, 9..K-1 from the second
+        const int64_t split_stride = (int64_t)em.R * 2 * ctx->V * 8;
+        k_estep_lk<4><<<grid, lk_threads(4), smem, ctx->stream>>>(v, em.Tq, xq_stride, em.Lq, lq_stride, 9, em.KP, 0, done, em.qbad);
+        k_estep_lk<4><<<grid, lk_threads(4), smem, ctx->stream>>>(v, em.Tq + split_stride, xq_stride, em.Lq, lq_stride, em.K - 9, em.KP, 9, done, em.qbad);
+        ctx->launches += 2;
+    } else {
+        if (lanes == 4) k_estep_lk<4><<<grid, lk_threads(4), smem, ctx->stream>>>(v, em.Tq, xq_stride, em.Lq, lq_stride, em.K, em.KP, 0, done, em.qbad);
+        else k_estep_lk<8><<<grid, lk_threads(8), smem, ctx->stream>>>(v, em.Tq, xq_stride, em.Lq, lq_stride, em.K, em.KP, 0, done, em.qbad);
+        ctx->launches += 1;
+    }
     SCS_CUDA(cudaGetLastError());
     return 0;
 }
@@ -297,8 +304,10 @@ static TableOut table_out(scs_ctx* ctx, int r0) {
     TableOut t;
     t.T = em.T + (int64_t)r0 * 2 * ctx->V * em.KP;
     if (em.Tq) {
-        t.Tq = em.Tq + (int64_t)r0 * 2 * ctx->V * 2 * em.q_lanes;
+        t.Tq = em.Tq + (int64_t)r0 * 2 * ctx->V * 2 * (em.q_split ? 4 : em.q_lanes);
         t.qlanes = em.q_lanes;
+        t.split = em.q_split;
+        t.split_stride = (int64_t)em.R * 2 * ctx->V * 8;
         t.qscale = ldexp(1.0, em.q_F);
         t.qbad = em.qbad + r0;
         t.qbad_next = em.qbad + em.R + r0;
@@ -583,6 +592,7 @@ int scs_em_begin(scs_ctx* ctx, int R, int K, const double* P0, int max_iter) {
             SCS_TRY(dev_alloc(ctx, &em.qbad, 2 * R));   // [R] flags, [R] their staging inside k_finalize
             SCS_CUDA(cudaMemsetAsync(em.qbad, 0, (size_t)R * 8, ctx->stream));
             if (lk_wanted(lanes)) {
+                em.q_split = lk_split(lanes) ? 1 : 0;
                 SCS_TRY(dev_alloc(ctx, &em.Lq, (int64_t)R * N * em.KP));
                 SCS_CUDA(cudaMemsetAsync(em.Lq, 0, (size_t)R * N * em.KP * 8, ctx->stream));
             }
@@ -808,7 +818,7 @@ int scs_em_info(scs_ctx* ctx, int64_t out[6]) {
     out[1] = em.Tq ? em.q_F : 0;
     out[2] = em.Lq ? ctx->LK.ntiles : em.Tq ? ctx->QE.ntiles : ctx->TE.ntiles;
     out[3] = 0;
-    out[4] = em.Lq ? 2 : em.Tq ? 1 : 0;
+    out[4] = em.Lq ? (em.q_split ? 3 : 2) : em.Tq ? 1 : 0;
     out[5] = em.Lq ? ctx->LK.ntasks : 0;
     if (em.Tq) {
         std::vector<int32_t> bad((size_t)em.R);

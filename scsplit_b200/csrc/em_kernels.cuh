@@ -456,8 +456,10 @@ __device__ __forceinline__ void update_prior(int r, int K, int KP, const double*
 // quantised copy Tq with the per-restart "does not fit" flag.
 struct TableOut {
     double* T = nullptr;          // [R][2V][KP]
-    uint64_t* Tq = nullptr;       // [R][2V][2 * qlanes]
+    uint64_t* Tq = nullptr;       // [R][2V][2 * qlanes]; split: [2][R][2V][8], table h at Tq + h * split_stride
     int qlanes = 0;
+    int split = 0;                // 16-value-wide table kept as two tables of 64-byte rows (EmState::q_split)
+    int64_t split_stride = 0;
     double qscale = 0.0;          // 2^F
     int32_t* qbad = nullptr;      // [R] the table of restart r does not fit the format
     int32_t* qbad_next = nullptr; // [R] staging of the flag while the blocks of an EM-loop launch are still writing the table
@@ -525,6 +527,15 @@ static __global__ void __launch_bounds__(FIN_THREADS) k_finalize(int64_t V, int 
             const int row = o / (2 * QL), rem = o - row * 2 * QL, sel = rem / QL, j = rem - sel * QL;
             if (v0 + row >= V) continue;
             const double* l = s_l[sel] + row * KP;
+            if (out.split) {                             // lanes 0..3: values 0..7 and the bytes of value 8; lanes 4..7: values 9..16
+                const int h = j >> 2, jj = j & 3, ka = 9 * h + 2 * jj, kb = ka + 1;
+                const uint64_t a = ka < K ? q_quant(l[ka], out.qscale, &bad) : 0ull;
+                const uint64_t b = kb < K ? q_quant(l[kb], out.qscale, &bad) : 0ull;
+                const uint64_t x = (h == 0 && 8 < K) ? q_quant(l[8], out.qscale, &bad) : 0ull;
+                uint4* dst = reinterpret_cast<uint4*>(out.Tq + h * out.split_stride + (((int64_t)r * 2 + sel) * V + v0 + row) * 8) + jj;
+                *dst = q_pack_lane(a, b, x, jj);
+                continue;
+            }
             const int ka = 2 * j, kb = 2 * j + 1, kx = 2 * QL;
             const uint64_t a = ka < K ? q_quant(l[ka], out.qscale, &bad) : 0ull;
             const uint64_t b = kb < K ? q_quant(l[kb], out.qscale, &bad) : 0ull;

@@ -17,6 +17,9 @@
 // RED.ADD.64 (integer atomics: order-free, hence still deterministic).  There are no per-(tile, cell) partial sums in memory
 // and no combine kernel: k_bayes turns the totals into L = -sum * 2^-F, adds the rare entries with counts above Q_REP_MAX in
 // fp64, and leaves the totals at zero for the next E-step.
+// A table of more than 9 values per row (K = 10..17) is kept as two tables of 64-byte rows and read in two passes over the same
+// stream (K and vbase: the values this pass adds and where they go in a cell's totals): two wavefronts per entry like one
+// 128-byte row, but with tiles of twice the rows, hence half the units to flush, and the cheaper 64-byte kernel.
 #pragma once
 #include "common.cuh"
 #include "estep_q.cuh"
@@ -50,6 +53,7 @@ struct LkStreamView {
     const int32_t* task_cell;    // [ntasks][32]
     const int32_t* tile_task;    // [ntiles + 1]
     const int64_t* cta_row;      // [gridDim.x + 1]
+    const int32_t* cta_tile;     // [gridDim.x] tile of the first row of each range
     int ntiles;
     int TR;
     int64_t xrows;
@@ -58,7 +62,7 @@ struct LkStreamView {
 template <int C>
 __global__ void __launch_bounds__(lk_threads(C), 1)
 k_estep_lk(const LkStreamView s, const uint64_t* __restrict__ Xq, int64_t xq_stride, unsigned long long* __restrict__ Lq, int64_t lq_stride,
-           int K, int KP, const int32_t* __restrict__ done, const int32_t* __restrict__ qbad) {
+           int K, int KP, int vbase, const int32_t* __restrict__ done, const int32_t* __restrict__ qbad) {
     // rows a lane keeps requested ahead = rows per unrolled block: 8 for 64-byte rows; 4 for 128-byte rows, whose block of 8
     // (1200 instructions) ran out of the instruction cache: `no_instructions` was the top stall of the first capture
     constexpr int ROWB = C * 16, RING = C <= 4 ? LK_RING : LK_RING / 2;
@@ -82,7 +86,7 @@ k_estep_lk(const LkStreamView s, const uint64_t* __restrict__ Xq, int64_t xq_str
     __syncthreads();
     uint32_t phase = 0;
 
-    int t = 0;
+    int t = __ldg(s.cta_tile + blockIdx.x);              // (walking the tiles from 0 cost the last CTAs 16 dependent round trips)
     for (int64_t x0 = xa; x0 < xb;) {
         while (t + 1 < s.ntiles && __ldg(s.task_row + __ldg(s.tile_task + t + 1)) <= x0) ++t;   // tile of stream row x0
         const int kt0 = __ldg(s.tile_task + t), kt1 = __ldg(s.tile_task + t + 1);
@@ -146,7 +150,7 @@ k_estep_lk(const LkStreamView s, const uint64_t* __restrict__ Xq, int64_t xq_str
                 a[j] = b[j] = pp[j] = 0ull;
             }
             // every lane holds all chunks of its rows, so the whole extra value is here
-            if (live && 2 * C < K && x) atomicAdd(Lq + (int64_t)cell * KP + 2 * C, (unsigned long long)x);
+            if (live && 2 * C < K && x) atomicAdd(Lq + (int64_t)cell * KP + vbase + 2 * C, (unsigned long long)x);
             const int oi = lane & 7;
 #pragma unroll
             for (int h = 0; h < 2 * C / 8; ++h) {
@@ -174,10 +178,10 @@ k_estep_lk(const LkStreamView s, const uint64_t* __restrict__ Xq, int64_t xq_str
                     const int v = 2 * ((slot >> 1) ^ rot_c) + (slot & 1);
                     const uint64_t val = R[8 * h + c8];
 #ifdef SCS_LK_NO_RED
-                    if (cell_c == -2 && v < K && val) atomicAdd(Lq + (int64_t)cell_c * KP + v, (unsigned long long)val);
+                    if (cell_c == -2 && v < K && val) atomicAdd(Lq + (int64_t)cell_c * KP + vbase + v, (unsigned long long)val);
 #else
-                    SCS_ASSERT(cell_c < 0 || (int64_t)cell_c * KP + v < lq_stride || v >= K);
-                    if (cell_c >= 0 && v < K && val) atomicAdd(Lq + (int64_t)cell_c * KP + v, (unsigned long long)val);
+                    SCS_ASSERT(cell_c < 0 || (int64_t)cell_c * KP + vbase + v < lq_stride || v >= K);
+                    if (cell_c >= 0 && v < K && val) atomicAdd(Lq + (int64_t)cell_c * KP + vbase + v, (unsigned long long)val);
 #endif
                 }
             }

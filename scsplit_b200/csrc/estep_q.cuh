@@ -45,6 +45,11 @@ inline int q_tile_rows(int lanes, int64_t xrows) {
     const int64_t cap = lanes == 4 ? 4094 : 2046;    // 12 / 11 bits of in-tile row per code; rows TR and TR + 1 are all zeros
     if (tr > cap) tr = cap;
     if (tr > xrows) tr = xrows;
+    if (tr < 1) tr = 1;
+    // equal tiles: a short last tile means short units there (3 % of a tile at a 60k-SNV pool with 64-byte rows: units of 8
+    // codes, flushed every 4 stream rows -- the CTA that got them ran 60 % longer than the others)
+    const int64_t ntiles = (xrows + tr - 1) / tr;
+    tr = (xrows + ntiles - 1) / ntiles;
     return (int)(tr < 1 ? 1 : tr);
 }
 // fraction bits for a pool whose deepest cell holds `depth` reads: depth * 2^(6+F) < 2^63

@@ -892,9 +892,15 @@ __global__ void k_lk_emit(int64_t ntasks, int ntiles, int64_t ncells, int TR, co
 // Equal-cost ranges of stream rows for the CTAs.  Running into another table tile costs a CTA far more than the load itself
 // (it drains, loads 227 KB, and every warp starts cold): a range is charged `charge` rows for every tile boundary inside it.
 __global__ void k_lk_plan(int ncta, int ntiles, int64_t nrows, const int32_t* __restrict__ tile_task, const int64_t* __restrict__ task_row,
-                          int64_t charge, int64_t* __restrict__ cta_row) {
+                          int64_t charge, int64_t* __restrict__ cta_row, int32_t* __restrict__ cta_tile) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j > ncta) return;
+    auto tile_of = [&](int64_t x) {                                // the last non-empty tile that starts at or before row x
+        int t = 0;
+        for (int u = 1; u < ntiles; ++u)
+            if (tile_task[u] < tile_task[u + 1] && task_row[tile_task[u]] <= x) t = u;
+        return t;
+    };
     auto cost = [&](int64_t x) {                                   // of the rows [0, x)
         int64_t c = x;
         for (int t = 1; t < ntiles; ++t) {
@@ -903,7 +909,7 @@ __global__ void k_lk_plan(int ncta, int ntiles, int64_t nrows, const int32_t* __
         }
         return c;
     };
-    if (j == 0 || j == ncta) { cta_row[j] = j ? nrows : 0; return; }
+    if (j == 0 || j == ncta) { cta_row[j] = j ? nrows : 0; if (j == 0) cta_tile[0] = tile_of(0); return; }
     const int64_t total = cost(nrows), target = (total * j + ncta - 1) / ncta;
     int64_t lo = 0, hi = nrows;
     while (lo < hi) {
@@ -913,6 +919,7 @@ __global__ void k_lk_plan(int ncta, int ntiles, int64_t nrows, const int32_t* __
     // a target inside the jump of a tile boundary: cut AT the boundary instead of one row into the next tile
     if (lo > 0 && cost(lo) - cost(lo - 1) > 1 && cost(lo - 1) < target) --lo;
     cta_row[j] = lo;
+    cta_tile[j] = tile_of(lo);
 }
 
 // one thread per cell: entries whose count is too large to be written as repeated codes
@@ -930,6 +937,7 @@ void free_lockstep(scs_ctx* ctx, LockstepStream& t) {
     dev_free(ctx, t.task_cell);
     dev_free(ctx, t.tile_task);
     dev_free(ctx, t.cta_row);
+    dev_free(ctx, t.cta_tile);
     dev_free(ctx, t.xheavy);
     t = LockstepStream();
 }
@@ -1039,10 +1047,11 @@ int build_lockstep(scs_ctx* ctx, const Stream& s, LockstepStream& t, int lanes, 
     }
     trace.mark("lk: emit");
     SCS_TRY(dev_alloc(ctx, &t.cta_row, ncta + 1));
+    SCS_TRY(dev_alloc(ctx, &t.cta_tile, ncta + 1));
     // (in stream rows of 64 codes; sweep at config 3, E-step sums: 95.2 us with no charge, 83.9 at 453, 82.8 at 1000, 84.8 at 2000, 88.0 at 3000)
     const char* tc_env = std::getenv("SCS_LK_TILE_COST");
     const int64_t charge = tc_env ? atoll(tc_env) : (int64_t)(TR + 2) * lanes * 16 / 256;
-    k_lk_plan<<<(ncta + 1 + 127) / 128, 128, 0, st>>>(ncta, ntiles, nrows, t.tile_task, t.task_row, charge, t.cta_row);
+    k_lk_plan<<<(ncta + 1 + 127) / 128, 128, 0, st>>>(ncta, ntiles, nrows, t.tile_task, t.task_row, charge, t.cta_row, t.cta_tile);
     SCS_TRY(dev_alloc(ctx, &t.xheavy, s.nrows));
     k_lk_xheavy<<<(unsigned)((s.nrows + 255) / 256), 256, 0, st>>>(s.nrows, s.hptr, s.hcnt, t.xheavy);
     ctx->launches += 2;

@@ -167,7 +167,7 @@ class Engine:
         out = (ctypes.c_int64 * 6)()
         check(self.lib.scs_em_info(self.h, out))
         return dict(q_lanes=int(out[0]), q_frac_bits=int(out[1]), tiles=int(out[2]), q_unfit_restarts=int(out[3]),
-                    q_form={0: "fp64", 1: "row groups", 2: "lock-step"}[int(out[4])], q_tasks=int(out[5]))
+                    q_form={0: "fp64", 1: "row groups", 2: "lock-step", 3: "lock-step, two 64-byte tables"}[int(out[4])], q_tasks=int(out[5]))
 
     def _shape(self, what):
         return {SCS_P: (self.V, self.K), SCS_W: (self.N, self.K), SCS_L: (self.N, self.K), SCS_LPS: (self.K,),

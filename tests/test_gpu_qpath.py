@@ -133,14 +133,19 @@ def test_lockstep_form_equals_row_group_form_bitwise(K, V, N, dens, E, monkeypat
     ref_s, alt_s = csr_matrix(ref.astype(np.int32)), csr_matrix(alt.astype(np.int32))
     P = np.stack([_random_P(V, K, 1), _random_P(V, K, 2)])
     out = {}
-    for form in ("lock-step", "row groups"):
+    forms = ("lock-step", "row groups") + (("lock-step wide",) if K > 9 else ())
+    for form in forms:
         monkeypatch.delenv("SCS_Q_GROUPS", raising=False)
-        monkeypatch.delenv("SCS_Q_LOCKSTEP", raising=False)
-        monkeypatch.setenv("SCS_Q_GROUPS" if form == "row groups" else "SCS_Q_LOCKSTEP", "1")   # (the default depends on the row width)
+        monkeypatch.delenv("SCS_Q_WIDE", raising=False)
+        if form == "row groups":
+            monkeypatch.setenv("SCS_Q_GROUPS", "1")
+        if form == "lock-step wide":                      # one pass over 128-byte rows instead of two over 64-byte rows
+            monkeypatch.setenv("SCS_Q_WIDE", "1")
         with E(ref_s, alt_s) as eng:
             eng.em_begin(P)
             info = eng.em_info()
-            assert info["q_form"] == form, info
+            assert info["q_form"] == {"lock-step": "lock-step" if K <= 9 else "lock-step, two 64-byte tables", "row groups": "row groups",
+                                      "lock-step wide": "lock-step"}[form], info
             eng.estep()
             first = [eng.get(SCS_L, r) for r in range(2)]
             eng.estep()
@@ -151,8 +156,9 @@ def test_lockstep_form_equals_row_group_form_bitwise(K, V, N, dens, E, monkeypat
     assert_close(out["lock-step"][0][0], L_o, RTOL, "L lock-step vs dense product")
     for r in range(2):
         assert np.array_equal(out["lock-step"][0][r], out["lock-step"][1][r]), "a repeated E-step must give the same sums"
-        for part in range(4):
-            assert np.array_equal(out["lock-step"][part][r], out["row groups"][part][r], equal_nan=True), (part, r)
+        for form in forms[1:]:
+            for part in range(4):
+                assert np.array_equal(out["lock-step"][part][r], out[form][part][r], equal_nan=True), (form, part, r)
 
 
 def test_unfit_table_takes_fp64_per_restart(E):
