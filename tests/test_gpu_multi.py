@@ -94,6 +94,15 @@ def _worker_batch(rank, world, port, out_dir):
         np.save(os.path.join(out_dir, "bW_%d.npy" % rank), np.stack([eng.get(SCS_W, r) for r in range(len(labels))]))
         np.save(os.path.join(out_dir, "bS_%d.npy" % rank), np.stack([eng.stats(r)["S"] for r in range(len(labels))]))
         np.save(os.path.join(out_dir, "bmeta_%d.npy" % rank), np.stack([it, cv, ll]).astype(np.float64))
+        # each restart alone on the same sharded pool: what the batch must reproduce bit for bit
+        alone_S, alone_it = [], []
+        for r in range(len(labels)):
+            eng.em_begin(P0[r])
+            eng.em_run()
+            alone_it.append(eng.em_status()[0][0])
+            alone_S.append(eng.stats(0)["S"])
+        np.save(os.path.join(out_dir, "bS1_%d.npy" % rank), np.stack(alone_S))
+        np.save(os.path.join(out_dir, "bit1_%d.npy" % rank), np.array(alone_it, dtype=np.float64))
         eng.close()
     finally:
         dist.destroy_process_group()
@@ -138,11 +147,16 @@ def test_two_gpu_restart_batch_statistics_survive_convergence(tmp_path):
     with np.errstate(invalid="ignore"):
         assert np.array_equal(W1 >= 0.99, W2 >= 0.99)
     assert np.allclose(m0[2], ll, rtol=1e-9, atol=0)
-    # the statistics belong to each restart's own last M-step; iteration counts may differ by the stop rule's last ulp, so
-    # compare where both runs stopped at the same iteration
+    # the statistics belong to each restart's own last M-step: a restart run ALONE on the same two shards stops at the same
+    # iteration and leaves the same bits (the 24 extra rounds and the restarts batched next to it changed nothing)
+    assert np.array_equal(np.load(tmp_path / "bit1_0.npy"), m0[0])
+    assert np.array_equal(np.load(tmp_path / "bS1_0.npy"), S2)
+    # against the single-GPU run: iteration counts may differ by the stop rule's last ulp (the LL is summed in another order),
+    # so the tight comparison is made where both runs stopped at the same iteration, a loose one everywhere (both have converged)
     same = m0[0] == it
-    assert same.any()
+    print("restarts stopping at the same iteration on 1 and 2 GPUs: %d of 3 (%s vs %s)" % (int(same.sum()), m0[0], it))
     assert np.allclose(S2[same], S1[same], rtol=1e-9, atol=1e-12)
+    assert np.allclose(S2, S1, rtol=1e-4, atol=1e-7)
 
 
 def _worker_cli(rank, world, port, argv, seed):
