@@ -80,26 +80,39 @@ k_estep_lk(const LkStreamView s, const uint64_t* __restrict__ Xq, int64_t xq_str
     const int rot = lane & (C - 1);
 
     const int64_t xa = __ldg(s.cta_row + blockIdx.x), xb = __ldg(s.cta_row + blockIdx.x + 1);
+    int t = __ldg(s.cta_tile + blockIdx.x);              // (walking the tiles from 0 cost the last CTAs 16 dependent round trips)
     if (xa >= xb) return;
-    if (tid == 0) mbar_init(bar, 1);
+    auto load_tile = [&](int tile) {                     // (thread 0) TMA bulk copies of one table tile, completing on `bar`
+        const int64_t rows_t = min((int64_t)TR, s.xrows - (int64_t)tile * TR);
+        const uint32_t bytes = (uint32_t)(rows_t * ROWB);
+        const char* src = reinterpret_cast<const char*>(Xq) + (int64_t)tile * TR * ROWB;
+        fence_proxy_async();
+        mbar_expect_tx(bar, bytes);
+        for (uint32_t off = 0; off < bytes; off += 32768u) bulk_g2s(smem + off, src + off, min(32768u, bytes - off), bar);
+    };
+    // The first tile is requested before anything else is looked up: a CTA cannot add a row before its 226 KB have arrived
+    // (launch + look-ups + loads alone take 13 us of the kernel's 82 at config 3), so the plan look-ups, the binary search for
+    // the warp's first task, its cells and its first stream words all go on while the tile is on its way.
+    // (Tried: clusters of two CTAs whose ranges start in the same tile loading it once, each CTA one half, multicast into both.
+    // No gain, 83.6 against 83.0 us: the L2 already serves neighbouring CTAs' requests for the same lines from one read.)
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        load_tile(t);
+    }
     for (int k = tid; k < 2 * ROWB / 8; k += blockDim.x) reinterpret_cast<uint64_t*>(smem + (size_t)TR * ROWB)[k] = 0ull;
     __syncthreads();
     uint32_t phase = 0;
+    bool first = true;
 
-    int t = __ldg(s.cta_tile + blockIdx.x);              // (walking the tiles from 0 cost the last CTAs 16 dependent round trips)
     for (int64_t x0 = xa; x0 < xb;) {
         while (t + 1 < s.ntiles && __ldg(s.task_row + __ldg(s.tile_task + t + 1)) <= x0) ++t;   // tile of stream row x0
         const int kt0 = __ldg(s.tile_task + t), kt1 = __ldg(s.tile_task + t + 1);
         const int64_t seg_end = min(xb, __ldg(s.task_row + kt1));
-        __syncthreads();                                  // every warp is done reading the previous tile
-        if (tid == 0) {
-            const int64_t rows_t = min((int64_t)TR, s.xrows - (int64_t)t * TR);
-            const uint32_t bytes = (uint32_t)(rows_t * ROWB);
-            const char* src = reinterpret_cast<const char*>(Xq) + (int64_t)t * TR * ROWB;
-            fence_proxy_async();
-            mbar_expect_tx(bar, bytes);
-            for (uint32_t off = 0; off < bytes; off += 32768u) bulk_g2s(smem + off, src + off, min(32768u, bytes - off), bar);
+        if (!first) {
+            __syncthreads();                              // every warp is done reading the previous tile
+            if (tid == 0) load_tile(t);
         }
+        first = false;
         // this warp's share of the segment, and the task its first row belongs to (while the tile is on its way)
         const int64_t len = seg_end - x0;
         const int64_t wa = x0 + len * warp / nwarps, wb = x0 + len * (warp + 1) / nwarps;
@@ -112,18 +125,27 @@ k_estep_lk(const LkStreamView s, const uint64_t* __restrict__ Xq, int64_t xq_str
             }
             k = lo;
         }
+        // stream rows are counted from the start of this warp's share
+        const int nrow = (int)(wb - wa);
+        int stop = 0, cell = -1, stop_n = 0, cell_n = -1;
+        const uint32_t* wp = s.words + wa * 32 + lane;
+        uint32_t ring[RING];
+        if (wa < wb) {
+            stop = (int)(min(__ldg(s.task_row + k + 1), wb) - wa);    // where the lanes' current units end (or the share does)
+            cell = __ldg(s.task_cell + (int64_t)k * 32 + lane);
+            // the next task's end and cells are fetched a task ahead
+            stop_n = (int)(min(__ldg(s.task_row + min(k + 2, kt1)), wb) - wa);
+            cell_n = (k + 1 < kt1) ? __ldg(s.task_cell + (int64_t)(k + 1) * 32 + lane) : -1;
+#pragma unroll
+            for (int i = 0; i < RING; ++i) ring[i] = __ldcs(wp + i * 32);
+        }
         mbar_wait(bar, phase);
         phase ^= 1u;
         x0 = seg_end;
+#ifdef SCS_LK_LOAD_ONLY    // (diagnostic build: launch, plan look-ups and the table tile loads, no rows; the results are wrong)
+        continue;
+#endif
         if (wa >= wb) continue;
-
-        // stream rows are counted from the start of this warp's share
-        const int nrow = (int)(wb - wa);
-        int stop = (int)(min(__ldg(s.task_row + k + 1), wb) - wa);    // where the lanes' current units end (or the share does)
-        int cell = __ldg(s.task_cell + (int64_t)k * 32 + lane);
-        // the next task's end and cells are fetched a task ahead
-        int stop_n = (int)(min(__ldg(s.task_row + min(k + 2, kt1)), wb) - wa);
-        int cell_n = (k + 1 < kt1) ? __ldg(s.task_cell + (int64_t)(k + 1) * 32 + lane) : -1;
 
         uint64_t a[C], b[C], pp[C];
 #pragma unroll
@@ -237,10 +259,6 @@ k_estep_lk(const LkStreamView s, const uint64_t* __restrict__ Xq, int64_t xq_str
                 cell_n = (k + 1 < kt1) ? __ldg(s.task_cell + (int64_t)(k + 1) * 32 + lane) : -1;
             }
         };
-        const uint32_t* wp = s.words + wa * 32 + lane;
-        uint32_t ring[RING];
-#pragma unroll
-        for (int i = 0; i < RING; ++i) ring[i] = __ldcs(wp + i * 32);
         int x = 0;                                       // next row to add
         for (int xb = 0; xb < nrow; xb += RING, wp += RING * 32) {
             if (stop >= xb + RING) {                  // the block lies inside the current piece
