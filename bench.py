@@ -333,7 +333,7 @@ def cells_leg(args, rank, world, local, barrier):
         "scaling": "strong", "e_us": kt["e_us"], "m_us": kt["m_us"], "bayes_us": kt["bayes_us"], "allreduce_us": kt["allreduce_us"],
         "allreduce_us_is": "elapsed on the communication stream per iteration (includes the time a collective waits for SMs behind the kernels it overlaps)",
         "allreduce_pieces_timed": kt["allreduce_n"], "allreduce_doubles": 2 * V * (K + (K & 1)) + (K + (K & 1)) + 2,
-        "estep": "fixed point, %d-byte rows, F=%d" % (16 * einfo["q_lanes"], einfo["q_frac_bits"]) if einfo["q_lanes"] else "fp64",
+        "estep": "fixed point, %d values per table row, F=%d, form: %s" % (4 * einfo["q_lanes"] + 1, einfo["q_frac_bits"], einfo["q_form"]) if einfo["q_lanes"] else "fp64",
         "hbm_frac_of_iteration": (eb + mb) / world / (dev_s / steps) / 1e9 / peak,
         "last_ll": float(ll[0]), "host_generation_s": gen_s, "clocks": res["clocks"],
     }
@@ -532,19 +532,19 @@ def run_cuda_arm(args):
             "init": "seed P from 3 random cells per state through scs_seed_af (the reference's trim/PCA/KMeans initialiser is host code outside the step)",
             "regime": "saturated posteriors (after %d warm-up iterations): E-step + sparse M-step; the soft start of a run is under `regimes`" % args.warmup,
             "estep": ("log tables in %d-bit fixed point (F=%d), %d-byte rows, exact integer accumulation; fp64 per restart when a table does not fit" % (
-                6 + einfo["q_frac_bits"], einfo["q_frac_bits"], 16 * einfo["q_lanes"]) + "; form: " + einfo["q_form"]) if einfo["q_lanes"] else "fp64 tables and accumulation",
+                6 + einfo["q_frac_bits"], einfo["q_frac_bits"], 64 if einfo["q_form"].startswith("lock-step,") else 16 * einfo["q_lanes"]) + "; form: " + einfo["q_form"]) if einfo["q_lanes"] else "fp64 tables and accumulation",
         },
         "cell_snv_per_sec": value * V * N_total,
         "wall_ms_per_step": 1000.0 * wall / args.steps,
         "clocks": clocks,
         "gpu_launches": int(launches),
         "last_ll": float(ll[0]),
-        "roofline": {"bound": "hbm", "kernel": ("E-step sums (k_estep_lk)" if einfo["q_form"] == "lock-step" else "E-step sums (k_estep_q + k_combine_q)") if dom == "E" and einfo["q_lanes"] else "E-step SpMM" if dom == "E" else "M-step sums",
+        "roofline": {"bound": "hbm", "kernel": ("E-step sums (k_estep_lk)" if einfo["q_form"].startswith("lock-step") else "E-step sums (k_estep_q + k_combine_q)") if dom == "E" and einfo["q_lanes"] else "E-step SpMM" if dom == "E" else "M-step sums",
                      "achieved": dom_bytes / (dom_us * 1e-6) / 1e9,
                      "peak": peak, "unit": "GB/s", "frac": dom_bytes / (dom_us * 1e-6) / 1e9 / peak, "traffic": traffic, "traffic_source": traffic_src,
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": int(dom_bytes), "avg_launch_us": dom_us,
                      "e_step": {"us": kt["e_us"], "bytes": int(eb), "GBps": eb / max(kt["e_us"], 1e-9) / 1e3, "launches_timed": kt["e_n"],
-                                "what": ("k_estep_lk: a lane per entry, 32 units in lock step, integer totals by RED.ADD.64 (k_bayes converts them to L)" if einfo["q_form"] == "lock-step" else
+                                "what": ("k_estep_lk: a lane per entry, 32 units in lock step, integer totals by RED.ADD.64 (k_bayes converts them to L)" if einfo["q_form"].startswith("lock-step") else
                                          "all launches that produce L: k_estep_q (per-(tile, cell) integer sums) + k_combine_q (fold over the tiles)") if einfo["q_lanes"] else "k_spmm_tiled + k_spmm_combine",
                                 "bayes_us": kt["bayes_us"],
                                 "with_bayes": {"us": kt["e_us"] + kt["bayes_us"], "frac": eb / max(kt["e_us"] + kt["bayes_us"], 1e-9) / 1e3 / peak,
