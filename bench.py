@@ -333,7 +333,7 @@ def cells_leg(args, rank, world, local, barrier):
         "scaling": "strong", "e_us": kt["e_us"], "m_us": kt["m_us"], "bayes_us": kt["bayes_us"], "allreduce_us": kt["allreduce_us"],
         "allreduce_us_is": "elapsed on the communication stream per iteration (includes the time a collective waits for SMs behind the kernels it overlaps)",
         "allreduce_pieces_timed": kt["allreduce_n"], "allreduce_doubles": 2 * V * (K + (K & 1)) + (K + (K & 1)) + 2,
-        "estep": "fixed point, %d values per table row, F=%d, form: %s" % (4 * einfo["q_lanes"] + 1, einfo["q_frac_bits"], einfo["q_form"]) if einfo["q_lanes"] else "fp64",
+        "estep": "fixed point, %d values per table row, F=%d, form: %s" % (2 * einfo["q_lanes"] + 1, einfo["q_frac_bits"], einfo["q_form"]) if einfo["q_lanes"] else "fp64",
         "hbm_frac_of_iteration": (eb + mb) / world / (dev_s / steps) / 1e9 / peak,
         "last_ll": float(ll[0]), "host_generation_s": gen_s, "clocks": res["clocks"],
     }

@@ -238,6 +238,7 @@ k_mstep_sparse(int64_t nrows, int64_t njobs, int64_t N, int K, const int32_t* __
 #pragma unroll
             for (int j = 0; j < UV; ++j) {  // every code (cell << 1 | dup) addresses the staged block: lo <= cell <= lo + n (the NOP word)
                 const uint32_t c_lo = (uint32_t)blk.lo, c_hi = (uint32_t)(blk.lo + blk.n);
+                (void)c_lo; (void)c_hi;                                  // (only the bounds-checked build reads them)
                 SCS_ASSERT((cur[j].x >> 1) >= c_lo && (cur[j].x >> 1) <= c_hi && (cur[j].y >> 1) >= c_lo && (cur[j].y >> 1) <= c_hi &&
                            (cur[j].z >> 1) >= c_lo && (cur[j].z >> 1) <= c_hi && (cur[j].w >> 1) >= c_lo && (cur[j].w >> 1) <= c_hi);
             }
