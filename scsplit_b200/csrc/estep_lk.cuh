@@ -59,6 +59,11 @@ struct LkStreamView {
     int64_t xrows;
 };
 
+#ifdef SCS_LK_TRACE     // (diagnostic build: per-CTA times of one launch on stdout)
+__device__ int lk_trace_launch = 0;
+__device__ __forceinline__ unsigned long long lk_now() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#endif
+
 template <int C>
 __global__ void __launch_bounds__(lk_threads(C), 1)
 k_estep_lk(const LkStreamView s, const uint64_t* __restrict__ Xq, int64_t xq_stride, unsigned long long* __restrict__ Lq, int64_t lq_stride,
@@ -79,6 +84,11 @@ k_estep_lk(const LkStreamView s, const uint64_t* __restrict__ Xq, int64_t xq_str
     const uint32_t smem_base = smem_u32(smem);
     const int rot = lane & (C - 1);
 
+#ifdef SCS_LK_TRACE
+    const unsigned long long tr_t0 = lk_now();
+    unsigned long long tr_t1 = 0;
+    int tr_segs = 0;
+#endif
     const int64_t xa = __ldg(s.cta_row + blockIdx.x), xb = __ldg(s.cta_row + blockIdx.x + 1);
     int t = __ldg(s.cta_tile + blockIdx.x);              // (walking the tiles from 0 cost the last CTAs 16 dependent round trips)
     if (xa >= xb) return;
@@ -142,6 +152,9 @@ k_estep_lk(const LkStreamView s, const uint64_t* __restrict__ Xq, int64_t xq_str
         mbar_wait(bar, phase);
         phase ^= 1u;
         x0 = seg_end;
+#ifdef SCS_LK_TRACE
+        if (!tr_segs++) tr_t1 = lk_now();
+#endif
 #ifdef SCS_LK_LOAD_ONLY    // (diagnostic build: launch, plan look-ups and the table tile loads, no rows; the results are wrong)
         continue;
 #endif
@@ -288,6 +301,18 @@ k_estep_lk(const LkStreamView s, const uint64_t* __restrict__ Xq, int64_t xq_str
             }
         }
     }
+#ifdef SCS_LK_TRACE
+    __syncthreads();
+    if (tid == 0) {
+        unsigned smid;
+        asm("mov.u32 %0, %%smid;" : "=r"(smid));
+        const int launch = atomicAdd(&lk_trace_launch, 0);
+        if (launch >= 30 * (int)gridDim.x && launch < 31 * (int)gridDim.x)
+            printf("lktrace cta %d sm %u rows %lld segs %d t0 %llu tile %llu end %llu\n", (int)blockIdx.x, smid, (long long)(xb - xa), tr_segs,
+                   tr_t0, tr_t1 - tr_t0, lk_now() - tr_t0);
+        atomicAdd(&lk_trace_launch, 1);
+    }
+#endif
 }
 
 }  // namespace scs
