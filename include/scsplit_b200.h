@@ -144,6 +144,15 @@ int scs_csv_shape(scs_csv* csv, int64_t out[5]);
 int scs_csv_fetch(scs_csv* csv, int64_t* indptr, int32_t* indices, int32_t* data, char* ids, char* barcodes);
 int scs_csv_free(scs_csv* csv);
 
+/* ---- output (host only): a float64 matrix in the text DataFrame.to_csv gives it ----
+ * Replaces model.P_s_c.to_csv(path) (scSplit:596; format 0: every value as the shortest string that reads back as the
+ * same double, laid out like Python's repr / numpy's str: "0.5", "1.0", "1e-05", "3.2e+17") and
+ * model.dist_matrix / model.pa_matrix .to_csv(path, float_format='%.0f') (scSplit:599-600; format 1).  NaN is an empty
+ * field (pandas' na_rep), infinities are "inf" / "-inf".  header: the first line without its newline; labels: the row
+ * labels, each followed by '\n'; values: row-major [rows][cols].  The caller passes only labels that need no quoting. */
+int scs_csv_write_f64(const char* path, const char* header, const char* labels, int64_t rows, int64_t cols, const double* values,
+                      int format);
+
 /* ---- instrumentation ---- */
 
 /* number of kernels this context has launched (for bench.py's gpu_launches) */

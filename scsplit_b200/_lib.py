@@ -49,6 +49,7 @@ SIGNATURES = {
     "scs_csv_shape": (c_int, [c_void_p, POINTER(c_int64)]),
     "scs_csv_fetch": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "scs_csv_free": (c_int, [c_void_p]),
+    "scs_csv_write_f64": (c_int, [c_char_p, c_char_p, c_char_p, c_int64, c_int64, c_void_p, c_int]),
     "scs_launch_count": (c_int, [c_void_p, POINTER(c_int64)]),
     "scs_set_timing": (c_int, [c_void_p, c_int]),
     "scs_kernel_times": (c_int, [c_void_p, POINTER(c_double), c_int]),

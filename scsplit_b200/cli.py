@@ -78,6 +78,35 @@ def elbow(points):
     return e
 
 
+_NEEDS_QUOTING = (',', '"', '\n', '\r')
+
+
+def frame_to_csv(frame, path, float_format=None):
+    """`frame.to_csv(path)` / `frame.to_csv(path, float_format='%.0f')` (scSplit:596, 599-600), byte for byte, through the
+    library's float writer (`scs_csv_write_f64`) instead of one Python string object per value; frames it does not cover
+    (non-float columns, labels that are not plain strings or would need quoting) go through pandas itself.
+    Returns True when the library wrote the file."""
+    import ctypes
+    from . import _lib
+    index, columns = frame.index, frame.columns
+    plain = (float_format in (None, '%.0f') and index.nlevels == 1 and columns.nlevels == 1 and len(columns) > 0
+             and (index.name is None or isinstance(index.name, str))
+             and all(dt == np.float64 for dt in frame.dtypes)
+             and all(isinstance(c, (int, np.integer, str)) and not isinstance(c, (bool, np.bool_)) for c in columns)
+             and all(isinstance(x, str) for x in index))
+    if plain:
+        head = [index.name or ''] + [str(c) for c in columns]
+        plain = not any(ch in x for x in head + list(index) for ch in _NEEDS_QUOTING)
+    if not plain:
+        frame.to_csv(path, float_format=float_format)
+        return False
+    labels = ''.join(x + '\n' for x in index)
+    values = np.ascontiguousarray(frame.values, dtype=np.float64)
+    _lib.check(_lib.load().scs_csv_write_f64(os.fsencode(path), ','.join(head).encode(), labels.encode(), len(index), len(columns),
+                                             values.ctypes.data_as(ctypes.c_void_p), 0 if float_format is None else 1))
+    return True
+
+
 def write_outputs(model, num, doublets, out):
     """scSplit_result.csv, scSplit_P_s_c.csv, scSplit_dist_variants.txt, scSplit_dist_matrix.csv, scSplit_PA_matrix.csv
     in the reference's formats (scSplit:582-600)."""
@@ -89,12 +118,12 @@ def write_outputs(model, num, doublets, out):
         frames.append(pd.DataFrame({'Barcode': model.reassigned[model.doublet], 'Cluster': 'DBL-' + str(model.doublet)}))
     frames = [f for f in frames if len(f)] or [pd.DataFrame({'Barcode': [], 'Cluster': []})]
     pd.concat(frames).to_csv(os.path.join(out, r'scSplit_result.csv'), sep='\t', index=False)
-    model.P_s_c.to_csv(os.path.join(out, r'scSplit_P_s_c.csv'))
+    frame_to_csv(model.P_s_c, os.path.join(out, r'scSplit_P_s_c.csv'))
     with open(os.path.join(out, r'scSplit_dist_variants.txt'), 'w') as f:
         for item in model.dist_variants:
             f.write(str(item) + '\n')
-    model.dist_matrix.to_csv(os.path.join(out, r'scSplit_dist_matrix.csv'), float_format='%.0f')
-    model.pa_matrix.to_csv(os.path.join(out, r'scSplit_PA_matrix.csv'), float_format='%.0f')
+    frame_to_csv(model.dist_matrix, os.path.join(out, r'scSplit_dist_matrix.csv'), float_format='%.0f')
+    frame_to_csv(model.pa_matrix, os.path.join(out, r'scSplit_PA_matrix.csv'), float_format='%.0f')
 
 
 def run(argv):

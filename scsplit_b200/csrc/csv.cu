@@ -2,12 +2,17 @@
 // pd.read_csv(header=0, index_col=0) + csr_matrix at scSplit:544-546): header "SNV,<barcode>,...", then one row per SNV
 // "<CHROM:POS>,<int>,<int>,...".  The reference materialises a dense int64 V x N frame first (4.8 GB at 30k x 20k);
 // this goes straight to CSR with one pass over an mmap, rows split across host threads.  Host-side I/O only.
+// At the other end of the run, scs_csv_write_f64 renders the float matrices the reference hands to DataFrame.to_csv
+// (scSplit:596, 599-600) in the same text form, byte for byte.
 #include <fcntl.h>
 #include <sys/mman.h>
 #include <sys/stat.h>
 #include <unistd.h>
 
 #include <algorithm>
+#include <charconv>
+#include <cmath>
+#include <cstdio>
 #include <cstring>
 #include <string>
 #include <thread>
@@ -75,6 +80,75 @@ void parse_chunk(Chunk* c, int64_t ncols) {
         ++row;
         p = line_end + 1;
     }
+}
+
+// One float64 as numpy / Python print it (what DataFrame.to_csv writes when no float_format is given): the shortest
+// digit string that reads back as the same double, positional for 1e-4 <= |x| < 1e16 (always with a fractional part:
+// "1.0"), otherwise d[.ddd]e+XX with at least two exponent digits; "inf" / "-inf"; nothing at all for NaN (na_rep='').
+// std::to_chars produces the shortest digits; only their layout is decided here.
+char* put_shortest(char* p, double x) {
+    if (x != x) return p;
+    if (std::isinf(x)) {
+        if (x < 0) *p++ = '-';
+        memcpy(p, "inf", 3);
+        return p + 3;
+    }
+    char tmp[48];
+    const auto r = std::to_chars(tmp, tmp + sizeof tmp, x, std::chars_format::scientific);
+    const char* q = tmp;
+    if (*q == '-') *p++ = *q++;
+    char dig[24];
+    int nd = 0;
+    for (; q < r.ptr && *q != 'e'; ++q)
+        if (*q != '.') dig[nd++] = *q;
+    ++q;                                          // 'e'
+    const bool eneg = *q == '-';
+    ++q;                                          // sign (to_chars always writes one)
+    int ex = 0;
+    for (; q < r.ptr; ++q) ex = ex * 10 + (*q - '0');
+    const int decpt = (eneg ? -ex : ex) + 1;      // value = 0.d1d2... * 10^decpt
+    if (decpt <= -4 || decpt > 16) {
+        *p++ = dig[0];
+        if (nd > 1) {
+            *p++ = '.';
+            memcpy(p, dig + 1, (size_t)nd - 1);
+            p += nd - 1;
+        }
+        *p++ = 'e';
+        int e10 = decpt - 1;
+        *p++ = e10 < 0 ? '-' : '+';
+        if (e10 < 0) e10 = -e10;
+        if (e10 >= 100) { *p++ = (char)('0' + e10 / 100); e10 %= 100; }
+        *p++ = (char)('0' + e10 / 10);
+        *p++ = (char)('0' + e10 % 10);
+    } else if (decpt <= 0) {
+        *p++ = '0';
+        *p++ = '.';
+        for (int i = 0; i < -decpt; ++i) *p++ = '0';
+        memcpy(p, dig, (size_t)nd);
+        p += nd;
+    } else if (decpt >= nd) {
+        memcpy(p, dig, (size_t)nd);
+        p += nd;
+        for (int i = nd; i < decpt; ++i) *p++ = '0';
+        *p++ = '.';
+        *p++ = '0';
+    } else {
+        memcpy(p, dig, (size_t)decpt);
+        p += decpt;
+        *p++ = '.';
+        memcpy(p, dig + decpt, (size_t)(nd - decpt));
+        p += nd - decpt;
+    }
+    return p;
+}
+
+// "%.0f" (the float_format of scSplit:599-600): the P/A matrices hold 0, 1 and NaN only, anything else goes through printf
+char* put_rounded(char* p, double x) {
+    if (x != x) return p;
+    if (x == 0.0 && !std::signbit(x)) { *p++ = '0'; return p; }
+    if (x == 1.0) { *p++ = '1'; return p; }
+    return p + snprintf(p, 330, "%.0f", x);
 }
 
 }  // namespace
@@ -188,6 +262,46 @@ int scs_csv_fetch(scs_csv* c, int64_t* indptr, int32_t* indices, int32_t* data, 
     if (data && c->nnz) memcpy(data, c->data.data(), (size_t)c->nnz * 4);
     if (ids) memcpy(ids, c->ids.data(), c->ids.size());
     if (barcodes) memcpy(barcodes, c->barcodes.data(), c->barcodes.size());
+    return 0;
+}
+
+int scs_csv_write_f64(const char* path, const char* header, const char* labels, int64_t rows, int64_t cols, const double* values,
+                      int format) {
+    SCS_CHECK(path && header && (labels || rows == 0) && (values || rows * cols == 0), "null argument");
+    SCS_CHECK(rows >= 0 && cols >= 0, "negative shape");
+    SCS_CHECK(format == 0 || format == 1, "unknown float format %d", format);
+    FILE* f = fopen(path, "wb");
+    SCS_CHECK(f, "cannot open %s for writing", path);
+    std::vector<char> buf((size_t)4 << 20);
+    const size_t field = format == 0 ? 32 : 336;            // longest rendering of one value, separator included
+    char* p = buf.data();
+    bool ok = true;
+    auto flush = [&]() {
+        if (p != buf.data() && fwrite(buf.data(), 1, (size_t)(p - buf.data()), f) != (size_t)(p - buf.data())) ok = false;
+        p = buf.data();
+    };
+    const size_t hl = strlen(header);
+    if (fwrite(header, 1, hl, f) != hl || fputc('\n', f) == EOF) ok = false;
+    const char* lab = labels;
+    for (int64_t r = 0; r < rows && ok; ++r) {
+        const char* le = strchr(lab, '\n');
+        if (!le) { fclose(f); set_error("row label %lld of %lld is missing", (long long)r, (long long)rows); return 1; }
+        const size_t need = (size_t)(le - lab) + (size_t)cols * field + 2;
+        if (need > buf.size()) { flush(); buf.resize(need); p = buf.data(); }
+        if ((size_t)(buf.data() + buf.size() - p) < need) flush();
+        memcpy(p, lab, (size_t)(le - lab));
+        p += le - lab;
+        lab = le + 1;
+        const double* row = values + r * cols;
+        for (int64_t c = 0; c < cols; ++c) {
+            *p++ = ',';
+            p = format == 0 ? put_shortest(p, row[c]) : put_rounded(p, row[c]);
+        }
+        *p++ = '\n';
+    }
+    flush();
+    if (fclose(f) != 0) ok = false;
+    SCS_CHECK(ok, "write to %s failed", path);
     return 0;
 }
 

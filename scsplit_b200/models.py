@@ -244,6 +244,39 @@ def _row_var(frame):
     return frame.var(axis=1)
 
 
+def _representatives_by_text(alt_or_ref, submatrix, informative):
+    """scSplit:291-296 as written: rows grouped by the concatenated text of their values."""
+    selected = []
+    informative_sub = submatrix[informative]
+    patt = informative_sub.astype(str).values.sum(axis=1)
+    inverse = np.asarray(np.unique(patt, return_inverse=True)[1]).ravel()
+    for j in range(int(inverse.max()) + 1):
+        members = informative_sub.index[np.flatnonzero(inverse == j)]
+        selected.append(alt_or_ref.loc[members].count(axis=1).idxmax())
+    return selected
+
+
+def pattern_representatives(alt_or_ref, submatrix, informative):
+    """One SNV per distinct presence/absence pattern among the informative rows of the column window (scSplit:291-296):
+    the row observed in most clusters of the ORIGINAL matrix, the first such row on ties.
+
+    The reference groups the rows by the concatenated text of their values and looks every group up again by label; the
+    informative rows are fully observed rows of a 0/1 matrix, so the pattern is an integer (one bit per cluster) and the
+    representative of every pattern is the head of its group after one sort by (pattern, observed clusters descending,
+    row position) -- the only step of the selection whose cost grows with the number of SNVs.  Frames that are not 0/1
+    or whose labels repeat (label look-ups would then return several rows) are grouped the reference's way.
+    """
+    pos = np.flatnonzero(informative)
+    vals = submatrix.values[pos]
+    if vals.shape[1] > 62 or not alt_or_ref.index.is_unique or not ((vals == 0) | (vals == 1)).all():
+        return _representatives_by_text(alt_or_ref, submatrix, informative)
+    key = (vals.astype(np.int64) << np.arange(vals.shape[1], dtype=np.int64)).sum(axis=1)
+    observed = alt_or_ref.count(axis=1).values[pos]
+    order = np.lexsort((pos, -observed, key))
+    heads = order[np.concatenate(([True], key[order][1:] != key[order][:-1]))]
+    return alt_or_ref.index[pos[heads]].tolist()
+
+
 def select_distinguishing(alt_or_ref, num, ncols):
     """Variant selection of scSplit:284-333 on the ternary matrix (rows = SNVs, columns = non-doublet clusters).
 
@@ -256,16 +289,9 @@ def select_distinguishing(alt_or_ref, num, ncols):
     while len(dist_variants) < num - 1:
         found, todo = [], []
         while len(found) < ncols - 1:
-            selected = []
-            informative_sub = submatrix[(_row_var(submatrix) > 0) & (submatrix.count(axis=1) == ncols)]
-            if informative_sub.index.values.size > 0:
-                patt = informative_sub.astype(str).values.sum(axis=1)
-                unq = np.unique(patt, return_inverse=True)
-                inverse = np.asarray(unq[1]).ravel()
-                for j in range(len(unq[0])):
-                    members = informative_sub.index[np.flatnonzero(inverse == j)]
-                    # per pattern: the row with most observed clusters in the ORIGINAL matrix, first on ties
-                    selected.append(alt_or_ref.loc[members].count(axis=1).idxmax())
+            informative = ((_row_var(submatrix) > 0) & (submatrix.count(axis=1) == ncols)).values
+            if informative.any():
+                selected = pattern_representatives(alt_or_ref, submatrix, informative)
                 subt = submatrix.reindex(np.unique(selected)).iloc[:, 0:ncols]
                 subt = subt.fillna(-1)
                 d = np.linalg.svd(subt, full_matrices=False)[1]
@@ -281,10 +307,10 @@ def select_distinguishing(alt_or_ref, num, ncols):
                         Vinv = np.linalg.solve(Vt, np.diag([1] * len(Vt)))
                         Dinv = np.linalg.solve(D, np.diag([1] * len(D)))
                         proj = np.asmatrix(np.zeros((colU, subt.shape[0])))
+                        rows = np.ascontiguousarray(subt.values, dtype=np.float64)
                         for j in range(subt.shape[0]):
-                            row = subt.iloc[j]
                             for i in range(colU):
-                                proj[i, j] = np.dot(U[:, i], row)
+                                proj[i, j] = np.dot(U[:, i], rows[j])
                         Wc = np.dot(np.dot(Vinv, Dinv), proj)
                         R = np.dot(basis, Wc)
                         diff = (subt.transpose() - R).transpose()

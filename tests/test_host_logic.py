@@ -184,3 +184,85 @@ def test_fixed_point_format_helpers():
     L = -np.array(want, dtype=np.float64) * 2.0 ** -F
     exact = (cnt[:, None].astype(np.float64) * x).sum(axis=0)
     assert np.allclose(L, exact, rtol=1e-12, atol=0)
+
+
+def _same_bytes(frame, tmp_path, float_format=None, native=True):
+    from scsplit_b200 import cli
+    a, b = str(tmp_path / "fast.csv"), str(tmp_path / "pandas.csv")
+    assert cli.frame_to_csv(frame, a, float_format=float_format) == native
+    frame.to_csv(b, float_format=float_format)
+    got, want = open(a, "rb").read(), open(b, "rb").read()
+    if got != want:
+        for i, (x, y) in enumerate(zip(got.split(b"\n"), want.split(b"\n"))):
+            assert x == y, "line %d: %r vs %r" % (i, x[:200], y[:200])
+    assert got == want
+
+
+def test_float_writer_equals_pandas_to_csv(tmp_path):
+    """csrc/csv.cu `scs_csv_write_f64` against DataFrame.to_csv, byte for byte, in the two forms the reference uses:
+    P_s_c.to_csv(path) (scSplit:596, shortest round-trip floats) and pa_matrix.to_csv(path, float_format='%.0f')
+    (scSplit:599-600)."""
+    rng = np.random.default_rng(11)
+    # every exponent, random mantissas (denormals included), both signs
+    bits = rng.integers(0, 2**63, 60000, dtype=np.uint64) | (rng.integers(0, 2, 60000).astype(np.uint64) << np.uint64(63))
+    vals = bits.view(np.float64).copy()
+    special = [0.0, -0.0, 1.0, -1.0, 0.5, 0.1, 0.99, 1 - 1e-13, 1e-4, 9.999e-5, 1e-5, 1.5e-5, 1e15, 1e16, 9999999999999998.0,
+               1.2345678901234567e16, 123456789012345678.0, 1e22, 1e23, 1e100, 1e-100, 1.5e300, 5e-324, 2.2250738585072014e-308,
+               1.7976931348623157e308, np.inf, -np.inf, np.nan, 3.0, 1234.5, 100.0, 1e-300, 0.3333333333333333, 2 / 3, 1e-40]
+    vals[:len(special)] = special
+    vals[100:200] = rng.integers(-10**9, 10**9, 100).astype(np.float64)              # integral values print as "x.0"
+    vals[200:5000] = 2.0 ** rng.uniform(-60, 60, 4800)                               # the everyday range
+    vals[5000:9000] = rng.random(4000)
+    frame = pd.DataFrame(vals.reshape(-1, 6), index=["BC%06d-1" % i for i in range(10000)], columns=range(6))
+    _same_bytes(frame, tmp_path)
+    # saturated posteriors as `scSplit run` writes them, index named, string column labels
+    W = np.full((3000, 9), 1e-250) * rng.random((3000, 9))
+    W[np.arange(3000), rng.integers(0, 9, 3000)] = 1 - rng.integers(0, 50, 3000) * 2.0 ** -53
+    W[5] = np.nan
+    named = pd.DataFrame(W, index=pd.Index(["c%d" % i for i in range(3000)], name="Barcode"), columns=[str(c) for c in range(9)])
+    _same_bytes(named, tmp_path)
+    # the ternary P/A matrix: 0, 1, NaN with '%.0f'; then arbitrary values through the same format
+    pa = rng.choice([0.0, 1.0, np.nan], size=(4000, 8), p=[0.5, 0.4, 0.1])
+    snv = ["%d:%d" % (1 + i % 22, 1000 + i) for i in range(4000)]
+    _same_bytes(pd.DataFrame(pa, index=snv, columns=[0, 1, 2, 3, 5, 6, 7, 8]), tmp_path, "%.0f")
+    odd = np.array([0.5, 1.5, 2.5, -0.4, -0.5, -0.0, 1e20, 123456.789, np.inf, -np.inf, np.nan, 1e300, 0.49999999999999994, 7.0, -3.5, 1e-9])
+    _same_bytes(pd.DataFrame(odd.reshape(4, 4), index=list("abcd"), columns=range(4)), tmp_path, "%.0f")
+    # empty frames (no distinguishing variants found) and frames the writer leaves to pandas
+    _same_bytes(pd.DataFrame(pa[:0], index=[], columns=range(8)), tmp_path, "%.0f")
+    _same_bytes(pd.DataFrame(pa[:0], index=pd.Index([], dtype=object), columns=range(8)), tmp_path)
+    _same_bytes(pd.DataFrame(pa[:3], index=['a,b', 'c"d', 'e'], columns=range(8)), tmp_path, "%.0f", native=False)
+    _same_bytes(pd.DataFrame(pa[:3], index=[1, 2, 3], columns=range(8)), tmp_path, native=False)
+    _same_bytes(pd.DataFrame({"x": [1, 2], "y": [0.5, np.nan]}, index=["a", "b"]), tmp_path, native=False)
+    _same_bytes(pd.DataFrame(pa[:2], index=["a", np.nan], columns=range(8)), tmp_path, native=False)
+    _same_bytes(pd.DataFrame(pa[:2], index=["a", "b"], columns=range(8)), tmp_path, "%.3f", native=False)
+
+
+def test_pattern_representatives_equal_the_text_grouping(monkeypatch):
+    """models.pattern_representatives (integer patterns, one sort) against the reference's grouping by concatenated value
+    text with a label look-up per group (scSplit:291-296, kept as models._representatives_by_text): same representatives on
+    random ternary matrices, and the same distinguishing variants from the whole selection with either of them."""
+    from scsplit_b200 import models as M
+    rng = np.random.default_rng(5)
+    cwd_note = os.path.join(os.getcwd(), "scSplit_dist_variants.txt")
+    for trial in range(12):
+        rows, cols = int(rng.integers(40, 1500)), int(rng.integers(2, 9))
+        p_nan = float(rng.choice([0.0, 0.05, 0.3]))
+        vals = rng.choice([0.0, 1.0, np.nan], size=(rows, cols), p=[(1 - p_nan) * 0.6, (1 - p_nan) * 0.4, p_nan])
+        frame = pd.DataFrame(vals, index=["%d:%d" % (1 + i % 22, 1000 + i) for i in range(rows)], columns=range(cols))
+        for width in range(cols, 1, -1):
+            sub = frame.iloc[:, 0:width]
+            informative = ((sub.var(axis=1) > 0) & (sub.count(axis=1) == width)).values
+            if not informative.any():
+                continue
+            assert sorted(M.pattern_representatives(frame, sub, informative)) == sorted(M._representatives_by_text(frame, sub, informative))
+        fast = M.select_distinguishing(frame, cols + 1, cols)
+        with monkeypatch.context() as mp:
+            mp.setattr(M, "pattern_representatives", M._representatives_by_text)
+            slow = M.select_distinguishing(frame, cols + 1, cols)
+        assert fast == slow
+    # repeated labels and values other than 0 / 1 take the text grouping itself
+    dup = pd.DataFrame(rng.choice([0.0, 1.0], size=(30, 3)), index=["1:%d" % (i % 20) for i in range(30)], columns=range(3))
+    inf = (dup.var(axis=1) > 0).values
+    assert sorted(map(str, M.pattern_representatives(dup, dup, inf))) == sorted(map(str, M._representatives_by_text(dup, dup, inf)))
+    if os.path.exists(cwd_note):
+        os.remove(cwd_note)
