@@ -78,9 +78,6 @@ def elbow(points):
     return e
 
 
-_NEEDS_QUOTING = (',', '"', '\n', '\r')
-
-
 def frame_to_csv(frame, path, float_format=None):
     """`frame.to_csv(path)` / `frame.to_csv(path, float_format='%.0f')` (scSplit:596, 599-600), byte for byte, through the
     library's float writer (`scs_csv_write_f64`) instead of one Python string object per value; frames it does not cover
@@ -92,17 +89,21 @@ def frame_to_csv(frame, path, float_format=None):
     plain = (float_format in (None, '%.0f') and index.nlevels == 1 and columns.nlevels == 1 and len(columns) > 0
              and (index.name is None or isinstance(index.name, str))
              and all(dt == np.float64 for dt in frame.dtypes)
-             and all(isinstance(c, (int, np.integer, str)) and not isinstance(c, (bool, np.bool_)) for c in columns)
-             and all(isinstance(x, str) for x in index))
+             and all(isinstance(c, (int, np.integer, str)) and not isinstance(c, (bool, np.bool_)) for c in columns))
     if plain:
-        head = [index.name or ''] + [str(c) for c in columns]
-        plain = not any(ch in x for x in head + list(index) for ch in _NEEDS_QUOTING)
+        rows = index.tolist()
+        head = ','.join([index.name or ''] + [str(c) for c in columns])
+        plain = all(type(x) is str for x in rows)
+    if plain:
+        labels = '\n'.join(rows) + '\n' if rows else ''
+        # a label holding a separator, a quote or a line break would be quoted by pandas: leave those frames to it
+        plain = (labels.count('\n') == len(rows) and head.count(',') == len(columns)
+                 and not any(ch in text for text in (labels, head) for ch in ('"', '\r')) and ',' not in labels and '\n' not in head)
     if not plain:
         frame.to_csv(path, float_format=float_format)
         return False
-    labels = ''.join(x + '\n' for x in index)
     values = np.ascontiguousarray(frame.values, dtype=np.float64)
-    _lib.check(_lib.load().scs_csv_write_f64(os.fsencode(path), ','.join(head).encode(), labels.encode(), len(index), len(columns),
+    _lib.check(_lib.load().scs_csv_write_f64(os.fsencode(path), head.encode(), labels.encode(), len(rows), len(columns),
                                              values.ctypes.data_as(ctypes.c_void_p), 0 if float_format is None else 1))
     return True
 
