@@ -11,6 +11,13 @@ def _ptr(a):
     return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
 
 
+def _expect(a, shape, name):
+    """The library reads plain pointers of implied length: a wrong shape must stop here, not read past the buffer."""
+    if a.shape != tuple(shape):
+        raise ValueError("%s has shape %r, expected %r" % (name, a.shape, tuple(shape)))
+    return a
+
+
 def _canonical_csr(m):
     """scipy CSR with sorted, duplicate-free indices and no explicit zeros (what csr_matrix(dense) gives, scSplit:546)."""
     from scipy.sparse import csr_matrix
@@ -102,6 +109,8 @@ class Engine:
     def seed_af(self, labels, K):
         labels = np.ascontiguousarray(labels, dtype=np.int32)
         single = labels.ndim == 1
+        if labels.ndim > 2 or labels.shape[-1] != self.N:
+            raise ValueError("labels must be [N] or [R][N] with N = %d cells (got %r)" % (self.N, labels.shape))
         labels = labels.reshape(-1, self.N)
         R = labels.shape[0]
         out = np.empty((R, self.V, K), dtype=np.float64)
@@ -109,8 +118,8 @@ class Engine:
         return out[0] if single else out
 
     def pattern_counts(self, keep_rows=None, keep_cols=None):
-        kr = None if keep_rows is None else np.ascontiguousarray(keep_rows, dtype=np.uint8)
-        kc = None if keep_cols is None else np.ascontiguousarray(keep_cols, dtype=np.uint8)
+        kr = None if keep_rows is None else _expect(np.ascontiguousarray(keep_rows, dtype=np.uint8), (self.V,), "keep_rows")
+        kc = None if keep_cols is None else _expect(np.ascontiguousarray(keep_cols, dtype=np.uint8), (self.N,), "keep_cols")
         rc = np.empty(self.V, dtype=np.int64)
         cc = np.empty(self.N, dtype=np.int64)
         check(self.lib.scs_pattern_counts(self.h, _ptr(kr), _ptr(kc), _ptr(rc), _ptr(cc)))
@@ -200,20 +209,26 @@ class Engine:
     # -- post-EM
     def doublet_scores(self, P, mask):
         P = np.ascontiguousarray(P, dtype=np.float64)
-        mask = np.ascontiguousarray(mask, dtype=np.uint8)
+        if P.ndim != 2:
+            raise ValueError("P must be a V x K matrix")
+        _expect(P, (self.V, P.shape[1]), "P")
+        mask = _expect(np.ascontiguousarray(mask, dtype=np.uint8), (self.N,), "mask")
         out = np.empty(P.shape[1], dtype=np.float64)
         check(self.lib.scs_doublet_scores(self.h, P.shape[1], _ptr(P), _ptr(mask), _ptr(out)))
         return out
 
     def refine_scores(self, P, labels):
         P = np.ascontiguousarray(P, dtype=np.float64)
-        labels = np.ascontiguousarray(labels, dtype=np.int32)
+        if P.ndim != 2:
+            raise ValueError("P must be a V x K matrix")
+        _expect(P, (self.V, P.shape[1]), "P")
+        labels = _expect(np.ascontiguousarray(labels, dtype=np.int32), (self.N,), "labels")
         out = np.empty(self.N, dtype=np.float64)
         check(self.lib.scs_refine_scores(self.h, P.shape[1], _ptr(P), _ptr(labels), _ptr(out)))
         return out
 
     def cluster_counts(self, labels, K):
-        labels = np.ascontiguousarray(labels, dtype=np.int32)
+        labels = _expect(np.ascontiguousarray(labels, dtype=np.int32), (self.N,), "labels")
         n_ref = np.empty((self.V, K), dtype=np.int64)
         n_alt = np.empty((self.V, K), dtype=np.int64)
         pa = np.empty((self.V, K), dtype=np.int8)
@@ -228,7 +243,7 @@ class Engine:
         return buf
 
     def comm_init(self, uid, rank, world):
-        uid = np.ascontiguousarray(uid, dtype=np.uint8)
+        uid = _expect(np.ascontiguousarray(uid, dtype=np.uint8), (128,), "uid")
         check(self.lib.scs_comm_init(self.h, _ptr(uid), int(rank), int(world)))
 
     # -- instrumentation

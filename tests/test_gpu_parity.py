@@ -318,6 +318,15 @@ def test_errors(E):
             eng.em_begin(np.full((int(g["V"]), 40), 0.5))  # K > SCS_MAX_K
         with pytest.raises(ValueError):
             eng.em_begin(np.full((5, 3), 0.5))             # wrong V
+        # arrays of the wrong length stop at the Python boundary (the C-ABI takes plain pointers of implied length)
+        V, N = int(g["V"]), int(g["N"])
+        for call in (lambda: eng.pattern_counts(np.ones(V - 1, np.uint8), None), lambda: eng.pattern_counts(None, np.ones(N + 1, np.uint8)),
+                     lambda: eng.seed_af(np.zeros(N - 1, np.int32), 3), lambda: eng.doublet_scores(np.full((V, 3), 0.5), np.ones(N - 1, np.uint8)),
+                     lambda: eng.doublet_scores(np.full((V + 1, 3), 0.5), np.ones(N, np.uint8)),
+                     lambda: eng.refine_scores(np.full((V, 3), 0.5), np.zeros(N + 2, np.int32)),
+                     lambda: eng.cluster_counts(np.zeros(N - 1, np.int32), 3)):
+            with pytest.raises(ValueError):
+                call()
     empty = csr_matrix((int(g["V"]), int(g["N"])), dtype=np.int16)
     with E(empty, empty) as eng:                           # all-zero input is legal: k_alt = 1/2 everywhere
         assert np.array_equal(eng.kalt(), np.full(int(g["V"]), 0.5))
