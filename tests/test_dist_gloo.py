@@ -1,5 +1,6 @@
 """world_size-2 gloo tests (CPU) of the multi-GPU host logic: shard plans, the packed statistics buffer that is
-all-reduced per M-step, the unique-id broadcast and the best-restart selection.  The arithmetic on each fake rank is
+all-reduced per M-step, the unique-id broadcast, the best-restart selection, and the drop-in's restart driver
+(models.core_batched) sharded over two ranks.  The arithmetic on each fake rank is
 the CPU oracle's (test infrastructure); the product's ranks run the same plan with the CUDA kernels + NCCL."""
 import os
 import sys
@@ -93,3 +94,127 @@ def test_shard_plans():
     assert D.select_best([None, None]) is None
     lay = D.stats_layout(30000, 9)
     assert lay["KP"] == 10 and lay["size"] == 2 * 30000 * 10 + 10 + 2        # 4.8 MB all-reduce payload at config 3
+
+
+# ---- the drop-in's restart driver under a process group (scSplit:470-490 sharded over ranks) --------------------------------
+
+class _OracleEngine:
+    """Host stand-in for scsplit_b200.engine.Engine, for driving models.core_batched on CPU ranks: the same methods, the
+    arithmetic is the CPU oracle's (test infrastructure; the product's ranks hold a CUDA engine each)."""
+
+    def __init__(self, ref, alt):
+        from conftest import scipy_count_fn
+        from oracle import em_oracle as O
+        self.O, self.ref, self.alt = O, ref, alt
+        self.V, self.N = ref.shape
+        self.h = 1
+        self._counts = scipy_count_fn(ref, alt)
+        self._kalt = O.kalt(ref, alt)
+        self.begun = []                                   # restarts per em_begin call, for the test to look at
+
+    def close(self):
+        self.h = None
+
+    def kalt(self):
+        return self._kalt
+
+    def pattern_counts(self, keep_rows=None, keep_cols=None):
+        return self._counts(keep_rows, keep_cols)
+
+    def seed_af(self, labels, K):
+        labels = np.asarray(labels)
+        if labels.ndim == 1:
+            return self.O.seed_af(self.ref, self.alt, self._kalt, labels, K)
+        return np.stack([self.O.seed_af(self.ref, self.alt, self._kalt, lab, K) for lab in labels])
+
+    def em_footprint(self, K):
+        return 1, 10 ** 12
+
+    def em_begin(self, P0):
+        self.P0 = P0 if P0.ndim == 3 else P0[None]
+        self.begun.append(len(self.P0))
+
+    def em_run(self):
+        self.res = [self.O.run_em(self.ref, self.alt, p, self._kalt) for p in self.P0]
+
+    def em_status(self):
+        return (np.array([r["iters"] for r in self.res], dtype=np.int32), np.array([r["convergence"] for r in self.res], dtype=np.int32),
+                np.array([r["LL"] for r in self.res], dtype=np.float64))
+
+    def get(self, what, restart=0):
+        r = self.res[restart]
+        if what == 4:
+            return np.asarray(r["hist"] + [0.0] * (300 - len(r["hist"])), dtype=np.float64)
+        return np.asarray({0: r["P"], 1: r["W"], 2: r["L"], 3: r["lPs"]}[what], dtype=np.float64)
+
+
+def _run_core(name, ems, out_dir):
+    """models.core_batched on the golden pool `name` with the oracle engine; returns what rank 0 (or the only process) got."""
+    import pandas as pd
+    from scsplit_b200 import models as M
+    g = load_golden(name)
+    mtx = [g["ref"], g["alt"], pd.Index(["1:%d" % (1000 + v) for v in range(g["ref"].shape[0])]),
+           pd.Index(["BC%05d-1" % c for c in range(g["ref"].shape[1])])]
+    eng = _OracleEngine(g["ref"], g["alt"])
+    real = M.get_engine
+    M.get_engine = lambda base_calls_mtx, device=0: eng
+    try:
+        np.random.seed(int(g["seed"]))
+        model, best = M.core_batched(mtx, g["K"], out_dir, ems)
+    finally:
+        M.get_engine = real
+    return model, best, eng
+
+
+def _core_worker(rank, world, port, name, ems, out_dir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rank_dir = os.path.join(out_dir, "rank%d" % rank)
+        os.makedirs(rank_dir)
+        model, best, eng = _run_core(name, ems, rank_dir)
+        assert sum(eng.begun) == len(range(rank, ems, world))          # this rank ran its share of the restarts, nothing else
+        np.save(os.path.join(out_dir, "best_%d.npy" % rank), np.array([best]))
+        if rank == 0:
+            np.savez(os.path.join(out_dir, "rank0.npz"), W=model.P_s_c.values, P=model.model_af.values, L=model.lP_c_s.values,
+                     lP_c_m=model.lP_c_m, assigned=np.array([len(a) for a in model.assigned]),
+                     first=np.array([a[0] if a else "" for a in model.assigned], dtype=str),
+                     initial=np.array([",".join(i) for i in model.initial], dtype=str))
+            assert os.path.exists(os.path.join(rank_dir, "scSplit.log"))
+        else:
+            assert model is None                                         # only rank 0 returns the populated model
+            assert not os.path.exists(os.path.join(rank_dir, "scSplit.log"))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("name,ems", [("k4_dnone", 5), ("k3_ragged", 4)])
+def test_restart_driver_sharded_over_two_ranks_equals_one_process(name, ems, tmp_path):
+    """models.core_batched under torchrun semantics (world 2, gloo): rank 0 draws every initialisation and broadcasts the
+    labels, the ranks run restarts r, r + 2, ..., the reference's selection rule (scSplit:482-484) runs on the gathered LLs,
+    the winner and the last restart's arrays travel to rank 0 -- whose model must equal, bit for bit, the one a single
+    process builds from the same seed."""
+    import torch.multiprocessing as mp
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_core_worker, args=(2, port, name, ems, str(tmp_path)), nprocs=2, join=True)
+    solo_dir = tmp_path / "solo"
+    solo_dir.mkdir()
+    model, best, eng = _run_core(name, ems, str(solo_dir))
+    assert sum(eng.begun) == ems
+    got = np.load(tmp_path / "rank0.npz")
+    assert int(np.load(tmp_path / "best_0.npy")[0]) == best == int(np.load(tmp_path / "best_1.npy")[0])
+    assert np.array_equal(got["W"], model.P_s_c.values, equal_nan=True)
+    assert np.array_equal(got["P"], model.model_af.values, equal_nan=True)
+    assert np.array_equal(got["L"], model.lP_c_s.values, equal_nan=True)
+    assert float(got["lP_c_m"]) == model.lP_c_m
+    assert got["assigned"].tolist() == [len(a) for a in model.assigned]
+    assert got["first"].tolist() == [a[0] if a else "" for a in model.assigned]
+    assert got["initial"].tolist() == [",".join(i) for i in model.initial]
+    # the log of rank 0 lists every restart and every log-likelihood, like the single process's
+    log2, log1 = open(tmp_path / "rank0" / "scSplit.log").read(), open(solo_dir / "scSplit.log").read()
+    assert log2.count("Model Log-Likelihood = ") == log1.count("Model Log-Likelihood = ") == ems
+    assert [l for l in log2.splitlines() if l.startswith("Model Log")] == [l for l in log1.splitlines() if l.startswith("Model Log")]
