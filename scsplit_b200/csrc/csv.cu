@@ -13,6 +13,7 @@
 #include <charconv>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <thread>
@@ -20,27 +21,55 @@
 
 #include "common.cuh"
 
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
+
+namespace {
+
+// the non-zero fields one parser thread found in its share of the rows (grown by realloc: big blocks are remapped, not copied)
+struct Entries {
+    int32_t* idx = nullptr;
+    int32_t* val = nullptr;
+    size_t n = 0, cap = 0;
+    Entries() = default;
+    Entries(const Entries&) = delete;
+    Entries& operator=(const Entries&) = delete;
+    ~Entries() { free(idx); free(val); }
+    bool reserve(size_t extra) {
+        if (n + extra <= cap) return true;
+        const size_t want = std::max<size_t>(cap * 2, std::max<size_t>(n + extra, (size_t)1 << 16));
+        int32_t* a = (int32_t*)realloc(idx, want * sizeof(int32_t));
+        if (a) idx = a;
+        int32_t* b = (int32_t*)realloc(val, want * sizeof(int32_t));
+        if (b) val = b;
+        if (!a || !b) return false;
+        cap = want;
+        return true;
+    }
+};
+
+struct Chunk {
+    const char* b = nullptr;
+    const char* e = nullptr;
+    std::vector<int64_t> row_nnz;
+    Entries ent;
+    std::string ids;
+    int err = 0;          // 1 = not a plain non-negative integer field, 2 = wrong number of fields, 3 = count overflow, 4 = out of memory
+    int64_t err_row = 0;
+};
+
+}  // namespace
+
 struct scs_csv {
     int64_t V = 0, N = 0, nnz = 0;
     std::string header_first;            // name of the index column ("SNV")
     std::string barcodes;                // '\n'-joined
     std::string ids;                     // '\n'-joined
-    std::vector<int64_t> indptr;
-    std::vector<int32_t> indices;
-    std::vector<int32_t> data;
+    std::vector<Chunk> chunks;           // the rows in file order, one share per parser thread; merged by scs_csv_fetch
 };
 
 namespace {
-
-struct Chunk {
-    const char* b;
-    const char* e;
-    std::vector<int64_t> row_nnz;
-    std::vector<int32_t> idx, val;
-    std::string ids;
-    int err = 0;          // 1 = not a plain non-negative integer field, 2 = wrong number of fields, 3 = count overflow
-    int64_t err_row = 0;
-};
 
 void parse_chunk(Chunk* c, int64_t ncols) {
     const char* p = c->b;
@@ -56,8 +85,43 @@ void parse_chunk(Chunk* c, int64_t ncols) {
         c->ids.append(p, (size_t)(q - p));
         c->ids.push_back('\n');
         ++q;
-        int64_t col = 0, nz = 0;
+        int64_t col = 0;
+        const size_t n0 = c->ent.n;
         while (true) {
+            // Count matrices are ~95 % zeros and nearly all counts have one digit.  Sixteen bytes = eight fields "d," at a time:
+            // one comparison says whether the block has that shape, a bit mask says which of its fields are not "0".  Rows of
+            // other shapes, and always the last field of a line, take the general code below.
+#if defined(__SSE2__)
+            while (q + 16 < le) {
+                const __m128i v = _mm_loadu_si128((const __m128i*)q);
+                const int commas = _mm_movemask_epi8(_mm_cmpeq_epi8(v, _mm_set1_epi8(',')));
+                const __m128i d = _mm_sub_epi8(v, _mm_set1_epi8('0'));
+                const int digits = _mm_movemask_epi8(_mm_cmpeq_epi8(_mm_subs_epu8(d, _mm_set1_epi8(9)), _mm_setzero_si128()));
+                if ((commas & 0xAAAA) != 0xAAAA || (digits & 0x5555) != 0x5555) break;
+                int nzm = ~_mm_movemask_epi8(_mm_cmpeq_epi8(d, _mm_setzero_si128())) & 0x5555;
+                if (nzm) {
+                    if (!c->ent.reserve(8)) { c->err = 4; c->err_row = row; return; }
+                    do {
+                        const int b = __builtin_ctz((unsigned)nzm);
+                        c->ent.idx[c->ent.n] = (int32_t)(col + (b >> 1));
+                        c->ent.val[c->ent.n++] = (int32_t)(q[b] - '0');
+                        nzm &= nzm - 1;
+                    } while (nzm);
+                }
+                col += 8;
+                q += 16;
+            }
+#endif
+            if (q + 2 < le && q[1] == ',' && q[0] >= '0' && q[0] <= '9') {       // one single-digit field
+                if (q[0] != '0') {
+                    if (!c->ent.reserve(1)) { c->err = 4; c->err_row = row; return; }
+                    c->ent.idx[c->ent.n] = (int32_t)col;
+                    c->ent.val[c->ent.n++] = (int32_t)(q[0] - '0');
+                }
+                ++col;
+                q += 2;
+                continue;
+            }
             while (q < le && (*q == ' ' || *q == '\t')) ++q;
             int64_t v = 0;
             const char* s = q;
@@ -69,14 +133,18 @@ void parse_chunk(Chunk* c, int64_t ncols) {
             if (q == s) { c->err = 1; c->err_row = row; return; }   // empty, negative, float, quoted ...
             while (q < le && (*q == ' ' || *q == '\t')) ++q;
             if (q < le && *q != ',') { c->err = 1; c->err_row = row; return; }
-            if (v) { c->idx.push_back((int32_t)col); c->val.push_back((int32_t)v); ++nz; }
+            if (v) {
+                if (!c->ent.reserve(1)) { c->err = 4; c->err_row = row; return; }
+                c->ent.idx[c->ent.n] = (int32_t)col;
+                c->ent.val[c->ent.n++] = (int32_t)v;
+            }
             ++col;
             if (q >= le) break;
             ++q;                                                   // the comma
             if (q >= le) { c->err = 1; c->err_row = row; return; }  // trailing comma = empty last field
         }
         if (col != ncols) { c->err = 2; c->err_row = row; return; }
-        c->row_nnz.push_back(nz);
+        c->row_nnz.push_back((int64_t)(c->ent.n - n0));
         ++row;
         p = line_end + 1;
     }
@@ -197,7 +265,8 @@ int scs_csv_parse(const char* path, int threads, scs_csv** out) {
         int nt = threads > 0 ? threads : (int)std::thread::hardware_concurrency();
         nt = std::max(1, std::min(nt, 64));
         if ((size_t)(end - body) < (size_t)(1 << 20)) nt = 1;
-        std::vector<Chunk> chunks((size_t)nt);
+        std::vector<Chunk>& chunks = c->chunks;
+        chunks = std::vector<Chunk>((size_t)nt);
         const char* cur = body;
         for (int i = 0; i < nt; ++i) {
             const char* stop = (i == nt - 1) ? end : body + (size_t)(end - body) / nt * (i + 1);
@@ -218,29 +287,21 @@ int scs_csv_parse(const char* path, int threads, scs_csv** out) {
         for (auto& ch : chunks) {
             if (ch.err) {
                 set_error("%s: data row %lld: %s", path, (long long)(V + ch.err_row + 1),
-                          ch.err == 1 ? "field is not a plain non-negative integer" : ch.err == 2 ? "wrong number of fields" : "count exceeds int32");
+                          ch.err == 1 ? "field is not a plain non-negative integer" : ch.err == 2 ? "wrong number of fields"
+                          : ch.err == 3 ? "count exceeds int32" : "out of memory");
                 rc = ch.err == 1 ? 2 : 1;   // 2 = declined (a general CSV reader may still accept it), 1 = malformed
                 break;
             }
             V += (int64_t)ch.row_nnz.size();
-            nnz += (int64_t)ch.idx.size();
+            nnz += (int64_t)ch.ent.n;
+            ch.b = ch.e = nullptr;          // the mapping goes away below
         }
         if (rc) break;
         c->V = V;
         c->nnz = nnz;
-        c->indptr.resize((size_t)V + 1);
-        c->indices.resize((size_t)nnz);
-        c->data.resize((size_t)nnz);
-        int64_t r = 0, z = 0;
-        c->indptr[0] = 0;
         for (auto& ch : chunks) {
-            for (int64_t k : ch.row_nnz) { c->indptr[(size_t)r + 1] = c->indptr[(size_t)r] + k; ++r; }
-            if (!ch.idx.empty()) {
-                memcpy(c->indices.data() + z, ch.idx.data(), ch.idx.size() * 4);
-                memcpy(c->data.data() + z, ch.val.data(), ch.val.size() * 4);
-                z += (int64_t)ch.idx.size();
-            }
             c->ids += ch.ids;
+            std::string().swap(ch.ids);
         }
     } while (false);
     munmap((void*)base, size);
@@ -257,9 +318,27 @@ int scs_csv_shape(scs_csv* c, int64_t out[5]) {
 
 int scs_csv_fetch(scs_csv* c, int64_t* indptr, int32_t* indices, int32_t* data, char* ids, char* barcodes) {
     SCS_CHECK(c, "null argument");
-    if (indptr) memcpy(indptr, c->indptr.data(), c->indptr.size() * 8);
-    if (indices && c->nnz) memcpy(indices, c->indices.data(), (size_t)c->nnz * 4);
-    if (data && c->nnz) memcpy(data, c->data.data(), (size_t)c->nnz * 4);
+    // every parser thread's share goes straight into the caller's arrays (its rows and entries start where the shares before it end)
+    std::vector<int64_t> row0(c->chunks.size() + 1, 0), ent0(c->chunks.size() + 1, 0);
+    for (size_t i = 0; i < c->chunks.size(); ++i) {
+        row0[i + 1] = row0[i] + (int64_t)c->chunks[i].row_nnz.size();
+        ent0[i + 1] = ent0[i] + (int64_t)c->chunks[i].ent.n;
+    }
+    auto place = [&](size_t i) {
+        const Chunk& ch = c->chunks[i];
+        if (indptr) {
+            int64_t at = ent0[i];
+            int64_t* o = indptr + row0[i];
+            for (int64_t k : ch.row_nnz) { *o++ = at; at += k; }
+        }
+        if (indices && ch.ent.n) memcpy(indices + ent0[i], ch.ent.idx, ch.ent.n * 4);
+        if (data && ch.ent.n) memcpy(data + ent0[i], ch.ent.val, ch.ent.n * 4);
+    };
+    std::vector<std::thread> pool;
+    for (size_t i = 1; i < c->chunks.size(); ++i) pool.emplace_back(place, i);
+    if (!c->chunks.empty()) place(0);
+    for (auto& t : pool) t.join();
+    if (indptr) indptr[c->V] = c->nnz;
     if (ids) memcpy(ids, c->ids.data(), c->ids.size());
     if (barcodes) memcpy(barcodes, c->barcodes.data(), c->barcodes.size());
     return 0;

@@ -266,3 +266,51 @@ def test_pattern_representatives_equal_the_text_grouping(monkeypatch):
     assert sorted(map(str, M.pattern_representatives(dup, dup, inf))) == sorted(map(str, M._representatives_by_text(dup, dup, inf)))
     if os.path.exists(cwd_note):
         os.remove(cwd_note)
+
+
+def test_csv_parser_block_path_on_random_files(tmp_path):
+    """The 16-byte block path of csrc/csv.cu (eight one-digit fields per step) against pd.read_csv on small random files:
+    every row width from 1 to 40 columns (line ends at every offset inside a block), counts of several digits, leading
+    zeros, blanks, CRLF, no newline at the end; malformed rows are refused, not misread."""
+    from scipy.sparse import csr_matrix
+    from scsplit_b200 import cli
+    from scsplit_b200._lib import ScsError
+    rng = np.random.default_rng(21)
+    for trial in range(60):
+        ncols, nrows = int(rng.integers(1, 41)), int(rng.integers(1, 30))
+        vals = rng.choice([0, 0, 0, 0, 0, 0, 0, 1, 2, 9, 10, 37, 2000, 123456], size=(nrows, ncols))
+        if trial % 5 == 0:
+            vals[:] = rng.integers(0, 10, size=vals.shape) * (rng.random(vals.shape) < 0.3)      # one-digit fields only
+        lines = ["SNV," + ",".join("c%d" % j for j in range(ncols))]
+        for i in range(nrows):
+            fields = [str(int(v)) for v in vals[i]]
+            if trial % 7 == 3:
+                fields = [("0" + f if rng.random() < 0.2 else f) for f in fields]                  # "00", "07"
+            if trial % 7 == 5:
+                fields = [(" " + f + " " if rng.random() < 0.2 else f) for f in fields]
+            lines.append("%d:%d," % (1 + i % 22, 1000 + i) + ",".join(fields))
+        eol = "\r\n" if trial % 4 == 1 else "\n"
+        text = eol.join(lines) + (eol if trial % 3 else "")
+        path = str(tmp_path / ("r%d.csv" % trial))
+        open(path, "w", newline="").write(text)
+        got, idx, cols = cli.read_count_csv(path, 1 + trial % 3)
+        assert got.shape == (nrows, ncols) and np.array_equal(got.toarray(), vals), trial
+        assert got.has_canonical_format and (got.data != 0).all()
+        assert idx.tolist() == ["%d:%d" % (1 + i % 22, 1000 + i) for i in range(nrows)] and cols.tolist() == ["c%d" % j for j in range(ncols)]
+    # malformed rows: a field too many / too few (also far inside a run of zeros), an empty field, a trailing comma
+    head = "SNV," + ",".join("c%d" % j for j in range(20)) + "\n"
+    good = "1:1," + ",".join(["0"] * 20) + "\n"
+    for bad in ("1:2," + ",".join(["0"] * 21), "1:2," + ",".join(["0"] * 19), "1:2," + ",".join(["0"] * 10 + [""] + ["0"] * 9),
+                "1:2," + ",".join(["0"] * 20) + ",", "1:2," + ",".join(["0"] * 19) + ","):
+        path = str(tmp_path / "bad.csv")
+        open(path, "w").write(head + good + bad + "\n" + good)
+        try:
+            got, _, _ = cli.read_count_csv(path)          # declined files go to pandas, which may accept an empty field as NaN
+        except (ScsError, Exception):
+            continue
+        want = pd.read_csv(path, header=0, index_col=0)
+        assert got.shape == want.shape and np.array_equal(np.nan_to_num(got.toarray(), nan=-1), np.nan_to_num(want.values.astype(float), nan=-1))
+    # counts beyond int32 are refused, never wrapped
+    open(str(tmp_path / "big.csv"), "w").write("SNV,a,b\n1:5,4294967297,0\n")
+    with pytest.raises(Exception):
+        cli.read_count_csv(str(tmp_path / "big.csv"))
