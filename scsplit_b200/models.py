@@ -58,7 +58,7 @@ def _log(output, text):
 class models:
     """Model state of one restart: SNVs, barcodes, P(s|c), log-likelihoods, allele-fraction model, assignments."""
 
-    def __init__(self, base_calls_mtx, num, output, device=0, _defer_seed=False):
+    def __init__(self, base_calls_mtx, num, output, device=0, _defer_seed=False, _trim=None):
         self.ref_bc_mtx, self.alt_bc_mtx = base_calls_mtx[0], base_calls_mtx[1]
         self.all_POS, self.barcodes = base_calls_mtx[2].tolist(), base_calls_mtx[3].tolist()
         self.num = num
@@ -76,8 +76,9 @@ class models:
         # background alt fraction (scSplit:100-103); (V,1) matrix like the reference's attribute
         self.k_alt = np.asmatrix(self.engine.kalt()).T
         # subset / PCA / KMeans initialisation: same np.random and argsort call sequence as scSplit:106-125
-        irows, icols, nrows, ncols = initialiser.trim_subset(self.engine.pattern_counts, len(self.all_POS),
-                                                             len(self.barcodes), self.num)
+        # (core_batched runs the trimming loops of all restarts first and hands each model its own: _trim)
+        irows, icols, nrows, ncols = _trim if _trim is not None else initialiser.trim_subset(
+            self.engine.pattern_counts, len(self.all_POS), len(self.barcodes), self.num)
         self._labels = initialiser.initial_labels(self.ref_bc_mtx, self.alt_bc_mtx, irows, icols, nrows, ncols, self.num)
         if self._labels is None:
             _log(output, 'Not enough informative cells to support model initialization. \n')
@@ -343,14 +344,65 @@ def _assign_lists(W, barcodes):
     return [sorted(bc[hit[:, n]].tolist()) for n in range(W.shape[1])]
 
 
-def _initialise(engine, base_calls_mtx, barcodes, num, output):
-    """The initialisation part of models.__init__ (scSplit:105-142) without the model's frames: (labels or None, initial lists)."""
-    irows, icols, nrows, ncols = initialiser.trim_subset(engine.pattern_counts, base_calls_mtx[0].shape[0], len(barcodes), num)
+def _labels_of_trim(base_calls_mtx, trim, barcodes, num, output):
+    """PCA / KMeans on a trimmed block (scSplit:126-142) without the model's frames: (labels or None, initial lists)."""
+    irows, icols, nrows, ncols = trim
     labels = initialiser.initial_labels(base_calls_mtx[0], base_calls_mtx[1], irows, icols, nrows, ncols, num)
     if labels is None:
         _log(output, 'Not enough informative cells to support model initialization. \n')
         return None, None
     return labels, [[barcodes[col] for col in icols[labels[icols] == n]] for n in range(num)]
+
+
+def _initialise(engine, base_calls_mtx, barcodes, num, output):
+    """The initialisation part of models.__init__ (scSplit:105-142) without the model's frames: (labels or None, initial lists)."""
+    trim = initialiser.trim_subset(engine.pattern_counts, base_calls_mtx[0].shape[0], len(barcodes), num)
+    return _labels_of_trim(base_calls_mtx, trim, barcodes, num, output)
+
+
+def _same_rng_state(a, b):
+    return a[0] == b[0] and a[2:] == b[2:] and np.array_equal(a[1], b[1])
+
+
+def _initialise_all(eng, base_calls_mtx, barcodes, num, output, ems, device):
+    """The `ems` initialisations of run.core (scSplit:473-477) on one shared `np.random` stream: (last model, labels, initial).
+
+    The reference alternates, per restart, the trimming loop (the only consumer of `np.random`: scSplit:113-114) and
+    StandardScaler / PCA / KMeans(random_state=0) on the surviving block.  Here the trimming loops of all restarts run
+    first, back to back on the stream, and the blocks are clustered afterwards: the loops need nothing of scikit-learn,
+    so they run while its modules are still being imported (cli.run loads them in a helper thread; after the count CSVs
+    that import is the longest single step of a run).  The order only matters if the clustering draws from `np.random`
+    as well (PCA's randomised solver on a large surviving block does): every block is therefore clustered from the
+    stream state its restart had in the reference's order, and the first clustering that moves the stream sends the
+    restarts after it back to the reference's alternating order, from the state it left.
+    """
+    V, N = base_calls_mtx[0].shape[0], len(barcodes)
+    trims, after = [], []
+    for i in range(ems):
+        trims.append(initialiser.trim_subset(eng.pattern_counts, V, N, num))
+        after.append(np.random.get_state())
+    model, labels, initial = None, [None] * ems, [None] * ems
+    ahead = True                                  # trims[i] / after[i] still are what the reference's order gives
+    for i in range(ems):
+        _log(output, 'Repeat ' + str(i + 1) + ' of ' + str(ems) + ' in demultiplexing ' + str(num) +
+             ' subpopulations (including doublets if expected)' + '\n')
+        _log(output, 'Building model... \n')
+        if ahead:
+            np.random.set_state(after[i])
+            trim = trims[i]
+        else:
+            trim = initialiser.trim_subset(eng.pattern_counts, V, N, num)
+        before = np.random.get_state()
+        if i == ems - 1:
+            model = models(base_calls_mtx, num, output, device=device, _defer_seed=True, _trim=trim)
+            labels[i], initial[i] = model._labels, getattr(model, 'initial', None)
+        else:
+            labels[i], initial[i] = _labels_of_trim(base_calls_mtx, trim, barcodes, num, output)
+        if ahead and not _same_rng_state(before, np.random.get_state()):
+            ahead = False
+    if ahead:
+        np.random.set_state(after[-1])
+    return model, labels, initial
 
 
 def _world():
@@ -398,15 +450,7 @@ def core_batched(base_calls_mtx, num, output, ems, device=0, chunk=64):
     eng = get_engine(base_calls_mtx, device)
     model, labels, initial = None, [None] * ems, [None] * ems
     if rank == 0:
-        for i in range(ems):
-            _log(output, 'Repeat ' + str(i + 1) + ' of ' + str(ems) + ' in demultiplexing ' + str(num) +
-                 ' subpopulations (including doublets if expected)' + '\n')
-            _log(output, 'Building model... \n')
-            if i == ems - 1:
-                model = models(base_calls_mtx, num, output, device=device, _defer_seed=True)
-                labels[i], initial[i] = model._labels, getattr(model, 'initial', None)
-            else:
-                labels[i], initial[i] = _initialise(eng, base_calls_mtx, barcodes, num, output)
+        model, labels, initial = _initialise_all(eng, base_calls_mtx, barcodes, num, output, ems, device)
     if world > 1:
         lab = np.full((ems, N), -2, dtype=np.int32)          # -2 rows: restarts whose initialisation failed
         if rank == 0:

@@ -218,3 +218,41 @@ def test_restart_driver_sharded_over_two_ranks_equals_one_process(name, ems, tmp
     log2, log1 = open(tmp_path / "rank0" / "scSplit.log").read(), open(solo_dir / "scSplit.log").read()
     assert log2.count("Model Log-Likelihood = ") == log1.count("Model Log-Likelihood = ") == ems
     assert [l for l in log2.splitlines() if l.startswith("Model Log")] == [l for l in log1.splitlines() if l.startswith("Model Log")]
+
+
+def test_trim_loops_ahead_of_the_clustering_keep_the_reference_stream(tmp_path, monkeypatch):
+    """models._initialise_all runs the trimming loops of all restarts before any block is clustered.  Same labels and the
+    same final `np.random` state as the reference's alternating order (trim, cluster, trim, cluster, ...: scSplit:473-477
+    with 106-135) -- also when a clustering step itself draws from `np.random` (PCA's randomised solver would), which must
+    send the later restarts back to the alternating order."""
+    import pandas as pd
+    from scsplit_b200 import initialiser, models as M
+    g = load_golden("k4_dnone")
+    ref, alt, K = g["ref"], g["alt"], g["K"]
+    barcodes = ["BC%05d-1" % c for c in range(ref.shape[1])]
+    mtx = [ref, alt, pd.Index(["1:%d" % (1000 + v) for v in range(ref.shape[0])]), pd.Index(barcodes)]
+    eng = _OracleEngine(ref, alt)
+    monkeypatch.setattr(M, "get_engine", lambda base_calls_mtx, device=0: eng)
+    real_labels = initialiser.initial_labels
+    for draws_in in ((), (1,), (0, 3)):                       # restarts whose clustering consumes random numbers
+        calls = []
+
+        def noisy(*a, **k):
+            if len(calls) in draws_in:
+                np.random.random(3)
+            calls.append(1)
+            return real_labels(*a, **k)
+
+        monkeypatch.setattr(initialiser, "initial_labels", noisy)
+        np.random.seed(99)
+        want = [M._initialise(eng, mtx, barcodes, K, str(tmp_path)) for _ in range(5)]      # the alternating order
+        want_state = np.random.get_state()
+        del calls[:]
+        np.random.seed(99)
+        model, labels, initial = M._initialise_all(eng, mtx, barcodes, K, str(tmp_path), 5, 0)
+        assert M._same_rng_state(np.random.get_state(), want_state), draws_in
+        for i in range(5):
+            assert np.array_equal(labels[i], want[i][0]) and initial[i] == want[i][1], (draws_in, i)
+        assert np.array_equal(model._labels, want[4][0]) and model.initial == want[4][1]
+    log = open(tmp_path / "scSplit.log").read()
+    assert log.count("Repeat 5 of 5 in demultiplexing") == 3 and log.count("Building model... ") == 15
