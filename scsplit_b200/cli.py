@@ -128,19 +128,6 @@ def write_outputs(model, num, doublets, out):
 
 
 def run(argv):
-    """`scSplit run` (scSplit:504-600).  While scikit-learn's modules load in a helper thread (_preload_sklearn) the main
-    thread parses the CSVs, uploads them and runs the restarts' trimming loops -- thousands of short numpy / library
-    calls, each of which gives the interpreter lock away and would, at CPython's default 5 ms switch interval, wait that
-    long to get it back from the importing thread.  The interval is shortened for the duration of the run."""
-    interval = sys.getswitchinterval()
-    sys.setswitchinterval(min(interval, float(os.environ.get('SCSPLIT_SWITCH_INTERVAL', '0.0002'))))
-    try:
-        return _run(argv)
-    finally:
-        sys.setswitchinterval(interval)
-
-
-def _run(argv):
     parser = argparse.ArgumentParser(prog='scSplit run', description='Demultiplex the scRNA-Seq using REF/ALT count matrices')
     parser.add_argument('-r', '--ref', required=True, help='REF count CSV input')
     parser.add_argument('-a', '--alt', required=True, help='ALT count CSV input')
