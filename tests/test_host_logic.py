@@ -314,3 +314,47 @@ def test_csv_parser_block_path_on_random_files(tmp_path):
     open(str(tmp_path / "big.csv"), "w").write("SNV,a,b\n1:5,4294967297,0\n")
     with pytest.raises(Exception):
         cli.read_count_csv(str(tmp_path / "big.csv"))
+
+
+def test_write_outputs_equals_the_pandas_writers(tmp_path):
+    """cli.write_outputs against the reference's own writer calls (scSplit:581-600, restated with pandas here): the five
+    result files byte for byte, with and without a doublet cluster, including an empty dist_matrix."""
+    from scsplit_b200 import cli
+    rng = np.random.default_rng(8)
+    V, N, K = 400, 300, 5
+    snv = ["%d:%d" % (1 + v % 22, 1000 + v) for v in range(V)]
+    bc = ["BC%05d-1" % c for c in range(N)]
+
+    class Model:
+        pass
+
+    for doublets, dbl in ((-1, 2), (0, -1), (0.1, 0)):
+        m = Model()
+        lab = rng.integers(0, K, N)
+        W = np.full((N, K), 1e-200) * rng.random((N, K))
+        W[np.arange(N), lab] = 1 - rng.integers(0, 9, N) * 2.0 ** -53
+        W[7] = np.nan
+        m.doublet = dbl
+        m.P_s_c = pd.DataFrame(W, index=bc, columns=range(K))
+        m.reassigned = [sorted(np.asarray(bc, dtype=object)[lab == k].tolist()) for k in range(K)]
+        cols = [k for k in range(K) if k != dbl]
+        pa = pd.DataFrame(rng.choice([0.0, 1.0, np.nan], size=(V, len(cols)), p=[0.5, 0.4, 0.1]), index=snv, columns=cols)
+        m.pa_matrix = pa
+        m.dist_variants = list(rng.choice(snv, 4, replace=False)) if doublets != 0 else []
+        m.dist_matrix = pa.reindex(m.dist_variants)
+        got_dir, want_dir = tmp_path / ("got%s" % dbl), tmp_path / ("want%s" % dbl)
+        got_dir.mkdir()
+        want_dir.mkdir()
+        cli.write_outputs(m, K, doublets, str(got_dir))
+        frames = [pd.DataFrame({"Barcode": m.reassigned[n], "Cluster": "SNG-" + str(n)}) for n in range(K) if n != dbl]
+        if doublets != 0:
+            frames.append(pd.DataFrame({"Barcode": m.reassigned[dbl], "Cluster": "DBL-" + str(dbl)}))
+        pd.concat(frames).to_csv(want_dir / "scSplit_result.csv", sep="\t", index=False)
+        m.P_s_c.to_csv(want_dir / "scSplit_P_s_c.csv")
+        with open(want_dir / "scSplit_dist_variants.txt", "w") as f:
+            for item in m.dist_variants:
+                f.write(str(item) + "\n")
+        m.dist_matrix.to_csv(want_dir / "scSplit_dist_matrix.csv", float_format="%.0f")
+        m.pa_matrix.to_csv(want_dir / "scSplit_PA_matrix.csv", float_format="%.0f")
+        for fn in ("scSplit_result.csv", "scSplit_P_s_c.csv", "scSplit_dist_variants.txt", "scSplit_dist_matrix.csv", "scSplit_PA_matrix.csv"):
+            assert open(got_dir / fn, "rb").read() == open(want_dir / fn, "rb").read(), (fn, doublets)
