@@ -491,7 +491,7 @@ def run_cuda_arm(args):
             with contextlib.redirect_stdout(io.StringIO()):          # ("Repeat n was chosen." belongs to the CLI, not to this line)
                 r = mod.run(argparse.Namespace(workload=args.workload, ems=30, seed=2003, keep=None))
             extras["cli_e2e"] = {k: r[k] for k in ("workload", "wall_s", "phases_s", "em_iterations", "csv_mb", "assigned_cells", "agreement_with_truth")}
-            extras["cli_e2e"]["reference"] = "profiles/r02_ref_cli_c3.json: the reference CLI took 1099 s for the same CSVs with -e 2 (this CLI: 1.3 s, identical partition, profiles/r02_cli_e2e_c3_e2.json); with -e 30 it was not run (~70 min estimated, BASELINE.md)"
+            extras["cli_e2e"]["reference"] = "the reference CLI on the same CSVs (one core of the build container): 1099 s with -e 2 (profiles/r02_ref_cli_c3.json; this CLI 1.3 s, identical partition, profiles/r02_cli_e2e_c3_e2.json) and 2443 s with -e 8 (profiles/r02_ref_cli_c3_e8.json; same optimum, LL -11323037.636696128, same cluster sizes); with -e 30 it was not run (~7400 s extrapolated from those two: 224 s per restart + 650 s)"
             if os.path.exists("scSplit_dist_variants.txt"):
                 os.remove("scSplit_dist_variants.txt")
         except Exception as exc:
