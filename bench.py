@@ -492,6 +492,10 @@ def run_cuda_arm(args):
                 r = mod.run(argparse.Namespace(workload=args.workload, ems=30, seed=2003, keep=None))
             extras["cli_e2e"] = {k: r[k] for k in ("workload", "wall_s", "phases_s", "em_iterations", "csv_mb", "assigned_cells", "agreement_with_truth")}
             extras["cli_e2e"]["reference"] = "the reference CLI on the same CSVs (one core of the build container): 1099 s with -e 2 (profiles/r02_ref_cli_c3.json; this CLI 1.3 s, identical partition, profiles/r02_cli_e2e_c3_e2.json) and 2443 s with -e 8 (profiles/r02_ref_cli_c3_e8.json; same optimum, LL -11323037.636696128, same cluster sizes); with -e 30 it was not run (~7400 s extrapolated from those two: 224 s per restart + 650 s)"
+            if "reference_wall_s" in r:      # tests/golden/cli_<workload>_e30.npz: the reference CLI's own -e 30 run on the same CSVs and seed
+                for k in ("reference_wall_s", "speedup_vs_reference_cli", "reference_assigned_cells", "cells_assigned_by_both", "agreement_with_reference"):
+                    extras["cli_e2e"][k] = r[k]
+                extras["cli_e2e"]["reference"] = "the reference CLI on the same CSVs and seed, -e 30, one core of the build container (oracle/make_c3_cli_reference.py -e 30, profiles/r02_ref_cli_c3_e30.json): reference_wall_s; with -e 2 1099 s, with -e 8 2443 s (profiles/r02_ref_cli_c3.json, _e8.json)"
             if os.path.exists("scSplit_dist_variants.txt"):
                 os.remove("scSplit_dist_variants.txt")
         except Exception as exc:

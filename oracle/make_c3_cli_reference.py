@@ -4,6 +4,7 @@ core), on the synthetic CSVs of scsplit_b200.synth, and records the wall time, t
 
     python oracle/make_c3_cli_reference.py [-e 2]   ->   profiles/r02_ref_cli_c3.json, tests/golden/cli_c3_e<E>.npz
     python oracle/make_c3_cli_reference.py -e 8     ->   profiles/r02_ref_cli_c3_e8.json (timing record only, no golden)
+    python oracle/make_c3_cli_reference.py -e 30    ->   profiles/r02_ref_cli_c3_e30.json, tests/golden/cli_c3_e30.npz (about two hours)
 
 The same CSVs, seed and -e go through this repo's CLI in tools/cli_e2e.py --workload c3 -e <E> --seed 2003."""
 import json, os, re, shutil, sys, tempfile, time, warnings
@@ -34,7 +35,7 @@ def main():
                "log_tail": log.strip().split("\n")[-3:], "host_cores_used": 1, "csv_mb": os.path.getsize(rp) / 1e6}
         with open(os.path.join(ROOT, "profiles", "r02_ref_cli_c3.json" if ems == 2 else "r02_ref_cli_c3_e%d.json" % ems), "w") as f:
             json.dump(out, f)
-        if ems == 2:
+        if ems in (2, 30):
             np.savez_compressed(os.path.join(ROOT, "tests", "golden", "cli_c3_e%d.npz" % ems),
                                 result_barcode=np.array(res["Barcode"].tolist(), dtype=str), result_cluster=np.array(res["Cluster"].tolist(), dtype=str),
                                 wall_s=np.float64(wall), em_iterations=np.int64(log.count("E-M Iteration ")), seed=np.int64(2003), ems=np.int64(ems))
