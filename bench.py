@@ -495,7 +495,7 @@ def run_cuda_arm(args):
             if "reference_wall_s" in r:      # tests/golden/cli_<workload>_e30.npz: the reference CLI's own -e 30 run on the same CSVs and seed
                 for k in ("reference_wall_s", "speedup_vs_reference_cli", "reference_assigned_cells", "cells_assigned_by_both", "agreement_with_reference"):
                     extras["cli_e2e"][k] = r[k]
-                extras["cli_e2e"]["reference"] = "the reference CLI on the same CSVs and seed, -e 30, one core of the build container (oracle/make_c3_cli_reference.py -e 30, profiles/r02_ref_cli_c3_e30.json): reference_wall_s; with -e 2 1099 s, with -e 8 2443 s (profiles/r02_ref_cli_c3.json, _e8.json)"
+                extras["cli_e2e"]["reference"] = "the reference CLI on the same CSVs and seed, -e 30, one core of the build container (oracle/make_c3_cli_reference.py -e 30, profiles/r02_ref_cli_c3_e30.json): 8254 s = `reference_wall_s` of this object, partition in tests/golden/cli_c3_e30.npz; with -e 2 it took 1099 s, with -e 8 2443 s (profiles/r02_ref_cli_c3.json, _e8.json)"
             if os.path.exists("scSplit_dist_variants.txt"):
                 os.remove("scSplit_dist_variants.txt")
         except Exception as exc:
